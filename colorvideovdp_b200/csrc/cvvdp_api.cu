@@ -1,0 +1,908 @@
+// cvvdp_api.cu -- host side of libcvvdp_b200.so: context, per-clip planning, kernel launches and the
+// host-buffer streaming path behind the C ABI declared in include/cvvdp_b200.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "cvvdp_kernels.cuh"
+
+using namespace cvvdp;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct LevelBuf {
+    int h = 0, w = 0;
+    float4 *g = nullptr;        // [B*nb*2][h*w]
+    float *partials = nullptr;  // [B*nb][tiles][4]
+    float *hm = nullptr;        // [nb][h*w] (heat map only)
+    float4 *lut = nullptr;      // [32]
+    int tiles_x = 0, tiles_y = 0;
+    int do_blur = 0;
+};
+
+struct Staging {
+    void *buf[2] = {nullptr, nullptr};  // test, ref
+    size_t bytes = 0;
+    cudaEvent_t copied = nullptr, consumed = nullptr;
+};
+
+}  // namespace
+
+struct cvvdp_b200_ctx {
+    int device = 0;
+    cvvdp_b200_params P;
+    cvvdp_b200_csf_lut lut;
+    cvvdp_b200_display disp;
+    bool have_display = false, planned = false;
+    cvvdp_b200_job job;
+    cvvdp_b200_plan_info info;
+    std::vector<LevelBuf> lv;
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    float blur_kern[2 * CVVDP_BHALO + 1];
+    int blur_pad = 0;
+    int max_smem_optin = 0;
+    cudaStream_t copy_stream = nullptr, work_stream = nullptr;
+    Staging stage[2];
+    float *q_dev = nullptr;       // for process_host / pool
+    size_t q_dev_bytes = 0;
+    void *hm_dev = nullptr;
+    size_t hm_dev_bytes = 0;
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(cvvdp_b200_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU_CHECK(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, CVVDP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                        \
+    } while (0)
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void free_plan(cvvdp_b200_ctx *ctx) {
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr;
+    ctx->arena_bytes = 0;
+    ctx->lv.clear();
+    for (auto &s : ctx->stage) {
+        for (auto &b : s.buf) {
+            if (b) cudaFree(b);
+            b = nullptr;
+        }
+        s.bytes = 0;
+    }
+    ctx->planned = false;
+}
+
+// ---- host restatements of the per-clip constants -------------------------------------------------
+
+// lpyr_dec.py:18-52 (+ cvvdp_metric.py:685-686)
+int band_setup(int W, int H, double ppd, cvvdp_b200_plan_info *info) {
+    const int max_levels = (int)floor(log2((double)std::min(H, W))) - 1;
+    int max_band = max_levels;
+    for (int k = 0; k < 15; ++k) {
+        const double band = (k == 0 ? 1.0 : 0.3228 * pow(2.0, -(double)(k - 1))) * ppd / 2.0;
+        if (band <= 0.2) {
+            max_band = k;
+            break;
+        }
+    }
+    int height = std::max(0, std::min(max_band + 1, max_levels));
+    if (height + 1 > CVVDP_MAX_BANDS) height = CVVDP_MAX_BANDS - 1;
+    info->n_bands = height + 1;
+    int h = H, w = W;
+    for (int i = 0; i <= height; ++i) {
+        info->rho_band[i] = (float)((i == 0 ? 1.0 : 0.3228 * pow(2.0, -(double)(i - 1))) * ppd / 2.0);
+        info->band_height[i] = h;
+        info->band_width[i] = w;
+        h = (h + 1) / 2;
+        w = (w + 1) / 2;
+    }
+    info->rho_band[height] = 0.1f;
+    return height + 1;
+}
+
+// cvvdp_metric.py:1057-1092; irfft(n=N) + fftshift restated as a direct inverse real DFT (N is odd).
+int temporal_filters(const cvvdp_b200_params &P, double fps, cvvdp_b200_plan_info *info) {
+    const int N = (int)(ceil(0.250 * fps / 2.0) * 2.0) + 1;
+    if (N > CVVDP_MAX_FILTER_LEN) return -1;
+    const int No = N / 2 + 1;
+    const double pi = 3.14159265358979323846;
+    for (int c = 0; c < 4; ++c) {
+        std::vector<double> R(No);
+        for (int k = 0; k < No; ++k) {
+            const double om = (double)(float)((fps / 2.0) * k / (double)(No - 1 > 0 ? No - 1 : 1));
+            if (c < 3) R[k] = exp(-pow(om, (double)P.beta_tf[c]) / (double)P.sigma_tf[c]);
+            else {
+                const double d = pow(om, (double)P.beta_tf[3]) - pow(5.0, (double)P.beta_tf[3]);
+                R[k] = exp(-(d * d) / (double)P.sigma_tf[3]);
+            }
+        }
+        for (int t = 0; t < N; ++t) {
+            double x = R[0];
+            for (int k = 1; k < No; ++k) x += 2.0 * R[k] * cos(2.0 * pi * k * t / (double)N);
+            x /= (double)N;
+            info->filters[c][(t + N / 2) % N] = (float)x;  // fftshift
+        }
+    }
+    return N;
+}
+
+// csf.py:38-46 + interp.py:152-178 in fp32
+void csf_row(const cvvdp_b200_csf_lut &lut, float rho, int ch, float *row) {
+    float log_rho[CVVDP_CSF_LUT_N];
+    for (int i = 0; i < CVVDP_CSF_LUT_N; ++i) log_rho[i] = log10f(lut.rho[i]);
+    const float x = log10f(rho);
+    int idx = 0;
+    while (idx < CVVDP_CSF_LUT_N && log_rho[idx] < x) ++idx;  // searchsorted(side='left')
+    idx = std::max(0, std::min(idx - 1, CVVDP_CSF_LUT_N - 2));
+    const float x0 = log_rho[idx], x1 = log_rho[idx + 1];
+    for (int l = 0; l < CVVDP_CSF_LUT_N; ++l) {
+        const float y0 = lut.logS[ch][l][idx], y1 = lut.logS[ch][l][idx + 1];
+        const float slope = (y1 - y0) / (x1 - x0);
+        row[l] = y0 + slope * (x - x0);
+    }
+}
+
+void to_display_dev(const cvvdp_b200_display &d, DisplayDev *o, int colorspace = CVVDP_CS_DKLD65) {
+    o->eotf = d.eotf;
+    o->gamma = d.gamma;
+    o->Ypeak = d.Y_peak;
+    const double Yblack = (double)d.Y_peak / (double)d.contrast;                 // display_model.py:374
+    const double Yrefl = (double)d.E_ambient / 3.14159265358979323846 * d.k_refl;  // l.373
+    o->Yblack = (float)Yblack;
+    o->Yrefl = (float)Yrefl;
+    o->exposure = d.exposure;
+    o->lin_lo = (float)std::max(0.005, Yblack);
+    // display_model.py:17-25, 255-256: (LMS2006_to_DKLd65 @ XYZ_to_LMS2006) @ rgb2xyz in fp32
+    const float A[9] = {1.f, 1.f, 0.f, 1.f, -2.311130179947035f, 0.f, -1.f, -1.f, 50.977571328718781f};
+    const float Bm[9] = {0.187596268556126f, 0.585168649077728f, -0.026384263306304f,
+                         -0.133397430663221f, 0.405505777260049f, 0.034502127690364f,
+                         0.000244379021663f, -0.000542995890619f, 0.019406849066323f};
+    float AB[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            float acc = 0.f;
+            for (int k = 0; k < 3; ++k) acc = acc + A[i * 3 + k] * Bm[k * 3 + j];
+            AB[i * 3 + j] = acc;
+        }
+    const float I3[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    const float *lhs = colorspace == CVVDP_CS_DKLD65 ? AB : (colorspace == CVVDP_CS_LMS2006 ? Bm : I3);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            if (colorspace == CVVDP_CS_RGB_LINEAR) {
+                o->M[i * 3 + j] = I3[i * 3 + j];
+                continue;
+            }
+            if (colorspace == CVVDP_CS_XYZ) {
+                o->M[i * 3 + j] = d.rgb2xyz[i * 3 + j];
+                continue;
+            }
+            float acc = 0.f;
+            for (int k = 0; k < 3; ++k) acc = acc + lhs[i * 3 + k] * d.rgb2xyz[k * 3 + j];
+            o->M[i * 3 + j] = acc;
+        }
+}
+
+size_t dtype_size(int dtype) {
+    switch (dtype) {
+        case CVVDP_DTYPE_U8: return 1;
+        case CVVDP_DTYPE_U16:
+        case CVVDP_DTYPE_F16: return 2;
+        default: return 4;
+    }
+}
+
+// frames (clip indices) the temporal stage reads to produce outputs [f0, f1)
+void needed_frames(const cvvdp_b200_ctx *ctx, int f0, int f1, int *lo, int *hi) {
+    const int fl = ctx->info.filter_len, F = ctx->job.n_frames;
+    int mn = f1 - 1, mx = f1 - 1;
+    for (int t = f0 - (fl - 1); t < f1; ++t) {
+        int s = t;
+        if (s < 0) {
+            if (ctx->job.padding == CVVDP_PAD_REPLICATE) s = 0;
+            else {
+                const int m = F - 1, a = -s - 1;
+                if (((a / m) & 1) == 0) s = (a % m) + 1;
+                else {
+                    s = t % m;
+                    if (s < 0) s += m;
+                }
+            }
+        }
+        mn = std::min(mn, s);
+        mx = std::max(mx, s);
+    }
+    *lo = mn;
+    *hi = mx + 1;
+}
+
+int check_clip(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *c, int lo, int hi, const char *name) {
+    if (!c || !c->data) return fail(ctx, CVVDP_ERR_INVALID, "%s clip is null", name);
+    if (lo < c->frame0 || hi > c->frame0 + c->n_frames)
+        return fail(ctx, CVVDP_ERR_INVALID, "%s view holds frames [%d,%d) but frames [%d,%d) are needed", name,
+                    c->frame0, c->frame0 + c->n_frames, lo, hi);
+    return CVVDP_OK;
+}
+
+ClipView to_view(const cvvdp_b200_clip *c) {
+    ClipView v;
+    v.data = c->data;
+    for (int i = 0; i < 5; ++i) v.s[i] = c->stride[i];
+    v.frame0 = c->frame0;
+    v.n_frames = c->n_frames;
+    return v;
+}
+
+// One block of frames [f0, f1) (f1 - f0 <= block_frames), inputs resident on the device.
+int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref, int f0, int f1,
+              float *q_dev, void *hm_dev, cudaStream_t st) {
+    const cvvdp_b200_job &job = ctx->job;
+    const cvvdp_b200_plan_info &info = ctx->info;
+    const cvvdp_b200_params &P = ctx->P;
+    const int n = f1 - f0, L = info.n_bands, B = job.batch;
+    const int pairs = B * n;
+    const bool do_hm = job.heatmap == CVVDP_HEATMAP_RAW;
+    const float eps = 1e-5f;
+
+    // ---- temporal stage ----
+    {
+        TemporalArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.clip[0] = to_view(test);
+        ta.clip[1] = to_view(ref);
+        // frames that already are DKLd65 (plugin sources) pass through with an identity matrix
+        to_display_dev(ctx->disp, &ta.dd, ctx->disp.eotf == CVVDP_EOTF_NONE ? CVVDP_CS_RGB_LINEAR : CVVDP_CS_DKLD65);
+        ta.dtype = job.dtype;
+        ta.cin = job.in_channels;
+        ta.B = B;
+        ta.H = job.height;
+        ta.W = job.width;
+        ta.F_total = job.n_frames;
+        ta.f0 = f0;
+        ta.f1 = f1;
+        ta.fl = info.filter_len;
+        ta.padding = job.padding;
+        ta.out = ctx->lv[0].g;
+        if (job.n_frames == 1) {  // image: R = DKL, no transient channel (cvvdp_metric.py:462-465)
+            ta.taps[0][0] = ta.taps[1][0] = ta.taps[2][0] = 1.f;
+            ta.taps[3][0] = 0.f;
+        } else {
+            for (int c = 0; c < 4; ++c)
+                for (int k = 0; k < info.filter_len; ++k) ta.taps[c][k] = info.filters[c][info.filter_len - 1 - k];
+        }
+        const long long npix = (long long)job.height * job.width;
+        dim3 grid((unsigned)((npix + CVVDP_TEMPORAL_THREADS - 1) / CVVDP_TEMPORAL_THREADS), (unsigned)(B * 2));
+        const size_t smem = (size_t)info.filter_len * 3 * CVVDP_TEMPORAL_THREADS * sizeof(float);
+        auto kfn = k_temporal;
+        CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
+        ctx->launches++;
+    }
+    // ---- Gaussian pyramid ----
+    for (int i = 0; i + 1 < L; ++i) {
+        ReduceArgs ra;
+        ra.in = ctx->lv[i].g;
+        ra.out = ctx->lv[i + 1].g;
+        ra.h = ctx->lv[i].h;
+        ra.w = ctx->lv[i].w;
+        ra.hc = ctx->lv[i + 1].h;
+        ra.wc = ctx->lv[i + 1].w;
+        dim3 grid((ra.wc + CVVDP_RTX - 1) / CVVDP_RTX, (ra.hc + CVVDP_RTY - 1) / CVVDP_RTY, pairs * 2);
+        auto kfn = k_reduce;
+        CVVDP_LAUNCH(kfn, grid, dim3(256), 0, st, ra);
+        ctx->launches++;
+    }
+    // ---- bands ----
+    const bool is_image = job.n_frames == 1;
+    const float ch_w[4] = {1.f, P.ch_chrom_w, P.ch_chrom_w, is_image ? 0.f : P.ch_trans_w};
+    const float t_int = is_image ? P.image_int : 1.f;
+    for (int i = 0; i + 1 < L; ++i) {
+        BandArgs ba;
+        memset(&ba, 0, sizeof(ba));
+        const LevelBuf &lv = ctx->lv[i];
+        ba.fine = lv.g;
+        ba.coarse = ctx->lv[i + 1].g;
+        ba.lut = lv.lut;
+        ba.partials = lv.partials;
+        ba.hm = do_hm ? lv.hm : nullptr;
+        ba.h = lv.h;
+        ba.w = lv.w;
+        ba.hc = ctx->lv[i + 1].h;
+        ba.wc = ctx->lv[i + 1].w;
+        ba.do_blur = lv.do_blur;
+        ba.mul = (i == 0) ? 1.f : 2.f;
+        {
+            const float x0 = log10f(ctx->lut.L_bkg[0]), x1 = log10f(ctx->lut.L_bkg[CVVDP_CSF_LUT_N - 1]);
+            const double sc = (double)(CVVDP_CSF_LUT_N - 1) / ((double)x1 - (double)x0);
+            ba.lut_a = (float)(log10(2.0) * sc);
+            ba.lut_b = (float)(-(double)x0 * sc);
+        }
+        for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) ba.kern[k] = ctx->blur_kern[k];
+        ba.mc = powf(10.f, P.mask_c);
+        for (int c = 0; c < 4; ++c) ba.q[c] = P.mask_q[c];
+        ba.p = P.mask_p;
+        for (int k = 0; k < 16; ++k) ba.X[k] = powf(2.f, P.xcm_weights[k]);
+        ba.dmax = powf(10.f, P.d_max);
+        ba.eps = eps;
+        ba.beta = P.beta;
+        for (int c = 0; c < 4; ++c) ba.hm_w[c] = ch_w[c] * t_int;
+        ba.hm_beta = P.beta_tch;
+        ba.hm_scale = (i == 0) ? 1.f : 0.5f;
+        dim3 grid(lv.tiles_x, lv.tiles_y, pairs);
+        auto kfn = k_band;
+        CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_BAND_THREADS), sizeof(BandSmem), st, ba);
+        ctx->launches++;
+    }
+    {
+        BasebandArgs bb;
+        memset(&bb, 0, sizeof(bb));
+        const LevelBuf &lv = ctx->lv[L - 1];
+        bb.g = lv.g;
+        bb.lut = lv.lut;
+        bb.partials = lv.partials;
+        bb.hm = do_hm ? lv.hm : nullptr;
+        bb.npix = lv.h * lv.w;
+        const float x0 = log10f(ctx->lut.L_bkg[0]), x1 = log10f(ctx->lut.L_bkg[CVVDP_CSF_LUT_N - 1]);
+        const double sc = (double)(CVVDP_CSF_LUT_N - 1) / ((double)x1 - (double)x0);
+        bb.lut_a = (float)(log10(2.0) * sc);
+        bb.lut_b = (float)(-(double)x0 * sc);
+        bb.eps = eps;
+        bb.beta = P.beta;
+        for (int c = 0; c < 4; ++c) bb.hm_w[c] = ch_w[c] * t_int * P.baseband_weight[c];
+        bb.hm_beta = P.beta_tch;
+        auto kfn = k_baseband;
+        CVVDP_LAUNCH(kfn, dim3(pairs), dim3(256), 0, st, bb);
+        ctx->launches++;
+    }
+    // ---- spatial pooling epilogue -> Q_per_ch ----
+    {
+        FinalizeArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        for (int i = 0; i < L; ++i) {
+            fa.partials[i] = ctx->lv[i].partials;
+            fa.ntiles[i] = (i == L - 1) ? 1 : ctx->lv[i].tiles_x * ctx->lv[i].tiles_y;
+            fa.npix[i] = ctx->lv[i].h * ctx->lv[i].w;
+        }
+        fa.L = L;
+        fa.C = info.n_channels;
+        fa.B = B;
+        fa.n = n;
+        fa.f_off = f0;
+        fa.F_total = job.n_frames;
+        fa.beta = P.beta;
+        fa.eps = eps;
+        fa.Q = q_dev;
+        const int warps = pairs * L;
+        auto kfn = k_finalize;
+        CVVDP_LAUNCH(kfn, dim3((warps * 32 + 127) / 128), dim3(128), 0, st, fa);
+        ctx->launches++;
+    }
+    // ---- heat map ----
+    if (do_hm) {
+        for (int i = L - 2; i >= 0; --i) {
+            ExpandAddArgs ea;
+            ea.coarse = ctx->lv[i + 1].hm;
+            ea.fine = ctx->lv[i].hm;
+            ea.h = ctx->lv[i].h;
+            ea.w = ctx->lv[i].w;
+            ea.hc = ctx->lv[i + 1].h;
+            ea.wc = ctx->lv[i + 1].w;
+            const long long npix = (long long)ea.h * ea.w;
+            auto kfn = k_expand_add;
+            CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), n), dim3(256), 0, st, ea);
+            ctx->launches++;
+        }
+        HeatmapOutArgs ha;
+        ha.img = ctx->lv[0].hm;
+        ha.out = (unsigned short *)hm_dev;
+        ha.npix = (long long)job.height * job.width;
+        ha.f_off = f0;
+        ha.jod_a = P.jod_a;
+        ha.jod_exp = P.jod_exp;
+        auto kfn = k_heatmap_out;
+        CVVDP_LAUNCH(kfn, dim3((unsigned)((ha.npix + 255) / 256), n), dim3(256), 0, st, ha);
+        ctx->launches++;
+    }
+    CU_CHECK(ctx, cudaGetLastError());
+    return CVVDP_OK;
+}
+
+int fill_pool_args(const cvvdp_b200_ctx *ctx, PoolArgs *pa, int B, int C, int F, int L) {
+    const cvvdp_b200_params &P = ctx->P;
+    memset(pa, 0, sizeof(*pa));
+    pa->B = B;
+    pa->C = C;
+    pa->F = F;
+    pa->L = L;
+    const float w[4] = {1.f, P.ch_chrom_w, P.ch_chrom_w, P.ch_trans_w};
+    for (int c = 0; c < 4; ++c) {
+        pa->ch_w[c] = w[c];
+        pa->bb_w[c] = P.baseband_weight[c];
+    }
+    pa->beta_sch = P.beta_sch;
+    pa->beta_tch = P.beta_tch;
+    pa->beta_t = P.beta_t;
+    pa->image_int = P.image_int;
+    pa->jod_a = P.jod_a;
+    pa->jod_exp = P.jod_exp;
+    pa->eps = 1e-5f;
+    return CVVDP_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int cvvdp_b200_abi_version(void) { return CVVDP_B200_ABI_VERSION; }
+
+const char *cvvdp_b200_last_error(const cvvdp_b200_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut *lut, int device,
+                      cvvdp_b200_ctx **out) {
+    if (!params || !lut || !out) return fail(nullptr, CVVDP_ERR_INVALID, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, CVVDP_ERR_CUDA, "no CUDA device available (%s): the B200 path has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, CVVDP_ERR_INVALID, "device %d out of range", device);
+    if (!(params->pu_dilate == 0.f || params->pu_dilate == 3.f))
+        return fail(nullptr, CVVDP_ERR_UNSUPPORTED, "pu_dilate must be 0 or 3 (got %g)", params->pu_dilate);
+    cvvdp_b200_ctx *ctx = new cvvdp_b200_ctx();
+    ctx->device = device;
+    ctx->P = *params;
+    ctx->lut = *lut;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, CVVDP_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    }
+    cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    // torchvision _get_gaussian_kernel1d(kernel_size = 4*sigma+1, sigma), cvvdp_metric.py:158
+    ctx->blur_pad = (int)(params->pu_dilate * 2);
+    if (ctx->blur_pad > 0) {
+        const int ks = 2 * ctx->blur_pad + 1;
+        float pdf[2 * CVVDP_BHALO + 1], sum = 0.f;
+        for (int i = 0; i < ks; ++i) {
+            const float x = -(float)ctx->blur_pad + (float)i;
+            pdf[i] = expf(-0.5f * (x / params->pu_dilate) * (x / params->pu_dilate));
+            sum += pdf[i];
+        }
+        for (int i = 0; i < ks; ++i) ctx->blur_kern[i] = pdf[i] / sum;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->work_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, CVVDP_ERR_CUDA, "stream creation failed");
+    }
+    for (auto &s : ctx->stage) {
+        cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming);
+    }
+    auto kb = k_band;
+    cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BandSmem));
+    auto kt = k_temporal;
+    cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         std::min(ctx->max_smem_optin, 227 * 1024));
+    *out = ctx;
+    return CVVDP_OK;
+}
+
+void cvvdp_b200_destroy(cvvdp_b200_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_plan(ctx);
+    if (ctx->q_dev) cudaFree(ctx->q_dev);
+    if (ctx->hm_dev) cudaFree(ctx->hm_dev);
+    for (auto &s : ctx->stage) {
+        if (s.copied) cudaEventDestroy(s.copied);
+        if (s.consumed) cudaEventDestroy(s.consumed);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->work_stream) cudaStreamDestroy(ctx->work_stream);
+    delete ctx;
+}
+
+int cvvdp_b200_set_display(cvvdp_b200_ctx *ctx, const cvvdp_b200_display *d) {
+    if (!ctx || !d) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    if (d->eotf < CVVDP_EOTF_SRGB || d->eotf > CVVDP_EOTF_NONE) return fail(ctx, CVVDP_ERR_INVALID, "unknown EOTF id %d", d->eotf);
+    if (!(d->ppd > 0.f)) return fail(ctx, CVVDP_ERR_INVALID, "ppd must be positive");
+    ctx->disp = *d;
+    ctx->have_display = true;
+    ctx->planned = false;  // cvvdp_metric.py:264 (self.lpyr = None)
+    return CVVDP_OK;
+}
+
+int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_plan_info *info_out) {
+    if (!ctx || !job) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    if (!ctx->have_display) return fail(ctx, CVVDP_ERR_STATE, "set_display must be called before plan");
+    if (job->batch < 1 || job->height < 4 || job->width < 4 || job->n_frames < 1)
+        return fail(ctx, CVVDP_ERR_INVALID, "bad job shape B=%d H=%d W=%d F=%d (H, W >= 4)", job->batch, job->height,
+                    job->width, job->n_frames);
+    if (job->in_channels != 1 && job->in_channels != 3)
+        return fail(ctx, CVVDP_ERR_INVALID, "The content must have either 1 or 3 color channels.");
+    if (job->n_frames > 1 && !(job->fps > 0.f))
+        return fail(ctx, CVVDP_ERR_INVALID, "When passing video sequences, you must set frames_per_second parameter");
+    if (job->dtype < CVVDP_DTYPE_U8 || job->dtype > CVVDP_DTYPE_F32) return fail(ctx, CVVDP_ERR_INVALID, "unknown dtype %d", job->dtype);
+    if (job->padding != CVVDP_PAD_REPLICATE && job->padding != CVVDP_PAD_SYMMETRIC)
+        return fail(ctx, CVVDP_ERR_INVALID, "Unknown padding method");
+    if (job->heatmap != CVVDP_HEATMAP_NONE && job->batch > 1)
+        return fail(ctx, CVVDP_ERR_INVALID, "Heatmaps not supported when batches are used");  // cvvdp_metric.py:311-312
+    if (ctx->disp.eotf == CVVDP_EOTF_HLG && job->in_channels != 3)
+        return fail(ctx, CVVDP_ERR_UNSUPPORTED, "HLG needs three colour channels");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    CU_CHECK(ctx, cudaDeviceSynchronize());
+    free_plan(ctx);
+    ctx->job = *job;
+    cvvdp_b200_plan_info &info = ctx->info;
+    memset(&info, 0, sizeof(info));
+    const int L = band_setup(job->width, job->height, (double)ctx->disp.ppd, &info);
+    info.n_channels = job->n_frames == 1 ? 3 : 4;
+    if (job->n_frames == 1) info.filter_len = 1;
+    else {
+        const int fl = temporal_filters(ctx->P, (double)job->fps, &info);
+        if (fl < 0) return fail(ctx, CVVDP_ERR_UNSUPPORTED, "temporal filter longer than %d taps", CVVDP_MAX_FILTER_LEN);
+        info.filter_len = fl;
+    }
+    if ((size_t)info.filter_len * 3 * CVVDP_TEMPORAL_THREADS * sizeof(float) > (size_t)std::min(ctx->max_smem_optin, 227 * 1024))
+        return fail(ctx, CVVDP_ERR_UNSUPPORTED, "temporal filter of %d taps does not fit in shared memory", info.filter_len);
+
+    // workspace per frame of a block (all batch items)
+    const size_t B = (size_t)job->batch;
+    const bool do_hm = job->heatmap == CVVDP_HEATMAP_RAW;
+    size_t per_frame = 0;
+    for (int i = 0; i < L; ++i) {
+        const size_t npix = (size_t)info.band_height[i] * info.band_width[i];
+        per_frame += align_up(B * 2 * npix * sizeof(float4), 256);
+        const size_t tiles = (i == L - 1) ? 1
+                                          : (size_t)((info.band_width[i] + CVVDP_BTX - 1) / CVVDP_BTX) *
+                                                ((info.band_height[i] + CVVDP_BTY - 1) / CVVDP_BTY);
+        per_frame += align_up(B * tiles * 4 * sizeof(float), 256);
+        if (do_hm) per_frame += align_up(npix * sizeof(float), 256);
+    }
+    size_t limit = job->workspace_limit_bytes > 0 ? (size_t)job->workspace_limit_bytes : (size_t)12 << 30;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) limit = std::min(limit, free_b / 2);
+    int nb = (int)std::min<size_t>(std::max<size_t>(limit / std::max<size_t>(per_frame, 1), 1), 32);
+    if (job->max_block_frames > 0) nb = std::min(nb, job->max_block_frames);
+    nb = std::min(nb, job->n_frames);
+    if ((long long)B * nb * 2 > 65535) nb = std::max(1, (int)(65535 / (B * 2)));
+    info.block_frames = nb;
+
+    // arena layout
+    ctx->lv.resize(L);
+    size_t off = 0;
+    std::vector<size_t> off_g(L), off_p(L), off_h(L), off_l(L);
+    for (int i = 0; i < L; ++i) {
+        LevelBuf &lv = ctx->lv[i];
+        lv.h = info.band_height[i];
+        lv.w = info.band_width[i];
+        lv.tiles_x = (lv.w + CVVDP_BTX - 1) / CVVDP_BTX;
+        lv.tiles_y = (lv.h + CVVDP_BTY - 1) / CVVDP_BTY;
+        lv.do_blur = (ctx->blur_pad > 0 && lv.h > ctx->blur_pad && lv.w > ctx->blur_pad) ? 1 : 0;  // cvvdp_metric.py:965
+        const size_t npix = (size_t)lv.h * lv.w;
+        off_g[i] = off;
+        off += align_up(B * nb * 2 * npix * sizeof(float4), 256);
+        const size_t tiles = (i == L - 1) ? 1 : (size_t)lv.tiles_x * lv.tiles_y;
+        off_p[i] = off;
+        off += align_up(B * nb * tiles * 4 * sizeof(float), 256);
+        off_h[i] = off;
+        if (do_hm) off += align_up((size_t)nb * npix * sizeof(float), 256);
+        off_l[i] = off;
+        off += align_up(CVVDP_CSF_LUT_N * sizeof(float4), 256);
+    }
+    ctx->arena_bytes = off;
+    info.workspace_bytes = (int64_t)off;
+    if (cudaMalloc(&ctx->arena, off) != cudaSuccess) {
+        ctx->arena = nullptr;
+        cudaGetLastError();
+        return fail(ctx, CVVDP_ERR_NOMEM, "cannot allocate %zu bytes of workspace", off);
+    }
+    // per-band CSF rows (csf.py:38-51 + cvvdp_metric.py:705-709), pre-scaled for exp2:
+    //   S * gain = 2^(row * log2(10) + log2(10^(sens_corr/20) * gain));  gain [1,1.45,1,1] only for the
+    //   masked bands (cvvdp_metric.py:835-837), not for the baseband (711-712).
+    const double log2_10 = log2(10.0);
+    const double sens = pow(10.0, (double)ctx->P.sensitivity_correction / 20.0);
+    const double gain[4] = {1.0, 1.45, 1.0, 1.0};
+    for (int i = 0; i < L; ++i) {
+        LevelBuf &lv = ctx->lv[i];
+        char *base = (char *)ctx->arena;
+        lv.g = (float4 *)(base + off_g[i]);
+        lv.partials = (float *)(base + off_p[i]);
+        lv.hm = do_hm ? (float *)(base + off_h[i]) : nullptr;
+        lv.lut = (float4 *)(base + off_l[i]);
+        float rows[4][CVVDP_CSF_LUT_N];
+        for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
+        float packed[CVVDP_CSF_LUT_N][4];
+        for (int l = 0; l < CVVDP_CSF_LUT_N; ++l)
+            for (int c = 0; c < 4; ++c) {
+                const double g = (i == L - 1) ? 1.0 : gain[c];
+                packed[l][c] = (float)((double)rows[c][l] * log2_10 + log2(sens * g));
+            }
+        CU_CHECK(ctx, cudaMemcpy(lv.lut, packed, sizeof(packed), cudaMemcpyHostToDevice));
+    }
+    ctx->planned = true;
+    if (info_out) *info_out = info;
+    return CVVDP_OK;
+}
+
+int cvvdp_b200_process_device(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref,
+                              int frame_begin, int frame_end, float *q_per_ch_dev, void *heatmap_dev, void *stream) {
+    if (!ctx) return CVVDP_ERR_INVALID;
+    if (!ctx->planned) return fail(ctx, CVVDP_ERR_STATE, "plan must be called before process");
+    if (frame_begin < 0 || frame_end > ctx->job.n_frames || frame_begin >= frame_end)
+        return fail(ctx, CVVDP_ERR_INVALID, "bad frame range [%d,%d)", frame_begin, frame_end);
+    if (!q_per_ch_dev) return fail(ctx, CVVDP_ERR_INVALID, "q_per_ch_dev is null");
+    if (ctx->job.heatmap != CVVDP_HEATMAP_NONE && !heatmap_dev) return fail(ctx, CVVDP_ERR_INVALID, "heatmap_dev is null");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    int lo, hi;
+    needed_frames(ctx, frame_begin, frame_end, &lo, &hi);
+    int rc;
+    if ((rc = check_clip(ctx, test, lo, hi, "test")) != CVVDP_OK) return rc;
+    if ((rc = check_clip(ctx, ref, lo, hi, "reference")) != CVVDP_OK) return rc;
+    const int nb = ctx->info.block_frames;
+    for (int f0 = frame_begin; f0 < frame_end; f0 += nb) {
+        const int f1 = std::min(f0 + nb, frame_end);
+        if ((rc = run_block(ctx, test, ref, f0, f1, q_per_ch_dev, heatmap_dev, (cudaStream_t)stream)) != CVVDP_OK) return rc;
+    }
+    return CVVDP_OK;
+}
+
+// ---- host-buffer path ---------------------------------------------------------------------------
+namespace {
+struct HostLayout {
+    // frames are copied per "outer index" (dims whose stride exceeds the frame stride) as contiguous spans
+    int outer_dims[4];
+    int n_outer = 0;
+    long long extent[5];
+    bool ok = false;
+};
+
+HostLayout analyse_layout(const cvvdp_b200_clip *c, const long long extent[5]) {
+    HostLayout hl;
+    for (int i = 0; i < 5; ++i) hl.extent[i] = extent[i];
+    const long long sF = c->stride[2];
+    if (sF <= 0) return hl;
+    // inner dims (stride < sF, extent > 1) must tile [0, sF) densely
+    std::vector<int> inner;
+    for (int d = 0; d < 5; ++d) {
+        if (d == 2 || extent[d] == 1) continue;
+        if (c->stride[d] == 0) continue;  // broadcast dim: nothing to copy per index
+        if (c->stride[d] < sF) inner.push_back(d);
+        else hl.outer_dims[hl.n_outer++] = d;
+    }
+    std::sort(inner.begin(), inner.end(), [&](int a, int b) { return c->stride[a] < c->stride[b]; });
+    long long expect = 1;
+    for (int d : inner) {
+        if (c->stride[d] != expect) return hl;
+        expect *= extent[d];
+    }
+    if (expect != sF) return hl;
+    hl.ok = true;
+    return hl;
+}
+}  // namespace
+
+int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref,
+                            int frame_begin, int frame_end, float *q_per_ch_host, void *heatmap_host) {
+    if (!ctx) return CVVDP_ERR_INVALID;
+    if (!ctx->planned) return fail(ctx, CVVDP_ERR_STATE, "plan must be called before process");
+    if (frame_begin < 0 || frame_end > ctx->job.n_frames || frame_begin >= frame_end)
+        return fail(ctx, CVVDP_ERR_INVALID, "bad frame range [%d,%d)", frame_begin, frame_end);
+    if (!q_per_ch_host) return fail(ctx, CVVDP_ERR_INVALID, "q_per_ch_host is null");
+    const cvvdp_b200_job &job = ctx->job;
+    const bool do_hm = job.heatmap == CVVDP_HEATMAP_RAW;
+    if (do_hm && !heatmap_host) return fail(ctx, CVVDP_ERR_INVALID, "heatmap_host is null");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    int lo, hi, rc;
+    needed_frames(ctx, frame_begin, frame_end, &lo, &hi);
+    if ((rc = check_clip(ctx, test, lo, hi, "test")) != CVVDP_OK) return rc;
+    if ((rc = check_clip(ctx, ref, lo, hi, "reference")) != CVVDP_OK) return rc;
+
+    const long long ext_t[5] = {test->stride[0] ? job.batch : 1, job.in_channels, 0, job.height, job.width};
+    const long long ext_r[5] = {ref->stride[0] ? job.batch : 1, job.in_channels, 0, job.height, job.width};
+    HostLayout hl[2] = {analyse_layout(test, ext_t), analyse_layout(ref, ext_r)};
+    if (!hl[0].ok || !hl[1].ok)
+        return fail(ctx, CVVDP_ERR_UNSUPPORTED,
+                    "host clips must store each frame densely (dims with a stride below the frame stride must tile it)");
+    const cvvdp_b200_clip *clips[2] = {test, ref};
+    const size_t esz = dtype_size(job.dtype);
+    const int nb = ctx->info.block_frames, fl = ctx->info.filter_len;
+    const int cap_frames = nb + fl - 1 + fl;  // block + history (+ symmetric look-ahead of the first block)
+
+    // staging buffers: [outer index][cap_frames][frame]
+    size_t need[2];
+    long long n_outer_idx[2];
+    for (int v = 0; v < 2; ++v) {
+        n_outer_idx[v] = 1;
+        for (int k = 0; k < hl[v].n_outer; ++k) n_outer_idx[v] *= hl[v].extent[hl[v].outer_dims[k]];
+        need[v] = (size_t)n_outer_idx[v] * cap_frames * (size_t)clips[v]->stride[2] * esz;
+    }
+    for (auto &s : ctx->stage) {
+        if (s.bytes < std::max(need[0], need[1])) {
+            for (auto &b : s.buf) {
+                if (b) cudaFree(b);
+                b = nullptr;
+            }
+            s.bytes = std::max(need[0], need[1]);
+            for (auto &b : s.buf)
+                if (cudaMalloc(&b, s.bytes) != cudaSuccess) {
+                    b = nullptr;
+                    s.bytes = 0;
+                    cudaGetLastError();
+                    return fail(ctx, CVVDP_ERR_NOMEM, "cannot allocate staging buffers");
+                }
+        }
+    }
+    const size_t q_bytes = (size_t)job.batch * ctx->info.n_channels * job.n_frames * ctx->info.n_bands * sizeof(float);
+    if (ctx->q_dev_bytes < q_bytes) {
+        if (ctx->q_dev) cudaFree(ctx->q_dev);
+        CU_CHECK(ctx, cudaMalloc(&ctx->q_dev, q_bytes));
+        ctx->q_dev_bytes = q_bytes;
+    }
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->q_dev, 0, q_bytes, ctx->work_stream));
+    const size_t hm_bytes = do_hm ? (size_t)job.n_frames * job.height * job.width * 2 : 0;
+    if (do_hm && ctx->hm_dev_bytes < hm_bytes) {
+        if (ctx->hm_dev) cudaFree(ctx->hm_dev);
+        CU_CHECK(ctx, cudaMalloc(&ctx->hm_dev, hm_bytes));
+        ctx->hm_dev_bytes = hm_bytes;
+    }
+
+    int blk = 0;
+    for (int f0 = frame_begin; f0 < frame_end; f0 += nb, ++blk) {
+        const int f1 = std::min(f0 + nb, frame_end);
+        Staging &sg = ctx->stage[blk & 1];
+        int wlo, whi;
+        needed_frames(ctx, f0, f1, &wlo, &whi);
+        if (whi - wlo > cap_frames) return fail(ctx, CVVDP_ERR_STATE, "internal: staging window too small");
+        if (blk >= 2) CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sg.consumed, 0));
+        cvvdp_b200_clip dev_clip[2];
+        for (int v = 0; v < 2; ++v) {
+            const cvvdp_b200_clip *c = clips[v];
+            const long long sF = c->stride[2];
+            dev_clip[v] = *c;
+            dev_clip[v].data = sg.buf[v];
+            dev_clip[v].frame0 = wlo;
+            dev_clip[v].n_frames = whi - wlo;
+            // device strides: inner dims + frame stride unchanged, outer dims compacted
+            long long ostride = (long long)cap_frames * sF;
+            // outer dims ordered by ascending host stride get ascending device strides
+            int order[4];
+            for (int k = 0; k < hl[v].n_outer; ++k) order[k] = hl[v].outer_dims[k];
+            std::sort(order, order + hl[v].n_outer, [&](int a, int b) { return c->stride[a] < c->stride[b]; });
+            long long dstr[5];
+            for (int d = 0; d < 5; ++d) dstr[d] = c->stride[d];
+            for (int k = 0; k < hl[v].n_outer; ++k) {
+                dstr[order[k]] = ostride;
+                ostride *= hl[v].extent[order[k]];
+            }
+            for (int d = 0; d < 5; ++d) dev_clip[v].stride[d] = dstr[d];
+            // copy one contiguous span of (whi - wlo) frames per outer index
+            long long idx[4] = {0, 0, 0, 0};
+            for (long long oi = 0; oi < n_outer_idx[v]; ++oi) {
+                long long hoff = (long long)(wlo - c->frame0) * sF, doff = 0;
+                for (int k = 0; k < hl[v].n_outer; ++k) {
+                    hoff += idx[k] * c->stride[order[k]];
+                    doff += idx[k] * dstr[order[k]];
+                }
+                CU_CHECK(ctx, cudaMemcpyAsync((char *)sg.buf[v] + doff * esz, (const char *)c->data + hoff * esz,
+                                              (size_t)(whi - wlo) * sF * esz, cudaMemcpyHostToDevice, ctx->copy_stream));
+                for (int k = 0; k < hl[v].n_outer; ++k) {
+                    if (++idx[k] < hl[v].extent[order[k]]) break;
+                    idx[k] = 0;
+                }
+            }
+        }
+        CU_CHECK(ctx, cudaEventRecord(sg.copied, ctx->copy_stream));
+        CU_CHECK(ctx, cudaStreamWaitEvent(ctx->work_stream, sg.copied, 0));
+        if ((rc = run_block(ctx, &dev_clip[0], &dev_clip[1], f0, f1, ctx->q_dev, ctx->hm_dev, ctx->work_stream)) != CVVDP_OK)
+            return rc;
+        CU_CHECK(ctx, cudaEventRecord(sg.consumed, ctx->work_stream));
+    }
+    CU_CHECK(ctx, cudaMemcpyAsync(q_per_ch_host, ctx->q_dev, q_bytes, cudaMemcpyDeviceToHost, ctx->work_stream));
+    if (do_hm) {
+        const size_t fbytes = (size_t)job.height * job.width * 2;
+        CU_CHECK(ctx, cudaMemcpyAsync((char *)heatmap_host + frame_begin * fbytes, (char *)ctx->hm_dev + frame_begin * fbytes,
+                                      (size_t)(frame_end - frame_begin) * fbytes, cudaMemcpyDeviceToHost, ctx->work_stream));
+    }
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->work_stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return CVVDP_OK;
+}
+
+int cvvdp_b200_pool_device(cvvdp_b200_ctx *ctx, const float *q_dev, int B, int C, int F, int L, float *jod_dev, void *stream) {
+    if (!ctx || !q_dev || !jod_dev) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    if (B < 1 || C < 1 || C > 4 || F < 1 || L < 1) return fail(ctx, CVVDP_ERR_INVALID, "bad Q_per_ch shape");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    PoolArgs pa;
+    fill_pool_args(ctx, &pa, B, C, F, L);
+    pa.Q = q_dev;
+    pa.jod = jod_dev;
+    auto kfn = k_pool;
+    CVVDP_LAUNCH(kfn, dim3(B), dim3(256), 0, (cudaStream_t)stream, pa);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return CVVDP_OK;
+}
+
+int cvvdp_b200_pool(cvvdp_b200_ctx *ctx, const float *q_host, int B, int C, int F, int L, float *jod_host) {
+    if (!ctx || !q_host || !jod_host) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    if (B < 1 || C < 1 || C > 4 || F < 1 || L < 1) return fail(ctx, CVVDP_ERR_INVALID, "bad Q_per_ch shape");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    const size_t qb = (size_t)B * C * F * L * sizeof(float);
+    float *q_dev = nullptr, *j_dev = nullptr;
+    CU_CHECK(ctx, cudaMalloc(&q_dev, qb + 256));
+    if (cudaMalloc(&j_dev, B * sizeof(float)) != cudaSuccess) {
+        cudaFree(q_dev);
+        return fail(ctx, CVVDP_ERR_NOMEM, "cudaMalloc failed");
+    }
+    int rc = CVVDP_OK;
+    if (cudaMemcpyAsync(q_dev, q_host, qb, cudaMemcpyHostToDevice, ctx->work_stream) != cudaSuccess) rc = CVVDP_ERR_CUDA;
+    if (rc == CVVDP_OK) rc = cvvdp_b200_pool_device(ctx, q_dev, B, C, F, L, j_dev, ctx->work_stream);
+    if (rc == CVVDP_OK && cudaMemcpyAsync(jod_host, j_dev, B * sizeof(float), cudaMemcpyDeviceToHost, ctx->work_stream) != cudaSuccess)
+        rc = CVVDP_ERR_CUDA;
+    if (cudaStreamSynchronize(ctx->work_stream) != cudaSuccess) rc = CVVDP_ERR_CUDA;
+    cudaFree(q_dev);
+    cudaFree(j_dev);
+    if (rc == CVVDP_ERR_CUDA) return fail(ctx, rc, "CUDA error in pool: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
+int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int batch, int in_channels, int height, int width,
+                        int dtype, int frame, int colorspace, float *dst_dev, int32_t *flags_dev, void *stream) {
+    if (!ctx || !src || !src->data || !dst_dev) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    if (!ctx->have_display) return fail(ctx, CVVDP_ERR_STATE, "set_display must be called first");
+    if (in_channels != 1 && in_channels != 3) return fail(ctx, CVVDP_ERR_INVALID, "The content must have either 1 or 3 color channels.");
+    if (frame < src->frame0 || frame >= src->frame0 + src->n_frames) return fail(ctx, CVVDP_ERR_INVALID, "frame %d outside the view", frame);
+    if (ctx->disp.eotf == CVVDP_EOTF_HLG && in_channels != 3) return fail(ctx, CVVDP_ERR_UNSUPPORTED, "HLG needs three colour channels");
+    if (colorspace < CVVDP_CS_DKLD65 || colorspace > CVVDP_CS_LMS2006) return fail(ctx, CVVDP_ERR_INVALID, "unknown colour space id %d", colorspace);
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrontendArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.clip = to_view(src);
+    to_display_dev(ctx->disp, &fa.dd, colorspace);
+    fa.dtype = dtype;
+    fa.cin = in_channels;
+    fa.B = batch;
+    fa.H = height;
+    fa.W = width;
+    fa.frame = frame - src->frame0;
+    fa.dst = dst_dev;
+    fa.flags = flags_dev;
+    const long long npix = (long long)height * width;
+    auto kfn = k_frontend;
+    CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), batch), dim3(256), 0, (cudaStream_t)stream, fa);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return CVVDP_OK;
+}
+
+int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

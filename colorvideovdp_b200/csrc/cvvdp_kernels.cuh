@@ -1,0 +1,766 @@
+// cvvdp_kernels.cuh -- sm_100a kernels of the ColorVideoVDP hot path.
+//
+// HBM layout of every pyramid level: planes of float4 "pixels", one plane per (batch item, frame,
+// video) with video 0 = test, 1 = reference; a pixel holds the four perceptual channels
+// (A-sust, RG, YV, A-trans) of that video, so each pixel is one aligned 128-bit load/store:
+//     level_i[((b * n + f) * 2 + v) * h_i * w_i + y * w_i + x]          (float4)
+// (the reference keeps [B, 8, N, H, W] planar fp32 with test/ref interleaved on the channel axis,
+// cvvdp_metric.py:550-560).  References in comments are paths in the reference tree.
+#pragma once
+#include "cvvdp_common.cuh"
+
+namespace cvvdp {
+
+// =================================================================================================
+// Front end: dtype unpack -> EOTF -> RGB->DKLd65   (video_source.py:320-346, display_model.py:333-365,
+// 241-276)
+// =================================================================================================
+__device__ __forceinline__ float load_unpack(const void *base, long long off, int dtype) {
+    switch (dtype) {
+        case CVVDP_DTYPE_U8: return (float)((const unsigned char *)base)[off] / 255.0f;
+        case CVVDP_DTYPE_U16: return (float)((const unsigned short *)base)[off] / 65535.0f;
+        case CVVDP_DTYPE_F16: return half_bits_to_float(((const unsigned short *)base)[off]);
+        default: return ((const float *)base)[off];
+    }
+}
+
+__device__ __forceinline__ float clamp01_keepnan(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
+
+__device__ __forceinline__ float srgb2lin(float p) {  // display_model.py:78-80
+    return p > 0.04045f ? f_pow((p + 0.055f) / 1.055f, 2.4f) : p / 12.92f;
+}
+__device__ __forceinline__ float pq2lin(float V) {  // display_model.py:58-70
+    const float c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f;
+    float im_t = f_pow(V, (float)(1.0 / 78.84375));
+    float num = fmaxf(im_t - c1, 0.f);
+    return 10000.0f * f_pow(num / (c2 - c3 * im_t), (float)(1.0 / 0.1593017578125));
+}
+
+// v[0..n) display-encoded -> absolute linear (cd/m^2), in place.  n = 1 or 3.
+__device__ __forceinline__ void eotf_forward(float *v, int n, const DisplayDev &d) {
+    const float a = d.Ypeak - d.Yblack;
+    if (d.eotf == CVVDP_EOTF_NONE) return;
+    if (d.eotf != CVVDP_EOTF_LINEAR) {
+        for (int i = 0; i < n; ++i) v[i] = clamp01_keepnan(v[i]);  // display_model.py:335-337
+    }
+    switch (d.eotf) {
+        case CVVDP_EOTF_SRGB:
+            for (int i = 0; i < n; ++i) {
+                float lin = srgb2lin(v[i]);
+                if (d.exposure != 1.f) lin = fminf(fmaxf(lin * d.exposure, 0.f), 1.f);
+                v[i] = a * lin + d.Yblack + d.Yrefl;
+            }
+            break;
+        case CVVDP_EOTF_PQ:
+            for (int i = 0; i < n; ++i)
+                v[i] = fminf(fmaxf(pq2lin(v[i]) * d.exposure, 0.005f), d.Ypeak) + d.Yblack + d.Yrefl;
+            break;
+        case CVVDP_EOTF_LINEAR:
+            for (int i = 0; i < n; ++i) v[i] = fminf(fmaxf(v[i] * d.exposure, d.lin_lo), d.Ypeak) + d.Yrefl;
+            break;
+        case CVVDP_EOTF_HLG: {  // display_model.py:89-108, 350-359 (needs all three channels)
+            const float ha = 0.17883277f, hb = 1.f - 4.f * ha, hc = 0.5f - ha * logf(4.f * ha);
+            float s[3];
+            for (int i = 0; i < 3; ++i)
+                s[i] = v[i] <= 0.5f ? v[i] * v[i] / 3.0f : (expf((v[i] - hc) / ha) + hb) / 12.0f;
+            float Ys = 0.2627f * s[0] + 0.6780f * s[1] + 0.0593f * s[2];
+            float gsc = powf(Ys, d.gamma - 1.f);
+            for (int i = 0; i < 3; ++i) {
+                float lin = gsc * s[i];
+                if (d.exposure != 1.f) lin = fminf(fmaxf(lin * d.exposure, 0.f), 1.f);
+                v[i] = a * lin + d.Yblack + d.Yrefl;
+            }
+        } break;
+        default:  // CVVDP_EOTF_GAMMA, display_model.py:360-362
+            for (int i = 0; i < n; ++i) {
+                float lin = fminf(fmaxf(f_pow(v[i], d.gamma) * d.exposure, 0.f), 1.f);
+                v[i] = a * lin + d.Yblack + d.Yrefl;
+            }
+    }
+}
+
+// Raw pixel of frame `fidx` (index inside the view) -> DKL triple.
+__device__ __forceinline__ void pixel_to_dkl(const ClipView &cv, long long base, int fidx, int cin, int dtype,
+                                             const DisplayDev &d, float &o0, float &o1, float &o2) {
+    float v[3];
+    const long long off = base + (long long)fidx * cv.s[2];
+    v[0] = load_unpack(cv.data, off, dtype);
+    if (cin == 3) {
+        v[1] = load_unpack(cv.data, off + cv.s[1], dtype);
+        v[2] = load_unpack(cv.data, off + 2 * cv.s[1], dtype);
+    }
+    eotf_forward(v, cin, d);  // CVVDP_EOTF_NONE: values pass through (the host then sets M = identity)
+    if (cin == 3) {  // display_model.py:266-269
+        o0 = (v[0] * d.M[0] + v[1] * d.M[1]) + v[2] * d.M[2];
+        o1 = (v[0] * d.M[3] + v[1] * d.M[4]) + v[2] * d.M[5];
+        o2 = (v[0] * d.M[6] + v[1] * d.M[7]) + v[2] * d.M[8];
+    } else {  // display_model.py:231-235 + the broadcast at cvvdp_metric.py:464-465, 503-504
+        o0 = o1 = o2 = v[0];
+    }
+}
+
+// cvvdp_metric.py:445-450
+__device__ __forceinline__ int symmetric_frame_index(int fi, int F) {
+    const int m = F - 1;
+    const int a = -fi - 1;  // fi < 0
+    if (((a / m) & 1) == 0) return (a % m) + 1;
+    int r = fi % m;
+    return r < 0 ? r + m : r;
+}
+
+// Standalone front end for the display-model plugin surface
+// (vvdp_display_photometry.source_2_target_colorspace(frame, 'DKLd65')).
+struct FrontendArgs {
+    ClipView clip;
+    DisplayDev dd;
+    int dtype, cin, B, H, W, frame;
+    float *dst;     // [B, cin, H, W]
+    int *flags;     // [0]: values outside 0..1, [1]: NaN, [2]: Inf  (may be null)
+};
+__global__ void __launch_bounds__(256) k_frontend(const FrontendArgs a) {
+    const long long npix = (long long)a.H * a.W;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (p >= npix) return;
+    const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
+    const long long base = b * a.clip.s[0] + y * a.clip.s[3] + x * a.clip.s[4] + (long long)a.frame * a.clip.s[2];
+    if (a.flags) {
+        for (int c = 0; c < a.cin; ++c) {
+            float v = load_unpack(a.clip.data, base + c * a.clip.s[1], a.dtype);
+            if (a.dd.eotf != CVVDP_EOTF_LINEAR && (v > 1.f || v < 0.f)) atomicAdd(&a.flags[0], 1);
+            if (v != v) atomicAdd(&a.flags[1], 1);
+            if (fabsf(v) == INFINITY) atomicAdd(&a.flags[2], 1);
+        }
+    }
+    float o0, o1, o2;
+    pixel_to_dkl(a.clip, base - (long long)a.frame * a.clip.s[2], a.frame, a.cin, a.dtype, a.dd, o0, o1, o2);
+    float *dst = a.dst + (long long)b * a.cin * npix + p;
+    dst[0] = o0;
+    if (a.cin == 3) {
+        dst[npix] = o1;
+        dst[2 * npix] = o2;
+    }
+}
+
+// =================================================================================================
+// Temporal stage: front end fused with the causal FIR  (cvvdp_metric.py:453-561)
+// One thread owns one pixel of one video and marches over the frames of the block with a ring of the
+// last `fl` DKL triples in shared memory, so every input frame is read and EOTF-ed exactly once per
+// block (+ fl-1 history frames at the start of the block).
+// =================================================================================================
+struct TemporalArgs {
+    ClipView clip[2];
+    DisplayDev dd;
+    int dtype, cin;
+    int B, H, W;
+    int F_total, f0, f1, fl, padding;
+    float4 *out;  // level 0: [B][n][2][H*W]
+    float taps[4][CVVDP_MAX_FILTER_LEN];  // taps[c][k] multiplies frame f-(fl-1)+k (= F_c flipped, l.556)
+};
+
+#define CVVDP_TEMPORAL_THREADS 256
+__global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const TemporalArgs a) {
+    CVVDP_DYN_SMEM(smem_raw);
+    float *ring = reinterpret_cast<float *>(smem_raw);  // [fl][3][threads]
+    const int tid = threadIdx.x;
+    const long long npix = (long long)a.H * a.W;
+    const long long p = (long long)blockIdx.x * CVVDP_TEMPORAL_THREADS + tid;
+    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
+    if (p >= npix) return;  // no block-level barriers in this kernel
+    const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
+    const ClipView &cv = a.clip[v];
+    const long long base = b * cv.s[0] + y * cv.s[3] + x * cv.s[4];
+    const int n = a.f1 - a.f0, fl = a.fl;
+    float4 *out = a.out + ((long long)b * n * 2 + v) * npix + p;
+    int slot = 0, last_s = -1;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    for (int t = a.f0 - (fl - 1); t < a.f1; ++t) {
+        int s = t;
+        if (s < 0) s = (a.padding == CVVDP_PAD_REPLICATE) ? 0 : symmetric_frame_index(s, a.F_total);
+        if (s != last_s) {
+            pixel_to_dkl(cv, base, s - cv.frame0, a.cin, a.dtype, a.dd, d0, d1, d2);
+            last_s = s;
+        }
+        ring[(slot * 3 + 0) * CVVDP_TEMPORAL_THREADS + tid] = d0;
+        ring[(slot * 3 + 1) * CVVDP_TEMPORAL_THREADS + tid] = d1;
+        ring[(slot * 3 + 2) * CVVDP_TEMPORAL_THREADS + tid] = d2;
+        if (t >= a.f0) {
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+            int ks = slot + 1 == fl ? 0 : slot + 1;  // oldest frame in the ring
+            for (int k = 0; k < fl; ++k) {
+                const float x0 = ring[(ks * 3 + 0) * CVVDP_TEMPORAL_THREADS + tid];
+                const float x1 = ring[(ks * 3 + 1) * CVVDP_TEMPORAL_THREADS + tid];
+                const float x2 = ring[(ks * 3 + 2) * CVVDP_TEMPORAL_THREADS + tid];
+                o0 = fmaf(a.taps[0][k], x0, o0);
+                o1 = fmaf(a.taps[1][k], x1, o1);
+                o2 = fmaf(a.taps[2][k], x2, o2);
+                o3 = fmaf(a.taps[3][k], x0, o3);  // transient channel filters the achromatic plane (l.557)
+                ks = ks + 1 == fl ? 0 : ks + 1;
+            }
+            out[(long long)(t - a.f0) * 2 * npix] = make_float4(o0, o1, o2, o3);
+        }
+        slot = slot + 1 == fl ? 0 : slot + 1;
+    }
+}
+
+// =================================================================================================
+// Gaussian pyramid reduce  (lpyr_dec.py:186-211): zero-padded 5-tap stride-2 passes (rows, then
+// columns) with the reference's edge fix-ups, including the parity quirk at line 206 (the ROW count
+// selects the right-edge rule of the column pass).
+// =================================================================================================
+struct ReduceArgs {
+    const float4 *in;
+    float4 *out;
+    int h, w, hc, wc;
+};
+#define CVVDP_RTX 32
+#define CVVDP_RTY 8
+#define CVVDP_RIW (2 * CVVDP_RTX + 3)
+#define CVVDP_RIH (2 * CVVDP_RTY + 3)
+
+__global__ void __launch_bounds__(256) k_reduce(const ReduceArgs a) {
+    __shared__ float4 s_in[CVVDP_RIH][CVVDP_RIW + 1];
+    __shared__ float4 s_ya[CVVDP_RTY][CVVDP_RIW + 1];
+    const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f;  // [K0 K1 K2 K1 K0], lpyr_dec.py:179
+    const int tid = threadIdx.x;
+    const int plane = blockIdx.z;
+    const int ox0 = blockIdx.x * CVVDP_RTX, oy0 = blockIdx.y * CVVDP_RTY;
+    const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
+    const float4 *src = a.in + (long long)plane * a.h * a.w;
+    for (int i = tid; i < CVVDP_RIH * CVVDP_RIW; i += 256) {
+        const int r = i / CVVDP_RIW, c = i - r * CVVDP_RIW;
+        const int gy = iy0 + r, gx = ix0 + c;
+        float4 v = f4(0.f);
+        if (gy >= 0 && gy < a.h && gx >= 0 && gx < a.w) v = src[(long long)gy * a.w + gx];
+        s_in[r][c] = v;
+    }
+    __syncthreads();
+    const bool rows_odd = (a.h & 1) != 0;
+    for (int i = tid; i < CVVDP_RTY * CVVDP_RIW; i += 256) {
+        const int oy = i / CVVDP_RIW, c = i - oy * CVVDP_RIW;
+        const int goy = oy0 + oy;
+        float4 acc = f4(0.f);
+        if (goy < a.hc) {
+            const int r = 2 * oy;
+            acc = K0 * s_in[r][c];
+            acc = fma4(K1, s_in[r + 1][c], acc);
+            acc = fma4(K2, s_in[r + 2][c], acc);
+            acc = fma4(K1, s_in[r + 3][c], acc);
+            acc = fma4(K0, s_in[r + 4][c], acc);
+            if (goy == 0) {  // l.195: x~(-1) = x(0), x~(-2) = x(1)
+                acc = fma4(K1, s_in[0 - iy0][c], acc);
+                acc = fma4(K0, s_in[min(1, a.h - 1) - iy0][c], acc);
+            }
+            if (goy == a.hc - 1) {  // l.196-199
+                if (rows_odd) {
+                    acc = fma4(K1, s_in[a.h - 1 - iy0][c], acc);
+                    acc = fma4(K0, s_in[max(a.h - 2, 0) - iy0][c], acc);
+                } else {
+                    acc = fma4(K0, s_in[a.h - 1 - iy0][c], acc);
+                }
+            }
+        }
+        s_ya[oy][c] = acc;
+    }
+    __syncthreads();
+    const int ox = tid % CVVDP_RTX, oy = tid / CVVDP_RTX;
+    const int gox = ox0 + ox, goy = oy0 + oy;
+    if (gox < a.wc && goy < a.hc) {
+        const int c = 2 * ox;
+        float4 acc = K0 * s_ya[oy][c];
+        acc = fma4(K1, s_ya[oy][c + 1], acc);
+        acc = fma4(K2, s_ya[oy][c + 2], acc);
+        acc = fma4(K1, s_ya[oy][c + 3], acc);
+        acc = fma4(K0, s_ya[oy][c + 4], acc);
+        if (gox == 0) {  // l.205
+            acc = fma4(K1, s_ya[oy][0 - ix0], acc);
+            acc = fma4(K0, s_ya[oy][min(1, a.w - 1) - ix0], acc);
+        }
+        if (gox == a.wc - 1) {  // l.206-209: the parity of the ROW count chooses the rule
+            if (rows_odd) {
+                acc = fma4(K1, s_ya[oy][a.w - 1 - ix0], acc);
+                acc = fma4(K0, s_ya[oy][max(a.w - 2, 0) - ix0], acc);
+            } else {
+                acc = fma4(K0, s_ya[oy][a.w - 1 - ix0], acc);
+            }
+        }
+        a.out[(long long)plane * a.hc * a.wc + (long long)goy * a.wc + gox] = acc;
+    }
+}
+
+// =================================================================================================
+// Fused band kernel (one launch per pyramid level i < L-1):
+//   expand(g_{i+1}) -> Laplacian -> Weber contrast (lpyr_dec.py:386-408) -> castleCSF LUT
+//   (csf.py:28-51) -> mult-mutual masking with the 13x13 phase-uncertainty Gaussian, cross-channel
+//   pooling and soft clamp (cvvdp_metric.py:817-856, 963-971, 753-764, 945-950) -> spatial
+//   p-norm partial sums (cvvdp_metric.py:722, 1032-1048) [-> per-band heat-map plane, 724-734].
+// A CTA owns a 32x32 tile; the mutual-masking term needs a +-6 halo (reflect at image borders), so
+// contrast/CSF are evaluated on the 44x44 extended tile held in shared memory.
+// =================================================================================================
+#define CVVDP_BTX 32
+#define CVVDP_BTY 32
+#define CVVDP_BHALO 6
+#define CVVDP_BEW (CVVDP_BTX + 2 * CVVDP_BHALO)  // 44
+#define CVVDP_BEH (CVVDP_BTY + 2 * CVVDP_BHALO)  // 44
+#define CVVDP_BCW (CVVDP_BEW / 2 + 2)            // 24 coarse columns
+#define CVVDP_BCH (CVVDP_BEH / 2 + 2)
+#define CVVDP_MM_STRIDE (CVVDP_BEW + 1)          // 45: conflict-free row-wise 128-bit access
+#define CVVDP_HB_STRIDE (CVVDP_BTX + 1)          // 33
+#define CVVDP_BAND_THREADS 256
+
+struct BandArgs {
+    const float4 *fine;    // level i   [pairs*2][h*w]
+    const float4 *coarse;  // level i+1 [pairs*2][hc*wc]
+    const float4 *lut;     // [32] per-level CSF rows of the 4 channels, pre-scaled: row*log2(10)+log2(sens*gain)
+    float *partials;       // [pairs][tiles][4]
+    float *hm;             // [pairs][h*w] per-band heat-map plane or null
+    int h, w, hc, wc;
+    int do_blur;
+    float mul;             // get_band: 1 for band 0, 2 for middle bands (lpyr_dec.py:60-66)
+    float lut_a, lut_b;    // LUT index = clamp(log2(L_bkg) * lut_a + lut_b, 0, 31)
+    float kern[2 * CVVDP_BHALO + 1];
+    float mc;              // 10^mask_c
+    float q[4], p;
+    float X[16];           // 2^xcm_weights [source][masked]
+    float dmax;            // 10^d_max
+    float eps;
+    float beta;
+    float hm_w[4];         // heat map: channel weights (x image_int)
+    float hm_beta, hm_scale;  // beta_tch, 1/band_mul (lpyr_dec.py:308-314)
+};
+
+struct BandSmem {
+    float4 lut[CVVDP_CSF_LUT_N];
+    float4 crs[2][CVVDP_BCH][CVVDP_BCW];
+    float4 mm[CVVDP_BEH][CVVDP_MM_STRIDE];
+    float4 df[CVVDP_BTY][CVVDP_BTX];
+    float4 hb[CVVDP_BEH][CVVDP_HB_STRIDE];
+    float red[CVVDP_BAND_THREADS / 32][4];
+};
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' padding
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+// Contrast / CSF / mutual-masking inputs of one pixel (phase 1).
+__device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lut, float4 gt, float4 gr, float4 et,
+                                           float4 er, float4 &mm, float4 &df) {
+    const float4 lt = gt - et, lr = gr - er;  // Laplacian (lpyr_dec.py:387)
+    const float Lt = fmaxf(et.x, 0.01f), Lr = fmaxf(er.x, 0.01f);  // l.394
+    const float it = a.mul / Lt, ir = a.mul / Lr;
+    const float cl = 1000.0f * a.mul;  // clamp(max=1000) before the band multiplier
+    const float4 ct = make_float4(fminf(lt.x * it, cl), fminf(lt.y * it, cl), fminf(lt.z * it, cl), fminf(lt.w * it, cl));
+    const float4 cr = make_float4(fminf(lr.x * ir, cl), fminf(lr.y * ir, cl), fminf(lr.z * ir, cl), fminf(lr.w * ir, cl));
+    // CSF: always from the reference background (cvvdp_metric.py:709); interp.py:55-60, 92-100
+    float ind = fminf(fmaxf(fmaf(f_lg2(Lr), a.lut_a, a.lut_b), 0.f), (float)(CVVDP_CSF_LUT_N - 1));
+    const int i0 = (int)ind;
+    const float fr = ind - (float)i0;
+    const int i1 = min(i0 + 1, CVVDP_CSF_LUT_N - 1);
+    const float4 va = s_lut[i0], vb = s_lut[i1];
+    const float w0 = 1.f - fr;
+    const float4 S = make_float4(f_ex2(va.x * w0 + vb.x * fr), f_ex2(va.y * w0 + vb.y * fr),
+                                 f_ex2(va.z * w0 + vb.z * fr), f_ex2(va.w * w0 + vb.w * fr));
+    const float4 Tp = make_float4(ct.x * S.x, ct.y * S.y, ct.z * S.z, ct.w * S.w);
+    const float4 Rp = make_float4(cr.x * S.x, cr.y * S.y, cr.z * S.z, cr.w * S.w);
+    mm = make_float4(fminf(fabsf(Tp.x), fabsf(Rp.x)), fminf(fabsf(Tp.y), fabsf(Rp.y)),
+                     fminf(fabsf(Tp.z), fabsf(Rp.z)), fminf(fabsf(Tp.w), fabsf(Rp.w)));
+    df = make_float4(fabsf(Tp.x - Rp.x), fabsf(Tp.y - Rp.y), fabsf(Tp.z - Rp.z), fabsf(Tp.w - Rp.w));
+}
+
+__device__ __forceinline__ float spow_fast(float x, float p, float eps, float eps_p) {
+    return f_pow(x + eps, p) - eps_p;  // safe_pow, cvvdp_metric.py:77-84
+}
+
+// Masking + clamp + pooling term of one pixel (phase 4).  m = blurred mutual-masking signal.
+__device__ __forceinline__ float4 band_mask(const BandArgs &a, float4 m, float4 df, const float *eps_q, float eps_p) {
+    const float t0 = f_pow(m.x * a.mc + a.eps, a.q[0]) - eps_q[0];
+    const float t1 = f_pow(m.y * a.mc + a.eps, a.q[1]) - eps_q[1];
+    const float t2 = f_pow(m.z * a.mc + a.eps, a.q[2]) - eps_q[2];
+    const float t3 = f_pow(m.w * a.mc + a.eps, a.q[3]) - eps_q[3];
+    float4 D;
+    float *Dp = &D.x;
+    const float dfv[4] = {df.x, df.y, df.z, df.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float Mk = t0 * a.X[0 * 4 + c] + t1 * a.X[1 * 4 + c] + t2 * a.X[2 * 4 + c] + t3 * a.X[3 * 4 + c];
+        const float P = f_pow(dfv[c] + a.eps, a.p) - eps_p;
+        // D_u = P / (1 + M);  D = Dmax * D_u / (Dmax + D_u)  ==  Dmax * P / (Dmax * (1 + M) + P)
+        Dp[c] = a.dmax * P * f_rcp(fmaf(a.dmax, 1.f + Mk, P));
+    }
+    return D;
+}
+
+__global__ void __launch_bounds__(CVVDP_BAND_THREADS) k_band(const BandArgs a) {
+    CVVDP_DYN_SMEM(smem_raw);
+    BandSmem &sm = *reinterpret_cast<BandSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.z;
+    const int x0 = blockIdx.x * CVVDP_BTX, y0 = blockIdx.y * CVVDP_BTY;
+    const int hal = a.do_blur ? CVVDP_BHALO : 0;
+    const int ex0 = x0 - hal, ey0 = y0 - hal;        // origin of the extended tile (even)
+    const int cx0 = ex0 / 2 - 1, cy0 = ey0 / 2 - 1;  // origin of the coarse tile (ex0, ey0 are even)
+    const long long npix = (long long)a.h * a.w, ncpix = (long long)a.hc * a.wc;
+    const float4 *fine_t = a.fine + (long long)pair * 2 * npix, *fine_r = fine_t + npix;
+    const float4 *crs_t = a.coarse + (long long)pair * 2 * ncpix;
+
+    // ---- phase 0: CSF rows + coarse tile (replicate-clamped, lpyr_dec.py:136-141) ----
+    if (tid < CVVDP_CSF_LUT_N) sm.lut[tid] = a.lut[tid];
+    for (int i = tid; i < 2 * CVVDP_BCH * CVVDP_BCW; i += CVVDP_BAND_THREADS) {
+        const int v = i / (CVVDP_BCH * CVVDP_BCW), rem = i - v * (CVVDP_BCH * CVVDP_BCW);
+        const int r = rem / CVVDP_BCW, c = rem - r * CVVDP_BCW;
+        const int cy = min(max(cy0 + r, 0), a.hc - 1), cx = min(max(cx0 + c, 0), a.wc - 1);
+        sm.crs[v][r][c] = crs_t[v * ncpix + (long long)cy * a.wc + cx];
+    }
+    __syncthreads();
+
+    // ---- phase 1: 2x2 quads of the extended tile: expand, contrast, CSF, |T'-R'| and min(|T'|,|R'|) ----
+    const int eh = CVVDP_BTY + 2 * hal, ew = CVVDP_BTX + 2 * hal;
+    const int qh = eh / 2, qw = ew / 2;
+    for (int qi = tid; qi < qh * qw; qi += CVVDP_BAND_THREADS) {
+        const int qy = qi / qw, qx = qi - qy * qw;
+        const int gy = ey0 + 2 * qy, gx = ex0 + 2 * qx;  // top-left fine pixel of the quad (even, even)
+        if (gy + 1 < 0 || gy >= a.h || gx + 1 < 0 || gx >= a.w) continue;
+        // expanded coarse values of the quad for test (v=0) and reference (v=1): rows then columns
+        float4 e[2][4];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            float4 ve[3], vo[3];  // vertical pass for the three coarse columns: even row, odd row
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float4 c0 = sm.crs[v][qy][qx + c], c1 = sm.crs[v][qy + 1][qx + c], c2 = sm.crs[v][qy + 2][qx + c];
+                ve[c] = fma4(0.1f, c2, fma4(0.8f, c1, 0.1f * c0));
+                vo[c] = fma4(0.5f, c2, 0.5f * c1);
+            }
+            e[v][0] = fma4(0.1f, ve[2], fma4(0.8f, ve[1], 0.1f * ve[0]));  // (even row, even col)
+            e[v][1] = fma4(0.5f, ve[2], 0.5f * ve[1]);                     // (even row, odd col)
+            e[v][2] = fma4(0.1f, vo[2], fma4(0.8f, vo[1], 0.1f * vo[0]));  // (odd row, even col)
+            e[v][3] = fma4(0.5f, vo[2], 0.5f * vo[1]);                     // (odd row, odd col)
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int py = gy + (k >> 1), px = gx + (k & 1);
+            if (py < 0 || py >= a.h || px < 0 || px >= a.w) continue;
+            const long long off = (long long)py * a.w + px;
+            float4 mm, df;
+            band_pixel(a, sm.lut, fine_t[off], fine_r[off], e[0][k], e[1][k], mm, df);
+            const int ly = py - ey0, lx = px - ex0;
+            sm.mm[ly][lx] = mm;
+            const int iy = py - y0, ix = px - x0;
+            if (iy >= 0 && iy < CVVDP_BTY && ix >= 0 && ix < CVVDP_BTX) sm.df[iy][ix] = df;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: horizontal pass of the phase-uncertainty Gaussian (reflect padding) ----
+    if (a.do_blur) {
+        for (int it = tid; it < CVVDP_BEH * (CVVDP_BTX / 4); it += CVVDP_BAND_THREADS) {
+            const int r = it % CVVDP_BEH, xg = it / CVVDP_BEH;
+            const int gy = ey0 + r;
+            if (gy < 0 || gy >= a.h) continue;
+            const int gxb = x0 + xg * 4;
+            if (gxb >= a.w) continue;
+            float4 win[2 * CVVDP_BHALO + 4];
+#pragma unroll
+            for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                int lx = reflect_idx(gxb + j - CVVDP_BHALO, a.w) - ex0;
+                lx = min(max(lx, 0), CVVDP_BEW - 1);  // only hit by outputs beyond the image (discarded)
+                win[j] = sm.mm[r][lx];
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                float4 acc = f4(0.f);
+#pragma unroll
+                for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) acc = fma4(a.kern[k], win[o + k], acc);
+                sm.hb[r][xg * 4 + o] = acc;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3/4: vertical pass, masking, clamp, pooling ----
+    float eps_q[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) eps_q[c] = f_pow(a.eps, a.q[c]);
+    const float eps_p = f_pow(a.eps, a.p);
+    const float eps_b = (a.beta == 2.0f) ? 0.f : f_pow(a.eps, a.beta);
+    float4 acc = f4(0.f);
+    {
+        const int ix = tid % CVVDP_BTX, yg = tid / CVVDP_BTX;  // 4 consecutive rows per thread
+        const int gx = x0 + ix;
+        const int gyb = y0 + yg * 4;
+        if (gx < a.w && gyb < a.h) {
+            float4 win[2 * CVVDP_BHALO + 4];
+            if (a.do_blur) {
+#pragma unroll
+                for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                    int ly = reflect_idx(gyb + j - CVVDP_BHALO, a.h) - ey0;
+                    ly = min(max(ly, 0), CVVDP_BEH - 1);
+                    win[j] = sm.hb[ly][ix];
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const int gy = gyb + o;
+                if (gy >= a.h) break;
+                float4 m;
+                if (a.do_blur) {
+                    m = f4(0.f);
+#pragma unroll
+                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) m = fma4(a.kern[k], win[o + k], m);
+                } else {
+                    m = sm.mm[yg * 4 + o][ix];
+                }
+                const float4 D = band_mask(a, m, sm.df[yg * 4 + o][ix], eps_q, eps_p);
+                if (a.beta == 2.0f) {  // (D+eps)^2 - eps^2 == D (D + 2 eps), exact at D = 0
+                    acc.x = fmaf(D.x, D.x + 2.f * a.eps, acc.x);
+                    acc.y = fmaf(D.y, D.y + 2.f * a.eps, acc.y);
+                    acc.z = fmaf(D.z, D.z + 2.f * a.eps, acc.z);
+                    acc.w = fmaf(D.w, D.w + 2.f * a.eps, acc.w);
+                } else {
+                    acc.x += f_pow(D.x + a.eps, a.beta) - eps_b;
+                    acc.y += f_pow(D.y + a.eps, a.beta) - eps_b;
+                    acc.z += f_pow(D.z + a.eps, a.beta) - eps_b;
+                    acc.w += f_pow(D.w + a.eps, a.beta) - eps_b;
+                }
+                if (a.hm) {  // cvvdp_metric.py:724-734: p-norm over the channels, then set_lband's 1/band_mul
+                    const float eb = f_pow(a.eps, a.hm_beta);
+                    float s = (f_pow(D.x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D.y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
+                              (f_pow(D.z * a.hm_w[2] + a.eps, a.hm_beta) - eb) + (f_pow(D.w * a.hm_w[3] + a.eps, a.hm_beta) - eb);
+                    const float ib = 1.f / a.hm_beta;
+                    a.hm[(long long)pair * npix + (long long)gy * a.w + gx] = (f_pow(s + a.eps, ib) - f_pow(a.eps, ib)) * a.hm_scale;
+                }
+            }
+        }
+    }
+    // ---- phase 5: deterministic block reduction of the four channel sums ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if ((tid & 31) == 0) {
+        sm.red[tid >> 5][0] = acc.x;
+        sm.red[tid >> 5][1] = acc.y;
+        sm.red[tid >> 5][2] = acc.z;
+        sm.red[tid >> 5][3] = acc.w;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < CVVDP_BAND_THREADS / 32; ++w) s += sm.red[w][tid];
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
+        a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
+    }
+}
+
+// =================================================================================================
+// Baseband (cvvdp_metric.py:711-712 with lpyr_dec.py:378-384): L_bkg is the spatial mean of the
+// clamped achromatic plane of each image; D = |T - R| * S (no gain, masking or clamp).
+// One CTA per (batch item, frame).
+// =================================================================================================
+struct BasebandArgs {
+    const float4 *g;       // level L-1 [pairs*2][npix]
+    const float4 *lut;     // [32] rows, pre-scaled: row*log2(10)+log2(sens)
+    float *partials;       // [pairs][1][4]
+    float *hm;             // [pairs][npix] or null
+    int npix;
+    float lut_a, lut_b;
+    float eps, beta;
+    float hm_w[4];
+    float hm_beta;
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    return s;
+}
+
+__global__ void __launch_bounds__(256) k_baseband(const BasebandArgs a) {
+    __shared__ float red[8];
+    const int tid = threadIdx.x, pair = blockIdx.x;
+    const float4 *gt = a.g + (long long)pair * 2 * a.npix, *gr = gt + a.npix;
+    float st = 0.f, sr = 0.f;
+    for (int i = tid; i < a.npix; i += 256) {
+        st += fmaxf(gt[i].x, 0.01f);
+        sr += fmaxf(gr[i].x, 0.01f);
+    }
+    const float Lt = block_sum_256(st, red) / (float)a.npix;
+    const float Lr = block_sum_256(sr, red) / (float)a.npix;
+    float ind = fminf(fmaxf(fmaf(log2f(Lr), a.lut_a, a.lut_b), 0.f), (float)(CVVDP_CSF_LUT_N - 1));
+    const int i0 = (int)ind;
+    const float fr = ind - (float)i0;
+    const int i1 = min(i0 + 1, CVVDP_CSF_LUT_N - 1);
+    const float4 va = a.lut[i0], vb = a.lut[i1];
+    const float S[4] = {exp2f(va.x * (1.f - fr) + vb.x * fr), exp2f(va.y * (1.f - fr) + vb.y * fr),
+                        exp2f(va.z * (1.f - fr) + vb.z * fr), exp2f(va.w * (1.f - fr) + vb.w * fr)};
+    const float eps_b = powf(a.eps, a.beta);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = tid; i < a.npix; i += 256) {
+        const float4 t = gt[i], r = gr[i];
+        const float tv[4] = {t.x, t.y, t.z, t.w}, rv[4] = {r.x, r.y, r.z, r.w};
+        float D[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float ct = fminf(tv[c] / Lt, 1000.f), cr = fminf(rv[c] / Lr, 1000.f);
+            D[c] = fabsf(ct - cr) * S[c];
+            acc[c] += (a.beta == 2.0f) ? D[c] * (D[c] + 2.f * a.eps) : powf(D[c] + a.eps, a.beta) - eps_b;
+        }
+        if (a.hm) {
+            const float eb = powf(a.eps, a.hm_beta);
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) s += powf(D[c] * a.hm_w[c] + a.eps, a.hm_beta) - eb;
+            const float ib = 1.f / a.hm_beta;
+            a.hm[(long long)pair * a.npix + i] = powf(s + a.eps, ib) - powf(a.eps, ib);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float s = block_sum_256(acc[c], red);
+        if (tid == 0) a.partials[(long long)pair * 4 + c] = s;
+    }
+}
+
+// =================================================================================================
+// Spatial pooling epilogue: fixed-order sum of the per-tile partials, then
+// Q = safe_pow(sum / N, 1 / beta)  (lp_norm, cvvdp_metric.py:1032-1048) -> Q_per_ch[B, C, F, L].
+// One warp per (pair, band).
+// =================================================================================================
+struct FinalizeArgs {
+    const float *partials[CVVDP_MAX_BANDS];
+    int ntiles[CVVDP_MAX_BANDS];
+    int npix[CVVDP_MAX_BANDS];
+    int L, C, B, n, f_off, F_total;
+    float beta, eps;
+    float *Q;  // [B][C][F_total][L]
+};
+
+__global__ void __launch_bounds__(128) k_finalize(const FinalizeArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int total = a.B * a.n * a.L;
+    const bool live = warp < total;  // whole warps only: keep every lane in the shuffles
+    const int wi = live ? warp : 0;
+    const int band = wi % a.L, pair = wi / a.L;
+    const int nt = a.ntiles[band];
+    const float4 *src = reinterpret_cast<const float4 *>(a.partials[band]) + (long long)pair * nt;
+    float4 acc = f4(0.f);
+    for (int t = lane; t < nt; t += 32) acc = acc + src[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (live && lane < a.C) {
+        const float s = lane == 0 ? acc.x : (lane == 1 ? acc.y : (lane == 2 ? acc.z : acc.w));
+        const float ib = 1.f / a.beta;
+        const float q = powf(s / (float)a.npix[band] + a.eps, ib) - powf(a.eps, ib);
+        const int b = pair / a.n, f = pair - b * a.n;
+        a.Q[(((long long)b * a.C + lane) * a.F_total + (a.f_off + f)) * a.L + band] = q;
+    }
+}
+
+// =================================================================================================
+// do_pooling_and_jods + met2jod (cvvdp_metric.py:610-658).  One CTA per batch item.
+// =================================================================================================
+struct PoolArgs {
+    const float *Q;  // [B][C][F][L]
+    float *jod;      // [B]
+    int B, C, F, L;
+    float ch_w[4], bb_w[4];
+    float beta_sch, beta_tch, beta_t, image_int, jod_a, jod_exp, eps;
+};
+__device__ __forceinline__ float spow_acc(float x, float p, float eps) { return powf(x + eps, p) - powf(eps, p); }
+__device__ __forceinline__ float met2jod_dev(float Q, float jod_a, float jod_exp) {
+    const float Qt = 0.1f;
+    if (Q <= Qt) return 10.f - jod_a * powf(Qt, jod_exp - 1.f) * Q;
+    return 10.f - jod_a * powf(Q, jod_exp);
+}
+__global__ void __launch_bounds__(256) k_pool(const PoolArgs a) {
+    __shared__ float red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float acc = 0.f, q_img = 0.f;
+    for (int f = tid; f < a.F; f += 256) {
+        float s_tc = 0.f;
+        for (int c = 0; c < a.C; ++c) {
+            float s = 0.f;
+            for (int l = 0; l < a.L; ++l) {
+                // reference order: Q * per_ch_w * per_sband_w (l.625)
+                float v = a.Q[(((long long)b * a.C + c) * a.F + f) * a.L + l] * a.ch_w[c];
+                v = (l == a.L - 1) ? v * a.bb_w[c] : v;
+                s += spow_acc(v, a.beta_sch, a.eps);
+            }
+            const float q_sc = spow_acc(s, 1.f / a.beta_sch, a.eps);
+            s_tc += spow_acc(q_sc, a.beta_tch, a.eps);
+        }
+        const float q_tc = spow_acc(s_tc, 1.f / a.beta_tch, a.eps);
+        q_img = q_tc;
+        acc += spow_acc(q_tc, a.beta_t, a.eps);
+    }
+    const float tot = block_sum_256(acc, red);
+    if (tid == 0) {
+        float Q;
+        if (a.F == 1) Q = q_img * a.image_int;  // l.636
+        else Q = spow_acc(tot / (float)a.F, 1.f / a.beta_t, a.eps);  // l.638
+        a.jod[b] = met2jod_dev(Q, a.jod_a, a.jod_exp);
+    }
+}
+
+// =================================================================================================
+// Heat map: reconstruct the per-band difference planes (lpyr_dec.py:328-335), then
+// 1 - met2jod(.)/10 in fp16 (cvvdp_metric.py:743-744, 398).
+// =================================================================================================
+struct ExpandAddArgs {
+    const float *coarse;  // [planes][hc*wc]
+    float *fine;          // [planes][h*w]   fine += expand(coarse)
+    int h, w, hc, wc;
+};
+__device__ __forceinline__ float expand_at(const float *c, int hc, int wc, int y, int x) {
+    const int j = y >> 1, i = x >> 1;
+    float col[3];
+    const int jm = max(j - 1, 0), jp = min(j + 1, hc - 1), im = max(i - 1, 0), ip = min(i + 1, wc - 1);
+    const int xs[3] = {im, i, ip};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float c0 = c[jm * wc + xs[k]], c1 = c[j * wc + xs[k]], c2 = c[jp * wc + xs[k]];
+        col[k] = (y & 1) ? fmaf(0.5f, c2, 0.5f * c1) : fmaf(0.1f, c2, fmaf(0.8f, c1, 0.1f * c0));
+    }
+    return (x & 1) ? fmaf(0.5f, col[2], 0.5f * col[1]) : fmaf(0.1f, col[2], fmaf(0.8f, col[1], 0.1f * col[0]));
+}
+__global__ void __launch_bounds__(256) k_expand_add(const ExpandAddArgs a) {
+    const long long npix = (long long)a.h * a.w;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int plane = blockIdx.y;
+    if (p >= npix) return;
+    const int y = (int)(p / a.w), x = (int)(p - (long long)y * a.w);
+    const float *c = a.coarse + (long long)plane * a.hc * a.wc;
+    a.fine[plane * npix + p] += expand_at(c, a.hc, a.wc, y, x);
+}
+struct HeatmapOutArgs {
+    const float *img;     // [B*n][npix]   (B == 1)
+    unsigned short *out;  // fp16 [F_total][npix]
+    long long npix;
+    int f_off;
+    float jod_a, jod_exp;
+};
+__global__ void __launch_bounds__(256) k_heatmap_out(const HeatmapOutArgs a) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (p >= a.npix) return;
+    const float v = 1.f - met2jod_dev(a.img[f * a.npix + p], a.jod_a, a.jod_exp) / 10.f;
+    a.out[(long long)(a.f_off + f) * a.npix + p] = float_to_half_bits(v);
+}
+
+}  // namespace cvvdp

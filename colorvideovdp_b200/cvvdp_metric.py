@@ -1,0 +1,440 @@
+"""ColorVideoVDP metric object -- drop-in for ``pycvvdp.cvvdp`` on the B200 hot path.
+
+Mirrors the public surface of the reference class (pycvvdp/cvvdp_metric.py:108-1218): constructor
+arguments, ``predict`` / ``predict_video_source``, ``set_display_model``, ``do_pooling_and_jods``,
+``get_info_string``, ``write_features_to_json`` and the ``stats`` dictionary.  All arithmetic of the
+hot loop runs in the native CUDA library (csrc/) behind the C ABI of include/cvvdp_b200.h; this file
+is host-side plumbing only and raises if the library or a CUDA device is missing.
+"""
+import ctypes
+import json
+import logging
+import math
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import utils
+from .display_model import vvdp_display_geometry, vvdp_display_photo_eotf, vvdp_display_photometry
+from .video_source import video_source_array
+from .vq_metric import register_metric, vq_exception, vq_metric
+
+_TORCH_DTYPES = {torch.uint8: N.DTYPE_U8, torch.int16: N.DTYPE_U16, torch.float16: N.DTYPE_F16,
+                 torch.float32: N.DTYPE_F32}
+
+# Test hook: tests/ may inject a mock native library (tests/emu) to exercise the host logic and the
+# kernel logic on machines without a GPU.  Never set by the package itself.
+_mock_library = None
+
+
+def _set_mock_library_for_tests(library):
+    global _mock_library
+    _mock_library = library
+
+
+def _native_inputs(config_paths):
+    """cvvdp_parameters.json + csf_lut_*.json -> the parameter structs of the C ABI
+    (replaces cvvdp.load_config, cvvdp_metric.py:146-229, and castleCSF.__init__, csf.py:8-25)."""
+    parameters_file = utils.config_files.find("cvvdp_parameters.json", config_paths)
+    par = utils.json2dict(parameters_file)
+    unsupported = []
+    if par.get("masking_model") != "mult-mutual":
+        unsupported.append(f"masking_model={par.get('masking_model')}")
+    if par.get("contrast") != "weber_g1":
+        unsupported.append(f"contrast={par.get('contrast')}")
+    if par.get("dclamp_type") != "soft":
+        unsupported.append(f"dclamp_type={par.get('dclamp_type')}")
+    if par.get("xchannel_masking") != "on":
+        unsupported.append("xchannel_masking=off")
+    if par.get("temp_filter", "default") != "default" or "block_channels" in par:
+        unsupported.append("temp_filter/block_channels")
+    if unsupported:
+        raise NotImplementedError("colorvideovdp_b200 implements the shipped ColorVideoVDP model only; "
+                                  "unsupported parameters: " + ", ".join(unsupported))
+    p = N.Params()
+    for key in ("mask_p", "mask_c", "beta", "beta_t", "beta_tch", "beta_sch", "sensitivity_correction", "jod_a",
+                "jod_exp", "image_int", "ch_chrom_w", "ch_trans_w", "d_max", "pu_dilate"):
+        setattr(p, key, float(par[key]))
+    for key, n in (("mask_q", 4), ("xcm_weights", 16), ("baseband_weight", 4), ("sigma_tf", 4), ("beta_tf", 4)):
+        vals = list(par[key])
+        if len(vals) != n:
+            raise RuntimeError(f"parameter {key} must have {n} entries")
+        arr = getattr(p, key)
+        for i in range(n):
+            arr[i] = float(vals[i])
+    lut_file = utils.config_files.find(f"csf_lut_{par['csf']}.json", config_paths)
+    lut_json = utils.json2dict(lut_file)
+    lut = N.CsfLut()
+    n = N.CSF_LUT_N
+    if len(lut_json["L_bkg"]) != n or len(lut_json["rho"]) != n:
+        raise RuntimeError("CSF LUT must be 32x32")
+    for i in range(n):
+        lut.L_bkg[i] = float(lut_json["L_bkg"][i])
+        lut.rho[i] = float(lut_json["rho"][i])
+    om = lut_json["omega"]
+    names = [f"o{om[0]}_c1", f"o{om[0]}_c2", f"o{om[0]}_c3", f"o{om[1]}_c1"]  # csf.py:17-23
+    for c, name in enumerate(names):
+        table = np.asarray(lut_json[name], dtype=np.float32)
+        ctypes.memmove(lut.logS[c], np.ascontiguousarray(table).ctypes.data, n * n * 4)
+    return p, lut, par, parameters_file
+
+
+_default_cache = None
+
+
+def _default_native_inputs():
+    global _default_cache
+    if _default_cache is None:
+        _default_cache = _native_inputs([])[:2]
+    return _default_cache
+
+
+def _band_frequencies(width, height, ppd):
+    """rho_band as the reference reports it in stats (lpyr_dec.py:18-52, cvvdp_metric.py:685-686)."""
+    max_levels = int(np.floor(np.log2(min(height, width)))) - 1
+    bands = np.concatenate([[1.0], np.power(2.0, -np.arange(0.0, 14.0)) * 0.3228], 0) * ppd / 2.0
+    invalid = np.nonzero(bands <= 0.2)[0]
+    max_band = max_levels if invalid.size == 0 else invalid[0]
+    n = int(np.clip(max_band + 1, 0, max_levels))
+    freqs = np.array([1.0] + [0.3228 * 2.0 ** (-f) for f in range(n)]) * ppd / 2.0
+    freqs[n] = 0.1
+    return freqs
+
+
+def _clip_of(t, batch, frame0=0):
+    c = N.Clip()
+    c.data = t.data_ptr()
+    st = t.stride()
+    for i in range(5):
+        c.stride[i] = st[i]
+    if t.shape[0] == 1 and batch > 1:
+        c.stride[0] = 0  # singleton batch broadcast (video_source.py:247-252)
+    c.frame0, c.n_frames = frame0, t.shape[2]
+    return c
+
+
+class cvvdp(vq_metric):
+    def __init__(self, display_name="standard_4k", display_photometry=None, display_geometry=None, config_paths=[],
+                 heatmap=None, quiet=False, device=None, temp_padding="replicate", use_checkpoints=False,
+                 dump_channels=None, gpu_mem=None):
+        self.quiet = quiet
+        self.heatmap = heatmap
+        self.temp_padding = temp_padding
+        self.gpu_mem = gpu_mem  # GB of workspace the engine may use
+        self.training_mode = False
+        assert heatmap in ["threshold", "supra-threshold", "raw", "none", None], "Unknown heatmap type"
+        self.do_heatmap = (self.heatmap is not None) and (self.heatmap != "none")
+        if use_checkpoints:
+            raise NotImplementedError("use_checkpoints (autograd through the metric) is outside the scope of the "
+                                      "CUDA hot path")
+        if dump_channels:
+            raise NotImplementedError("dump_channels (debug video dumps) is outside the scope of the CUDA hot path")
+        self.dump_channels = None
+        if _mock_library is not None:
+            self.device = torch.device("cpu")  # tests only: mock device shares the host address space
+        else:
+            if device is None:
+                device = torch.device("cuda")
+            device = torch.device(device)
+            if device.type != "cuda" or not torch.cuda.is_available():
+                raise RuntimeError("colorvideovdp_b200 runs on a CUDA device only: there is no CPU fallback "
+                                   f"(requested device '{device}', torch.cuda.is_available()="
+                                   f"{torch.cuda.is_available()})")
+            if device.index is None:
+                device = torch.device("cuda", torch.cuda.current_device())
+            self.device = device
+        self._plan_key = None
+        self._info = None
+        self.set_display_model(display_name, display_photometry=display_photometry,
+                               display_geometry=display_geometry, config_paths=config_paths)
+        self.load_config(config_paths)
+
+    # ------------------------------------------------------------------------------------------
+    def train(self, do_training=True):
+        self.training_mode = do_training
+
+    def load_config(self, config_paths):
+        params, lut, par, self.parameters_file = _native_inputs(config_paths)
+        logging.debug(f"Loading ColorVideoVDP parameters from '{self.parameters_file}'")
+        self._params = params
+        self.version = par["version"]
+        # the calibrated values, exposed under the reference's attribute names
+        dev = self.device
+        for key in ("mask_p", "mask_c", "beta", "beta_t", "beta_tch", "beta_sch", "sensitivity_correction", "jod_a",
+                    "jod_exp", "image_int", "ch_chrom_w", "ch_trans_w", "d_max", "mask_q", "xcm_weights",
+                    "baseband_weight", "sigma_tf", "beta_tf"):
+            setattr(self, key, torch.as_tensor(par[key], dtype=torch.float32, device=dev))
+        self.pu_dilate = par["pu_dilate"]
+        self.masking_model = par["masking_model"]
+        self.contrast = par["contrast"]
+        dev_index = 0 if self.device.type != "cuda" else self.device.index
+        self._ctx = N.Context(params, lut, dev_index, library=_mock_library)
+        self._plan_key = None
+
+    def set_display_model(self, display_name="standard_4k", display_photometry=None, display_geometry=None,
+                          config_paths=[]):
+        if display_photometry is None:
+            self.display_photometry = vvdp_display_photometry.load(display_name, config_paths)
+            self.display_name = display_name
+        else:
+            self.display_photometry = display_photometry
+            self.display_name = getattr(display_photometry, "short_name", "unspecified")
+        if display_geometry is None:
+            self.display_geometry = vvdp_display_geometry.load(display_name, config_paths)
+        else:
+            self.display_geometry = display_geometry
+        self.pix_per_deg = self.display_geometry.get_ppd()
+        self._plan_key = None
+
+    def predict(self, test_cont, reference_cont, dim_order="BCFHW", frames_per_second=0):
+        test_vs = video_source_array(test_cont, reference_cont, frames_per_second, dim_order=dim_order,
+                                     display_photometry=self.display_photometry)
+        return self.predict_video_source(test_vs)
+
+    # ------------------------------------------------------------------------------------------
+    def _plan(self, B, H, W, F, fps, cin, dtype_id, photo):
+        """(Re)build the native plan when the job or the display changed.  photo=None: frames already
+        are DKLd65 (plugin sources), the front end passes them through."""
+        if self.temp_padding not in ("replicate", "symmetric"):
+            raise RuntimeError(f'Unknown padding method "{self.temp_padding}"')
+        if photo is None:
+            disp = vvdp_display_photo_eotf(1.0, contrast=1.0, EOTF="linear").native_display(self.pix_per_deg,
+                                                                                           passthrough=True)
+        else:
+            disp = photo.native_display(self.pix_per_deg)
+        hm = N.HEATMAP_RAW if self.do_heatmap else N.HEATMAP_NONE
+        key = (B, H, W, F, float(fps), cin, dtype_id, self.temp_padding, hm, bytes(disp), self.gpu_mem)
+        if key != self._plan_key:
+            self._ctx.set_display(disp)
+            job = N.Job(batch=B, height=H, width=W, n_frames=F, fps=float(fps), in_channels=cin, dtype=dtype_id,
+                        padding=N.PAD_REPLICATE if self.temp_padding == "replicate" else N.PAD_SYMMETRIC,
+                        heatmap=hm, max_block_frames=0,
+                        workspace_limit_bytes=int(self.gpu_mem * 1e9) if self.gpu_mem else 0)
+            self._info = self._ctx.plan(job)
+            self._plan_key = key
+        return self._info
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else None
+
+    def _needed_frames(self, f0, f1, fl, F):
+        """Clip frames the temporal stage reads for outputs [f0, f1) (cvvdp_metric.py:501-529)."""
+        lo, hi = f1 - 1, f1
+        for t in range(f0 - (fl - 1), f1):
+            s = t
+            if s < 0:
+                s = 0 if self.temp_padding == "replicate" else self._get_symmetric_frame_index(s, F)
+            lo, hi = min(lo, s), max(hi, s + 1)
+        return lo, hi
+
+    def _get_symmetric_frame_index(self, frame_ind, frame_count):
+        """cvvdp_metric.py:445-450"""
+        is_even = (math.floor((abs(frame_ind) - 1) / (frame_count - 1)) % 2) == 0
+        if is_even:
+            return ((abs(frame_ind) - 1) % (frame_count - 1)) + 1
+        return frame_ind % (frame_count - 1)
+
+    def compute_q_per_ch(self, vid_source, frame_range=None):
+        """The hot loop: Q_per_ch [B,C,F,L] (torch, on the metric's device; frames outside `frame_range`
+        are zero) and the raw heat map (fp16 [1,1,F,H,W] on the device, or None)."""
+        H, W, F = vid_source.get_video_size()
+        B = vid_source.get_batch_size()
+        if B > 1 and self.do_heatmap:
+            raise vq_exception("Heatmaps not supported when batches are used")
+        if getattr(vid_source, "is_temporally_filtered", False):
+            raise NotImplementedError("pre-filtered video sources ('DKLd65_trans') are not supported")
+        fps = vid_source.get_frames_per_second() if F > 1 else 0
+        f0, f1 = (0, F) if frame_range is None else frame_range
+        fast = type(vid_source) is video_source_array and type(vid_source.dm_photometry) is vvdp_display_photo_eotf
+        if fast:
+            return self._run_arrays(vid_source, B, H, W, F, fps, f0, f1)
+        return self._run_plugin(vid_source, B, H, W, F, fps, f0, f1)
+
+    def _alloc_outputs(self, B, C, F, L, H, W):
+        Q = torch.zeros((B, C, F, L), dtype=torch.float32, device=self.device)
+        hm = torch.zeros((1, 1, F, H, W), dtype=torch.float16, device=self.device) if self.do_heatmap else None
+        return Q, hm
+
+    def _run_arrays(self, vs, B, H, W, F, fps, f0, f1):
+        """Fast path: raw clip tensors, display model fused into the CUDA front end."""
+        test, ref = vs.test_video, vs.reference_video
+        if test.dtype != ref.dtype:
+            raise RuntimeError("Test and reference must have the same dtype")
+        if vs.dm_photometry is not self.display_photometry and vs.dm_photometry != self.display_photometry:
+            logging.warning("video source and metric use different display models; using the video source's")
+        info = self._plan(B, H, W, F, fps, test.shape[1], _TORCH_DTYPES[test.dtype], vs.dm_photometry)
+        C, L = info.n_channels, info.n_bands
+        on_device = test.device == self.device and ref.device == self.device
+        if on_device:
+            Q, hm = self._alloc_outputs(B, C, F, L, H, W)
+            self._ctx.process_device(_clip_of(test, B), _clip_of(ref, B), f0, f1, Q.data_ptr(),
+                                     hm.data_ptr() if hm is not None else None, self._stream())
+            return Q, hm
+        if test.device.type != "cpu" or ref.device.type != "cpu":
+            test, ref = test.to(self.device), ref.to(self.device)
+            Q, hm = self._alloc_outputs(B, C, F, L, H, W)
+            self._ctx.process_device(_clip_of(test, B), _clip_of(ref, B), f0, f1, Q.data_ptr(),
+                                     hm.data_ptr() if hm is not None else None, self._stream())
+            return Q, hm
+        # host clips: streamed upload overlapped with compute inside the native library
+        pin = self.device.type == "cuda"
+        Qh = torch.zeros((B, C, F, L), dtype=torch.float32, pin_memory=pin)
+        hmh = torch.zeros((1, 1, F, H, W), dtype=torch.float16, pin_memory=pin) if self.do_heatmap else None
+        try:
+            self._ctx.process_host(_clip_of(test, B), _clip_of(ref, B), f0, f1, Qh.data_ptr(),
+                                   hmh.data_ptr() if hmh is not None else None)
+        except N.NativeError as e:
+            if "densely" not in str(e):
+                raise
+            test, ref = test.contiguous(), ref.contiguous()  # exotic layout: normalise to BCFHW first
+            self._ctx.process_host(_clip_of(test, B), _clip_of(ref, B), f0, f1, Qh.data_ptr(),
+                                   hmh.data_ptr() if hmh is not None else None)
+        return Qh, hmh
+
+    def _run_plugin(self, vs, B, H, W, F, fps, f0, f1):
+        """Any third-party video_source: frames are pulled through get_*_frame(..., 'DKLd65'), strictly in
+        increasing order and reference before test, and enter the CUDA path at the temporal stage (the
+        display model is the plugin's business)."""
+        fl = 1 if F == 1 else int(math.ceil(0.250 * fps / 2) * 2) + 1  # cvvdp_metric.py:1059
+        cache_t, cache_r = {}, {}
+
+        def fetch(f):
+            if f not in cache_r:
+                cache_r[f] = vs.get_reference_frame(f, device=self.device, colorspace="DKLd65").to(
+                    device=self.device, dtype=torch.float32)
+                cache_t[f] = vs.get_test_frame(f, device=self.device, colorspace="DKLd65").to(
+                    device=self.device, dtype=torch.float32)
+            return cache_t[f], cache_r[f]
+
+        first_lo, _ = self._needed_frames(f0, f0 + 1, fl, F)
+        cin = fetch(first_lo)[1].shape[1]
+        info = self._plan(B, H, W, F, fps, cin, N.DTYPE_F32, None)
+        assert info.filter_len == fl
+        Q, hm = self._alloc_outputs(B, info.n_channels, F, info.n_bands, H, W)
+        nb = info.block_frames
+        cur = f0
+        while cur < f1:
+            end = min(cur + nb, f1)
+            lo, hi = self._needed_frames(cur, end, fl, F)
+            frames = [fetch(f) for f in range(lo, hi)]
+            win_t = torch.cat([fr[0] for fr in frames], dim=2)
+            win_r = torch.cat([fr[1] for fr in frames], dim=2)
+            self._ctx.process_device(_clip_of(win_t, B, lo), _clip_of(win_r, B, lo), cur, end, Q.data_ptr(),
+                                     hm.data_ptr() if hm is not None else None, self._stream())
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()  # the windows are released below
+            cur = end
+            if cur < f1:
+                keep_lo, _ = self._needed_frames(cur, min(cur + nb, f1), fl, F)
+                for f in [k for k in cache_r if k < keep_lo]:
+                    cache_t.pop(f), cache_r.pop(f)
+        return Q, hm
+
+    # ------------------------------------------------------------------------------------------
+    def predict_video_source(self, vid_source, frame_range=None):
+        """JOD and statistics for the clip of `vid_source` (cvvdp_metric.py:304-441).  `frame_range`
+        restricts the frames evaluated by this process (frame sharding, see distributed.py); the JOD then
+        only covers those frames unless the caller all-reduces stats['Q_per_ch'] first."""
+        H, W, F = vid_source.get_video_size()
+        Q_per_ch, heatmap = self.compute_q_per_ch(vid_source, frame_range)
+        Q_jod = self.do_pooling_and_jods(Q_per_ch if frame_range is None else Q_per_ch[:, :, frame_range[0]:frame_range[1]])
+        stats = self._make_stats(Q_per_ch, heatmap, vid_source, H, W, F)
+        return (Q_jod.squeeze(), stats)
+
+    def _make_stats(self, Q_per_ch, heatmap, vid_source, H, W, F):
+        stats = {}
+        stats["Q_per_ch"] = Q_per_ch.detach().cpu().numpy()
+        stats["rho_band"] = _band_frequencies(W, H, self.pix_per_deg)
+        stats["frames_per_second"] = vid_source.get_frames_per_second()
+        stats["width"] = W
+        stats["height"] = H
+        stats["N_frames"] = F
+        if self.do_heatmap:
+            hm = heatmap.detach().cpu()
+            if self.heatmap != "raw":
+                from .visualize_diff_map import colorize_heatmap
+                hm = colorize_heatmap(hm, vid_source, self.heatmap, self.device)
+            stats["heatmap"] = hm
+        return stats
+
+    def get_ch_weights(self, no_channels):
+        w = torch.stack([torch.as_tensor(1.0, device=self.ch_chrom_w.device), self.ch_chrom_w, self.ch_chrom_w,
+                         self.ch_trans_w])
+        return w[0:no_channels].view(1, -1, 1, 1)
+
+    def do_pooling_and_jods(self, Q_per_ch):
+        """Pool Q_per_ch [B,C,F,L] over bands, channels and frames and map to JOD
+        (cvvdp_metric.py:610-643); runs in the native pooling kernel."""
+        if isinstance(Q_per_ch, np.ndarray):
+            Q_per_ch = torch.from_numpy(np.ascontiguousarray(Q_per_ch, dtype=np.float32))
+        Q = Q_per_ch.detach().to(torch.float32).contiguous()
+        B, C, F, L = Q.shape
+        if Q.device == self.device and self.device.type == "cuda":
+            jod = torch.empty((B,), dtype=torch.float32, device=self.device)
+            self._ctx.pool_device(Q.data_ptr(), B, C, F, L, jod.data_ptr(), self._stream())
+            return jod.squeeze()
+        Qh = Q.cpu()
+        jod = torch.empty((B,), dtype=torch.float32)
+        self._ctx.pool(Qh.data_ptr(), B, C, F, L, jod.data_ptr())
+        return jod.to(self.device).squeeze()
+
+    def met2jod(self, Q):
+        """cvvdp_metric.py:646-658 (tiny, element-wise; host tensors or device tensors alike)."""
+        Q = torch.as_tensor(Q)
+        Q_t = 0.1
+        jod_a, jod_exp = float(self.jod_a), float(self.jod_exp)
+        jod_a_p = jod_a * (Q_t ** (jod_exp - 1.0))
+        return torch.where(Q <= Q_t, 10.0 - jod_a_p * Q, 10.0 - jod_a * Q.clamp(min=Q_t) ** jod_exp)
+
+    def full_name(self):
+        return "ColorVideoVDP"
+
+    def quality_unit(self):
+        return "JOD"
+
+    def short_name(self):
+        return "cvvdp"
+
+    def get_info_string(self):
+        if self.display_name.startswith("standard_"):
+            standard_str = self.display_name
+        else:
+            standard_str = f"custom-display: {self.display_name}"
+        L_black, L_refl = self.display_photometry.get_black_level()
+        return f'"{self.full_name()} v{self.version}, {self.pix_per_deg:.4g} [pix/deg], ' \
+               f'Lpeak={self.display_photometry.get_peak_luminance():.5g}, ' \
+               f'Lblack={L_black:.4g}, Lrefl={L_refl:.4g} [cd/m^2], ({standard_str})"'
+
+    def write_features_to_json(self, stats, dest_fname):
+        """cvvdp_metric.py:1112-1127: per-channel/per-band features `t{c}_b{b}` for calibration/."""
+        Q_per_ch = stats["Q_per_ch"]
+        fmap = {}
+        for key, value in stats.items():
+            if key not in ["Q_per_ch", "heatmap"]:
+                fmap[key] = value.tolist() if isinstance(value, np.ndarray) else value
+        for cc in range(Q_per_ch.shape[1]):
+            for bb in range(Q_per_ch.shape[3]):
+                fmap[f"t{cc}_b{bb}"] = Q_per_ch[:, cc, :, bb].tolist()
+        with open(dest_fname, "w", encoding="utf-8") as f:
+            json.dump(fmap, f, ensure_ascii=False, indent=4)
+
+    def distogram_array(self, stats):
+        """Numeric part of export_distogram (cvvdp_metric.py:1160-1170): per channel/frame/band JOD loss."""
+        Q = torch.as_tensor(stats["Q_per_ch"], dtype=torch.float32).clone()
+        if Q.shape[0] != 1:
+            raise vq_exception("Exporting distograms in batch mode is not supported")
+        ch_no = Q.shape[1]
+        Q[:, :, :, -1] *= self.baseband_weight[0:ch_no].cpu().view(-1, 1)
+        Q *= self.get_ch_weights(ch_no).cpu() * ch_no
+        return (10.0 - self.met2jod(Q)).numpy()
+
+    def export_distogram(self, stats, fname, jod_max=None, base_size=6):
+        try:
+            import matplotlib.pyplot as plt  # noqa: F401
+        except Exception:
+            raise RuntimeError("matplotlib is missing. Please install it before exporting distograms.")
+        raise NotImplementedError("plotting is outside the scope of the CUDA hot path; use distogram_array(stats)")
+
+
+register_metric(cvvdp)

@@ -1,0 +1,173 @@
+/*
+ * cvvdp_b200.h -- C ABI of the B200-native ColorVideoVDP hot path (libcvvdp_b200.so).
+ *
+ * The reference (gfxdisp/ColorVideoVDP, pure Python/PyTorch) has no FFI; the entry points below are
+ * what a binding for its hot path binds.  Each one names the reference interface it replaces
+ * (paths relative to the reference tree).  Plain pointers and sizes only: no torch types, no C++
+ * types, no exceptions across the boundary.  Every function returns CVVDP_OK (0) or a negative
+ * error code; cvvdp_b200_last_error() gives the message.  One context = one CUDA device, not
+ * re-entrant (same contract as one `pycvvdp.cvvdp` object, cvvdp_metric.py:108-140).
+ *
+ * Pointers named *_dev are device pointers on the context's device, *_host are host pointers.
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ */
+#ifndef CVVDP_B200_H
+#define CVVDP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVVDP_B200_ABI_VERSION 1
+#define CVVDP_MAX_BANDS 16
+#define CVVDP_MAX_FILTER_LEN 129
+#define CVVDP_CSF_LUT_N 32
+
+enum { CVVDP_OK = 0, CVVDP_ERR_INVALID = -1, CVVDP_ERR_CUDA = -2, CVVDP_ERR_NOMEM = -3, CVVDP_ERR_STATE = -4,
+       CVVDP_ERR_UNSUPPORTED = -5 };
+
+/* Input element types accepted by video_source_array._get_frame (video_source.py:324-342). */
+enum { CVVDP_DTYPE_U8 = 0,   /* /255 */
+       CVVDP_DTYPE_U16 = 1,  /* uint16 (or int16 bit pattern, "& 0xFFFF"), /65535 */
+       CVVDP_DTYPE_F16 = 2, CVVDP_DTYPE_F32 = 3 };
+
+/* EOTFs of vvdp_display_photo_eotf.forward (display_model.py:333-365). */
+enum { CVVDP_EOTF_SRGB = 0, CVVDP_EOTF_PQ = 1, CVVDP_EOTF_LINEAR = 2, CVVDP_EOTF_HLG = 3, CVVDP_EOTF_GAMMA = 4,
+       CVVDP_EOTF_NONE = 5 /* input already is DKLd65 (frames from a third-party video_source plugin) */ };
+
+/* Temporal padding (cvvdp_metric.py:506-532). */
+enum { CVVDP_PAD_REPLICATE = 0, CVVDP_PAD_SYMMETRIC = 1 };
+
+/* Target colour spaces of cvvdp_b200_frontend (linear_2_target_colorspace, display_model.py:241-276). */
+enum { CVVDP_CS_DKLD65 = 0, CVVDP_CS_RGB_LINEAR = 1 /* forward() only */, CVVDP_CS_XYZ = 2, CVVDP_CS_LMS2006 = 3 };
+
+/* Heat map (cvvdp_metric.py:117,396-401).  Only the partition-independent raw map is produced natively. */
+enum { CVVDP_HEATMAP_NONE = 0, CVVDP_HEATMAP_RAW = 1 };
+
+/* cvvdp_parameters.json (cvvdp_metric.py:146-229).  Replaces cvvdp.load_config. */
+typedef struct {
+    float mask_p, mask_c;
+    float mask_q[4];
+    float xcm_weights[16];           /* log2 weights, 4x4 row-major [source ch][masked ch] (cvvdp_metric.py:758) */
+    float beta, beta_t, beta_tch, beta_sch;
+    float sensitivity_correction;    /* dB */
+    float jod_a, jod_exp;
+    float image_int;
+    float ch_chrom_w, ch_trans_w;
+    float baseband_weight[4];
+    float d_max;                     /* log10 */
+    float sigma_tf[4], beta_tf[4];
+    float pu_dilate;                 /* sigma of the phase-uncertainty Gaussian; kernel = 4*sigma+1 taps */
+} cvvdp_b200_params;
+
+/* csf_lut_<version>.json (csf.py:8-23): log10-sensitivity tables [L_bkg][rho] for the four
+ * perceptual channels A-sust (o0_c1), RG (o0_c2), YV (o0_c3), A-trans (o5_c1). */
+typedef struct {
+    float L_bkg[CVVDP_CSF_LUT_N];
+    float rho[CVVDP_CSF_LUT_N];
+    float logS[4][CVVDP_CSF_LUT_N][CVVDP_CSF_LUT_N];
+} cvvdp_b200_csf_lut;
+
+/* Display photometry + geometry (display_model.py:301-376, 503-526).  Replaces
+ * vvdp_display_photo_eotf / vvdp_display_geometry as seen by cvvdp.set_display_model. */
+typedef struct {
+    int32_t eotf;            /* CVVDP_EOTF_* */
+    float gamma;             /* CVVDP_EOTF_GAMMA: exponent; CVVDP_EOTF_HLG: system gamma */
+    float Y_peak, contrast, E_ambient, k_refl, exposure;
+    float rgb2xyz[9];        /* row-major RGB2X, RGB2Y, RGB2Z (color_spaces.json) */
+    float ppd;               /* pixels per visual degree */
+} cvvdp_b200_display;
+
+/* One prediction job (what cvvdp.predict_video_source derives from the video source, cvvdp_metric.py:304-355). */
+typedef struct {
+    int32_t batch;           /* B */
+    int32_t height, width;   /* H, W */
+    int32_t n_frames;        /* F of the whole clip (1 = image) */
+    float fps;               /* 0 for images */
+    int32_t in_channels;     /* 1 or 3 */
+    int32_t dtype;           /* CVVDP_DTYPE_* */
+    int32_t padding;         /* CVVDP_PAD_* */
+    int32_t heatmap;         /* CVVDP_HEATMAP_* */
+    int32_t max_block_frames;/* frames per pass (0 = choose from the workspace budget) */
+    int64_t workspace_limit_bytes; /* 0 = default */
+} cvvdp_b200_job;
+
+typedef struct {
+    int32_t n_bands;         /* L */
+    int32_t n_channels;      /* C: 3 image, 4 video */
+    int32_t filter_len;      /* fl (1 for images) */
+    int32_t block_frames;    /* frames processed per pass */
+    float rho_band[CVVDP_MAX_BANDS];       /* cpd; baseband already 0.1 (cvvdp_metric.py:685-686) */
+    int32_t band_height[CVVDP_MAX_BANDS], band_width[CVVDP_MAX_BANDS];
+    float filters[4][CVVDP_MAX_FILTER_LEN]; /* temporal filters F[c][0..fl-1] (cvvdp_metric.py:1057-1092) */
+    int64_t workspace_bytes;
+} cvvdp_b200_plan_info;
+
+/* A strided view of a [B,C,F,H,W] clip: strides in ELEMENTS; batch stride 0 broadcasts a singleton
+ * batch (video_source.py:247-252).  `frame0` is the clip frame index stored at F-index 0 of the view
+ * and `n_frames` how many frames the view holds, so a caller may pass a window of a longer clip. */
+typedef struct {
+    const void *data;
+    int64_t stride[5];       /* B, C, F, H, W */
+    int32_t frame0, n_frames;
+} cvvdp_b200_clip;
+
+typedef struct cvvdp_b200_ctx cvvdp_b200_ctx;
+
+/* ABI / build information: returns CVVDP_B200_ABI_VERSION. */
+int cvvdp_b200_abi_version(void);
+/* Message of the last error on this context (or the last create error when ctx is NULL). */
+const char *cvvdp_b200_last_error(const cvvdp_b200_ctx *ctx);
+
+/* cvvdp.__init__/load_config (cvvdp_metric.py:109-229) + castleCSF.__init__ (csf.py:8-25). */
+int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut *lut, int device,
+                      cvvdp_b200_ctx **out);
+void cvvdp_b200_destroy(cvvdp_b200_ctx *ctx);
+
+/* cvvdp.set_display_model (cvvdp_metric.py:246-264). */
+int cvvdp_b200_set_display(cvvdp_b200_ctx *ctx, const cvvdp_b200_display *display);
+
+/* The per-clip set-up of predict_video_source (cvvdp_metric.py:317-355): pyramid shape
+ * (lpyr_dec.py:18-52), temporal filters (1057-1092), CSF rows per band (csf.py:38-46), block size
+ * (565-594), workspace allocation. */
+int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_plan_info *info);
+
+/* The hot loop (cvvdp_metric.py:374-392 = read_block_of_frames 453-561 + process_block_of_frames
+ * 660-751) for clip frames [frame_begin, frame_end) with test/reference views resident in HBM.
+ * Writes Q_per_ch[b][c][f][band] for those frames into q_per_ch_dev (fp32, full [B,C,F,L] layout,
+ * other frames untouched) and, when planned, the raw heat map [1,1,F,H,W] fp16 into heatmap_dev.
+ * Asynchronous on `stream`. */
+int cvvdp_b200_process_device(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref,
+                              int frame_begin, int frame_end, float *q_per_ch_dev, void *heatmap_dev,
+                              void *stream);
+
+/* Same, with test/reference in HOST memory (pinned for full overlap): frames are uploaded in blocks
+ * on a copy stream overlapped with compute, results are returned to host memory, and the call
+ * returns after everything has completed.  q_per_ch_host: [B,C,F,L] fp32; heatmap_host: fp16 or NULL. */
+int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref,
+                            int frame_begin, int frame_end, float *q_per_ch_host, void *heatmap_host);
+
+/* do_pooling_and_jods + met2jod (cvvdp_metric.py:610-658) on a host Q_per_ch [B,C,F,L]; jod_host: [B]. */
+int cvvdp_b200_pool(cvvdp_b200_ctx *ctx, const float *q_per_ch_host, int B, int C, int F, int L, float *jod_host);
+/* Same on device buffers, asynchronous on `stream` (used right after process_device / the all-reduce). */
+int cvvdp_b200_pool_device(cvvdp_b200_ctx *ctx, const float *q_per_ch_dev, int B, int C, int F, int L,
+                           float *jod_dev, void *stream);
+
+/* vvdp_display_photometry.source_2_target_colorspace(frame, colorspace) for one strided [B,C,1,H,W]
+ * frame (display_model.py:206-276 + video_source.py:320-346): dst_dev is dense fp32 [B,3 or 1,H,W];
+ * colorspace is a CVVDP_CS_* id (CVVDP_CS_RGB_LINEAR = vvdp_display_photo_eotf.forward alone).
+ * Also counts values outside 0..1 / NaN / Inf (the warnings of display_model.py:335-337 and
+ * video_source.py:48-59) into flags_dev[0..2] when not NULL. */
+int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int batch, int in_channels, int height,
+                        int width, int dtype, int frame, int colorspace, float *dst_dev, int32_t *flags_dev,
+                        void *stream);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVVDP_B200_H */

@@ -1,0 +1,153 @@
+"""Kernel + host logic on the mock device (tests/emu): the *same* CUDA sources compiled for the CPU,
+checked against the reference-generated fixtures and the numpy oracle.  This is what keeps tile/halo
+indexing, padding rules and the host orchestration honest on a machine without a GPU; numerics of
+the real MUFU paths are covered by the -m gpu tests."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import synth
+from emu_util import mock_device  # noqa: F401
+from oracle import cvvdp_oracle as O
+
+import colorvideovdp_b200 as cv
+
+
+@pytest.mark.parametrize("name", gu.case_names())
+def test_golden_cases_on_mock_device(name, mock_device):
+    z, meta = gu.load_case(name)
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"], heatmap=meta["heatmap"])
+    jod, stats = m.predict(z["test"], z["ref"], dim_order=meta["dim_order"], frames_per_second=meta["fps"])
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert np.max(np.abs(np.asarray(jod, dtype=np.float64) - z["jod"])) <= gu.JOD_TOL
+    assert np.allclose(stats["rho_band"], z["rho_band"])
+    assert stats["N_frames"] == z["Q_per_ch"].shape[2]
+    if meta["heatmap"] == "raw":
+        hm = stats["heatmap"]
+        assert hm.dtype == torch.float16 and tuple(hm.shape) == z["heatmap"].shape
+        assert np.max(np.abs(hm.float().numpy() - z["heatmap"].astype(np.float32))) <= gu.HEATMAP_ATOL
+
+
+def test_identical_pair_is_exactly_10(mock_device):
+    tst, ref = synth.make_pair_u8(3, 4, 40, 56)
+    m = cv.cvvdp(display_name="standard_fhd")
+    jod, stats = m.predict(ref, ref, frames_per_second=30)
+    assert float(jod) == 10.0
+    assert np.all(stats["Q_per_ch"] == 0)
+
+
+def test_frame_blocks_and_ranges_are_partition_independent(mock_device):
+    """Blocking (gpu_mem limit -> 1..n frames per pass) and frame ranges must not change any value."""
+    tst, ref = synth.make_pair_u8(4, 9, 36, 48)
+    m = cv.cvvdp(display_name="standard_fhd", temp_padding="symmetric")
+    _, full = m.predict(tst, ref, frames_per_second=24)
+    small = cv.cvvdp(display_name="standard_fhd", temp_padding="symmetric", gpu_mem=1e-6)  # -> 1 frame per block
+    _, blk = small.predict(tst, ref, frames_per_second=24)
+    assert small._info.block_frames == 1
+    assert np.array_equal(full["Q_per_ch"], blk["Q_per_ch"])
+    vs = cv.video_source_array(tst, ref, 24, display_photometry=m.display_photometry)
+    Qa, _ = m.compute_q_per_ch(vs, (0, 4))
+    Qb, _ = m.compute_q_per_ch(vs, (4, 9))
+    assert np.array_equal((Qa + Qb).numpy(), full["Q_per_ch"])
+
+
+def test_dim_orders_and_strided_views(mock_device):
+    tst, ref = synth.make_pair_u8(5, 1, 33, 47)
+    m = cv.cvvdp(display_name="standard_4k")
+    j0, s0 = m.predict(tst, ref, dim_order="BCFHW")
+    hwc_t = np.ascontiguousarray(tst[0, :, 0].transpose(1, 2, 0))
+    hwc_r = np.ascontiguousarray(ref[0, :, 0].transpose(1, 2, 0))
+    j1, s1 = m.predict(hwc_t, hwc_r, dim_order="HWC")
+    whc_t, whc_r = np.ascontiguousarray(hwc_t.transpose(1, 0, 2)), np.ascontiguousarray(hwc_r.transpose(1, 0, 2))
+    j2, s2 = m.predict(whc_t, whc_r, dim_order="WHC")
+    assert np.array_equal(s0["Q_per_ch"], s1["Q_per_ch"]) and np.array_equal(s0["Q_per_ch"], s2["Q_per_ch"])
+    assert float(j0) == float(j1) == float(j2)
+
+
+def test_plugin_video_source_matches_fast_path(mock_device):
+    """A third-party video_source (frames pulled one by one in DKLd65) must agree with the fused path."""
+    tst, ref = synth.make_pair_u8(6, 7, 36, 52)
+    m = cv.cvvdp(display_name="standard_fhd")
+    _, fast = m.predict(tst, ref, frames_per_second=30)
+    dm, P = O.Display("standard_fhd"), None
+
+    class OracleFrontendSource(cv.video_source):
+        def get_video_size(self):
+            return (36, 52, 7)
+
+        def get_frames_per_second(self):
+            return 30
+
+        def _frame(self, arr, f, device):
+            return torch.from_numpy(O.frontend(arr[:, :, f], dm))[:, :, None].to(device)
+
+        def get_test_frame(self, f, device, colorspace):
+            assert colorspace == "DKLd65"
+            return self._frame(tst, f, device)
+
+        def get_reference_frame(self, f, device, colorspace):
+            return self._frame(ref, f, device)
+
+    _, plug = m.predict_video_source(OracleFrontendSource())
+    gu.assert_q_close(plug["Q_per_ch"], fast["Q_per_ch"], "plugin vs fast")
+
+
+def test_display_model_forward_on_mock_device(mock_device):
+    """display_model plugin surface: forward() and source_2_target_colorspace('DKLd65')."""
+    rng = np.random.default_rng(0)
+    V = rng.random((2, 3, 1, 20, 24), dtype=np.float32)
+    for name in ("standard_4k", "standard_hdr_pq", "standard_hdr_linear", "standard_hdr_hlg"):
+        dm = cv.vvdp_display_photometry.load(name, [])
+        odm = O.Display(name)
+        # the mock device has no CUDA: call the kernel wrapper directly on CPU tensors
+        from colorvideovdp_b200 import _native as N
+        from colorvideovdp_b200.cvvdp_metric import _default_native_inputs
+        import emu_util
+        ctx = N.Context(*_default_native_inputs(), 0, library=emu_util.emu_library())
+        ctx.set_display(dm.native_display())
+        Vt = torch.from_numpy(V)
+        out = torch.empty((2, 3, 20, 24))
+        clip = N.Clip()
+        clip.data = Vt.data_ptr()
+        for i, s in enumerate(Vt.stride()):
+            clip.stride[i] = s
+        clip.frame0, clip.n_frames = 0, 1
+        ctx.frontend(clip, 2, 3, 20, 24, N.DTYPE_F32, 0, N.CS_RGB_LINEAR, out.data_ptr(), None, None)
+        L_ref = O.eotf_forward(V[:, :, 0], odm)
+        assert np.max(np.abs(out.numpy() - L_ref) / np.abs(L_ref)) < 1e-4, name
+        ctx.frontend(clip, 2, 3, 20, 24, N.DTYPE_F32, 0, N.CS_DKLD65, out.data_ptr(), None, None)
+        D_ref = O.frontend(V[:, :, 0], odm)
+        assert np.max(np.abs(out.numpy() - D_ref)) < 1e-4 * np.abs(D_ref).max(), name
+        ctx.close()
+
+
+def test_pooling_entry_point_matches_oracle(mock_device):
+    rng = np.random.default_rng(1)
+    m = cv.cvvdp(display_name="standard_4k")
+    P = O.Params()
+    for shape in [(1, 3, 1, 8), (2, 4, 17, 9), (3, 4, 300, 5)]:
+        Q = (rng.random(shape) * 2).astype(np.float32)
+        Q[0, 0, 0, 0] = 0
+        jod = m.do_pooling_and_jods(Q)
+        ref = O.do_pooling_and_jods(Q, P)
+        assert np.allclose(np.atleast_1d(jod.numpy()), ref, atol=2e-5)
+
+
+def test_error_behaviour(mock_device):
+    m = cv.cvvdp(display_name="standard_4k")
+    a = np.zeros((1, 3, 4, 32, 32), np.uint8)
+    with pytest.raises(RuntimeError, match="frames_per_second"):
+        m.predict(a, a)  # video without fps (video_source.py:279-280)
+    with pytest.raises(RuntimeError, match="1 or 3 color channels"):
+        m.predict(np.zeros((1, 2, 1, 32, 32), np.uint8), np.zeros((1, 2, 1, 32, 32), np.uint8))
+    with pytest.raises(RuntimeError, match="same shape"):
+        m.predict(np.zeros((1, 3, 1, 32, 32), np.uint8), np.zeros((1, 3, 1, 32, 40), np.uint8))
+    hm = cv.cvvdp(display_name="standard_4k", heatmap="raw")
+    with pytest.raises(cv.vq_exception):
+        hm.predict(np.zeros((2, 3, 1, 32, 32), np.uint8), np.zeros((2, 3, 1, 32, 32), np.uint8))
+    bad = cv.cvvdp(display_name="standard_4k", temp_padding="valid")
+    with pytest.raises(RuntimeError, match="padding"):
+        bad.predict(a, a, frames_per_second=30)
+    with pytest.raises(RuntimeError, match="Display model not found"):
+        cv.cvvdp(display_name="no_such_display")
