@@ -76,7 +76,16 @@ SYMBOLS = {
     "cvvdp_b200_frontend": (C.c_int, [C.c_void_p, C.POINTER(Clip), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_launch_count": (C.c_int64, [C.c_void_p]),
+    "cvvdp_b200_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "cvvdp_b200_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
 }
+
+KERNEL_KINDS = ["temporal", "reduce", "band", "baseband", "finalize", "heatmap", "pool", "frontend"]
+
+
+class KernelStat(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("launches", C.c_int32), ("total_ms", C.c_float),
+                ("algo_bytes", C.c_double)]
 
 ABI_VERSION = 1
 
@@ -166,3 +175,14 @@ class Context:
 
     def launch_count(self):
         return int(self._lib.cvvdp_b200_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.cvvdp_b200_profile_enable(self._h, 1 if on else 0), "profile_enable")
+
+    def profile_read(self):
+        """[{kind, level, launches, total_ms, algo_bytes}] since the last read (synchronises the device)."""
+        buf = (KernelStat * 128)()
+        n = C.c_int(0)
+        self._check(self._lib.cvvdp_b200_profile_read(self._h, buf, 128, C.byref(n)), "profile_read")
+        return [dict(kind=KERNEL_KINDS[buf[i].kind], level=buf[i].level, launches=buf[i].launches,
+                     total_ms=float(buf[i].total_ms), algo_bytes=float(buf[i].algo_bytes)) for i in range(n.value)]

@@ -56,6 +56,13 @@ struct cvvdp_b200_ctx {
     void *hm_dev = nullptr;
     size_t hm_dev_bytes = 0;
     long long launches = 0;
+    bool prof = false;
+    struct ProfRec {
+        int kind, level;
+        double bytes;
+        cudaEvent_t a, b;
+    };
+    std::vector<ProfRec> prof_recs;
     std::string err;
 };
 
@@ -81,6 +88,29 @@ int fail(cvvdp_b200_ctx *ctx, int code, const char *fmt, ...) {
     } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Brackets one kernel launch with events when profiling is on; always counts the launch.
+struct LaunchScope {
+    cvvdp_b200_ctx *ctx;
+    cudaStream_t st;
+    cudaEvent_t b = nullptr;
+    LaunchScope(cvvdp_b200_ctx *c, cudaStream_t s, int kind, int level, double bytes) : ctx(c), st(s) {
+        ctx->launches++;
+        if (!ctx->prof) return;
+        cvvdp_b200_ctx::ProfRec r;
+        r.kind = kind;
+        r.level = level;
+        r.bytes = bytes;
+        cudaEventCreateWithFlags(&r.a, 0);
+        cudaEventCreateWithFlags(&r.b, 0);
+        cudaEventRecord(r.a, st);
+        b = r.b;
+        ctx->prof_recs.push_back(r);
+    }
+    ~LaunchScope() {
+        if (b) cudaEventRecord(b, st);
+    }
+};
 
 void free_plan(cvvdp_b200_ctx *ctx) {
     if (ctx->arena) cudaFree(ctx->arena);
@@ -298,8 +328,11 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         dim3 grid((unsigned)((npix + CVVDP_TEMPORAL_THREADS - 1) / CVVDP_TEMPORAL_THREADS), (unsigned)(B * 2));
         const size_t smem = (size_t)info.filter_len * 3 * CVVDP_TEMPORAL_THREADS * sizeof(float);
         auto kfn = k_temporal;
+        int wlo, whi;
+        needed_frames(ctx, f0, f1, &wlo, &whi);
+        const double bytes = (double)npix * B * 2 * ((double)(whi - wlo) * job.in_channels * dtype_size(job.dtype) + 16.0 * n);
+        LaunchScope ls(ctx, st, CVVDP_K_TEMPORAL, 0, bytes);
         CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
-        ctx->launches++;
     }
     // ---- Gaussian pyramid ----
     for (int i = 0; i + 1 < L; ++i) {
@@ -312,8 +345,8 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ra.wc = ctx->lv[i + 1].w;
         dim3 grid((ra.wc + CVVDP_RTX - 1) / CVVDP_RTX, (ra.hc + CVVDP_RTY - 1) / CVVDP_RTY, pairs * 2);
         auto kfn = k_reduce;
+        LaunchScope ls(ctx, st, CVVDP_K_REDUCE, i, (double)pairs * 2 * 16.0 * ((double)ra.h * ra.w + (double)ra.hc * ra.wc));
         CVVDP_LAUNCH(kfn, grid, dim3(256), 0, st, ra);
-        ctx->launches++;
     }
     // ---- bands ----
     const bool is_image = job.n_frames == 1;
@@ -353,8 +386,10 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ba.hm_scale = (i == 0) ? 1.f : 0.5f;
         dim3 grid(lv.tiles_x, lv.tiles_y, pairs);
         auto kfn = k_band;
+        LaunchScope ls(ctx, st, CVVDP_K_BAND, i,
+                       (double)pairs * 2 * 16.0 * ((double)ba.h * ba.w + (double)ba.hc * ba.wc) +
+                           (do_hm ? (double)pairs * 4.0 * ba.h * ba.w : 0.0));
         CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_BAND_THREADS), sizeof(BandSmem), st, ba);
-        ctx->launches++;
     }
     {
         BasebandArgs bb;
@@ -374,8 +409,8 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         for (int c = 0; c < 4; ++c) bb.hm_w[c] = ch_w[c] * t_int * P.baseband_weight[c];
         bb.hm_beta = P.beta_tch;
         auto kfn = k_baseband;
+        LaunchScope ls(ctx, st, CVVDP_K_BASEBAND, L - 1, (double)pairs * 2 * 16.0 * bb.npix);
         CVVDP_LAUNCH(kfn, dim3(pairs), dim3(256), 0, st, bb);
-        ctx->launches++;
     }
     // ---- spatial pooling epilogue -> Q_per_ch ----
     {
@@ -397,8 +432,10 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         fa.Q = q_dev;
         const int warps = pairs * L;
         auto kfn = k_finalize;
+        double pbytes = 0;
+        for (int i = 0; i < L; ++i) pbytes += (double)pairs * fa.ntiles[i] * 16.0;
+        LaunchScope ls(ctx, st, CVVDP_K_FINALIZE, 0, pbytes);
         CVVDP_LAUNCH(kfn, dim3((warps * 32 + 127) / 128), dim3(128), 0, st, fa);
-        ctx->launches++;
     }
     // ---- heat map ----
     if (do_hm) {
@@ -412,8 +449,8 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             ea.wc = ctx->lv[i + 1].w;
             const long long npix = (long long)ea.h * ea.w;
             auto kfn = k_expand_add;
+            LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, i, (double)n * 4.0 * (2.0 * npix + (double)ea.hc * ea.wc));
             CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), n), dim3(256), 0, st, ea);
-            ctx->launches++;
         }
         HeatmapOutArgs ha;
         ha.img = ctx->lv[0].hm;
@@ -423,8 +460,8 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ha.jod_a = P.jod_a;
         ha.jod_exp = P.jod_exp;
         auto kfn = k_heatmap_out;
+        LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, -1, (double)n * 6.0 * ha.npix);
         CVVDP_LAUNCH(kfn, dim3((unsigned)((ha.npix + 255) / 256), n), dim3(256), 0, st, ha);
-        ctx->launches++;
     }
     CU_CHECK(ctx, cudaGetLastError());
     return CVVDP_OK;
@@ -845,8 +882,10 @@ int cvvdp_b200_pool_device(cvvdp_b200_ctx *ctx, const float *q_dev, int B, int C
     pa.Q = q_dev;
     pa.jod = jod_dev;
     auto kfn = k_pool;
-    CVVDP_LAUNCH(kfn, dim3(B), dim3(256), 0, (cudaStream_t)stream, pa);
-    ctx->launches++;
+    {
+        LaunchScope ls(ctx, (cudaStream_t)stream, CVVDP_K_POOL, 0, (double)B * C * F * L * 4.0);
+        CVVDP_LAUNCH(kfn, dim3(B), dim3(256), 0, (cudaStream_t)stream, pa);
+    }
     CU_CHECK(ctx, cudaGetLastError());
     return CVVDP_OK;
 }
@@ -897,12 +936,51 @@ int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int bat
     fa.flags = flags_dev;
     const long long npix = (long long)height * width;
     auto kfn = k_frontend;
-    CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), batch), dim3(256), 0, (cudaStream_t)stream, fa);
-    ctx->launches++;
+    {
+        LaunchScope ls(ctx, (cudaStream_t)stream, CVVDP_K_FRONTEND, 0, (double)npix * batch * in_channels * (dtype_size(dtype) + 4.0));
+        CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), batch), dim3(256), 0, (cudaStream_t)stream, fa);
+    }
     CU_CHECK(ctx, cudaGetLastError());
     return CVVDP_OK;
 }
 
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int cvvdp_b200_profile_enable(cvvdp_b200_ctx *ctx, int enable) {
+    if (!ctx) return CVVDP_ERR_INVALID;
+    ctx->prof = enable != 0;
+    return CVVDP_OK;
+}
+
+int cvvdp_b200_profile_read(cvvdp_b200_ctx *ctx, cvvdp_b200_kernel_stat *out, int max_entries, int *n_entries) {
+    if (!ctx || !out || !n_entries) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    CU_CHECK(ctx, cudaDeviceSynchronize());
+    int n = 0;
+    for (auto &r : ctx->prof_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+        int k = 0;
+        for (; k < n; ++k)
+            if (out[k].kind == r.kind && out[k].level == r.level) break;
+        if (k == n) {
+            if (n >= max_entries) continue;
+            out[n].kind = r.kind;
+            out[n].level = r.level;
+            out[n].launches = 0;
+            out[n].total_ms = 0.f;
+            out[n].algo_bytes = 0.0;
+            ++n;
+        }
+        out[k].launches++;
+        out[k].total_ms += ms;
+        out[k].algo_bytes += r.bytes;
+    }
+    ctx->prof_recs.clear();
+    *n_entries = n;
+    return CVVDP_OK;
+}
 
 }  // extern "C"

@@ -258,38 +258,48 @@ class cvvdp(vq_metric):
 
     def _run_arrays(self, vs, B, H, W, F, fps, f0, f1):
         """Fast path: raw clip tensors, display model fused into the CUDA front end."""
-        test, ref = vs.test_video, vs.reference_video
-        if test.dtype != ref.dtype:
-            raise RuntimeError("Test and reference must have the same dtype")
         if vs.dm_photometry is not self.display_photometry and vs.dm_photometry != self.display_photometry:
             logging.warning("video source and metric use different display models; using the video source's")
-        info = self._plan(B, H, W, F, fps, test.shape[1], _TORCH_DTYPES[test.dtype], vs.dm_photometry)
+        return self.q_per_ch_from_tensors(vs.test_video, vs.reference_video, F, fps, (f0, f1), 0, vs.dm_photometry)
+
+    def q_per_ch_from_tensors(self, test, ref, n_frames_total, frames_per_second, frame_range=None, first_frame=0,
+                              photometry=None):
+        """Q_per_ch for BCFHW tensors that hold clip frames [first_frame, first_frame + test.shape[2]) of a
+        clip with `n_frames_total` frames (a window is enough as long as it covers the temporal support
+        of `frame_range`).  Device tensors go through process_device, host tensors through the streaming
+        process_host path.  Returns (Q_per_ch [B,C,F_total,L] zero outside frame_range, raw heat map)."""
+        photo = photometry if photometry is not None else self.display_photometry
+        if not isinstance(photo, vvdp_display_photo_eotf):
+            raise RuntimeError("the fused front end needs a vvdp_display_photo_eotf display model")
+        if test.dtype != ref.dtype:
+            raise RuntimeError("Test and reference must have the same dtype")
+        B = max(test.shape[0], ref.shape[0])
+        H, W, F = test.shape[3], test.shape[4], int(n_frames_total)
+        if B > 1 and self.do_heatmap:
+            raise vq_exception("Heatmaps not supported when batches are used")
+        fps = frames_per_second if F > 1 else 0
+        f0, f1 = (0, F) if frame_range is None else frame_range
+        info = self._plan(B, H, W, F, fps, test.shape[1], _TORCH_DTYPES[test.dtype], photo)
         C, L = info.n_channels, info.n_bands
-        on_device = test.device == self.device and ref.device == self.device
-        if on_device:
-            Q, hm = self._alloc_outputs(B, C, F, L, H, W)
-            self._ctx.process_device(_clip_of(test, B), _clip_of(ref, B), f0, f1, Q.data_ptr(),
-                                     hm.data_ptr() if hm is not None else None, self._stream())
-            return Q, hm
         if test.device.type != "cpu" or ref.device.type != "cpu":
             test, ref = test.to(self.device), ref.to(self.device)
             Q, hm = self._alloc_outputs(B, C, F, L, H, W)
-            self._ctx.process_device(_clip_of(test, B), _clip_of(ref, B), f0, f1, Q.data_ptr(),
-                                     hm.data_ptr() if hm is not None else None, self._stream())
+            self._ctx.process_device(_clip_of(test, B, first_frame), _clip_of(ref, B, first_frame), f0, f1,
+                                     Q.data_ptr(), hm.data_ptr() if hm is not None else None, self._stream())
             return Q, hm
         # host clips: streamed upload overlapped with compute inside the native library
         pin = self.device.type == "cuda"
         Qh = torch.zeros((B, C, F, L), dtype=torch.float32, pin_memory=pin)
         hmh = torch.zeros((1, 1, F, H, W), dtype=torch.float16, pin_memory=pin) if self.do_heatmap else None
         try:
-            self._ctx.process_host(_clip_of(test, B), _clip_of(ref, B), f0, f1, Qh.data_ptr(),
-                                   hmh.data_ptr() if hmh is not None else None)
+            self._ctx.process_host(_clip_of(test, B, first_frame), _clip_of(ref, B, first_frame), f0, f1,
+                                   Qh.data_ptr(), hmh.data_ptr() if hmh is not None else None)
         except N.NativeError as e:
             if "densely" not in str(e):
                 raise
             test, ref = test.contiguous(), ref.contiguous()  # exotic layout: normalise to BCFHW first
-            self._ctx.process_host(_clip_of(test, B), _clip_of(ref, B), f0, f1, Qh.data_ptr(),
-                                   hmh.data_ptr() if hmh is not None else None)
+            self._ctx.process_host(_clip_of(test, B, first_frame), _clip_of(ref, B, first_frame), f0, f1,
+                                   Qh.data_ptr(), hmh.data_ptr() if hmh is not None else None)
         return Qh, hmh
 
     def _run_plugin(self, vs, B, H, W, F, fps, f0, f1):

@@ -164,6 +164,21 @@ int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int bat
                         int width, int dtype, int frame, int colorspace, float *dst_dev, int32_t *flags_dev,
                         void *stream);
 
+/* Per-kernel timing for bench.py's roofline: when enabled, every launch is bracketed by CUDA events on
+ * its stream.  profile_read synchronises the device, aggregates by (kind, pyramid level) and resets.
+ * algo_bytes is the ALGORITHMIC HBM traffic of those launches:
+ * temporal = input bytes read once + 32 B/pixel written, reduce = 32 read + 8 written per input
+ * pixel-pair, band = 32 + 8 read per level pixel-pair, ... */
+enum { CVVDP_K_TEMPORAL = 0, CVVDP_K_REDUCE = 1, CVVDP_K_BAND = 2, CVVDP_K_BASEBAND = 3, CVVDP_K_FINALIZE = 4,
+       CVVDP_K_HEATMAP = 5, CVVDP_K_POOL = 6, CVVDP_K_FRONTEND = 7 };
+typedef struct {
+    int32_t kind, level, launches;
+    float total_ms;
+    double algo_bytes;
+} cvvdp_b200_kernel_stat;
+int cvvdp_b200_profile_enable(cvvdp_b200_ctx *ctx, int enable);
+int cvvdp_b200_profile_read(cvvdp_b200_ctx *ctx, cvvdp_b200_kernel_stat *out, int max_entries, int *n_entries);
+
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx);
 

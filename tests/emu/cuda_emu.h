@@ -248,6 +248,7 @@ static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { *
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 template <typename T> static inline cudaError_t cudaFuncSetAttribute(T, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) {
     *v = (a == cudaDevAttrMultiProcessorCount) ? 4 : 232448;

@@ -1,0 +1,162 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path through the C ABI against the
+reference-generated fixtures (tests/golden) and the numpy oracle on seeded inputs, plus
+size-independent properties at full BASELINE sizes.  Tolerances: |dJOD| <= 1e-3,
+|dQ_per_ch| <= 1e-3 |Q| + 1e-5, raw heat map (fp16, 0..1) <= 2e-3."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+import synth
+from oracle import cvvdp_oracle as O
+
+import colorvideovdp_b200 as cv
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _t(a):
+    if isinstance(a, np.ndarray) and a.dtype == np.uint16:
+        a = a.view(np.int16)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("resident", ["device", "host"])
+@pytest.mark.parametrize("name", gu.case_names())
+def test_golden_fixtures(name, resident):
+    z, meta = gu.load_case(name)
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"], heatmap=meta["heatmap"], device=DEV)
+    tst, ref = (z["test"], z["ref"]) if resident == "host" else (_t(z["test"]), _t(z["ref"]))
+    jod, stats = m.predict(tst, ref, dim_order=meta["dim_order"], frames_per_second=meta["fps"])
+    assert jod.device.type == "cuda"
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert np.max(np.abs(jod.cpu().numpy().astype(np.float64) - z["jod"])) <= gu.JOD_TOL
+    if meta["heatmap"] == "raw":
+        hm = stats["heatmap"]
+        assert hm.dtype == torch.float16 and hm.device.type == "cpu"
+        assert np.max(np.abs(hm.float().numpy() - z["heatmap"].astype(np.float32))) <= gu.HEATMAP_ATOL
+    assert m._ctx.launch_count() > 0
+
+
+CASES = [  # (seed, F, H, W, fps, display, padding, dtype)
+    (31, 1, 256, 256, 0, "standard_fhd", "replicate", "u8"),       # BASELINE config 1
+    (32, 12, 135, 240, 30, "standard_fhd", "replicate", "u8"),     # odd H / even W: lpyr_dec.py:206 quirk
+    (33, 6, 136, 241, 60, "standard_4k", "symmetric", "f32"),      # even H / odd W, fl=17 > F
+    (34, 20, 100, 180, 60, "standard_hdr_pq", "replicate", "u16"),
+    (35, 5, 270, 480, 120, "standard_4k", "replicate", "f16"),     # fl=31
+    (36, 3, 97, 33, 25, "standard_phone", "symmetric", "u8"),      # tiles with ragged edges, tall image
+]
+
+
+@pytest.mark.parametrize("seed,F,H,W,fps,display,padding,dtype", CASES)
+def test_against_oracle(seed, F, H, W, fps, display, padding, dtype):
+    if dtype == "u16":
+        tst, ref = synth.make_pair_pq_u16(seed, F, H, W)
+    else:
+        tst, ref = synth.make_pair_u8(seed, F, H, W)
+        if dtype == "f32":
+            tst, ref = tst.astype(np.float32) / 255, ref.astype(np.float32) / 255
+        if dtype == "f16":
+            tst, ref = (tst.astype(np.float32) / 255).astype(np.float16), (ref.astype(np.float32) / 255).astype(np.float16)
+    m = cv.cvvdp(display_name=display, temp_padding=padding, device=DEV)
+    jod, stats = m.predict(_t(tst), _t(ref), frames_per_second=fps)
+    jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, display, padding)
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"seed {seed}")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
+
+
+def test_heatmap_against_oracle():
+    tst, ref = synth.make_pair_u8(41, 4, 120, 200)
+    m = cv.cvvdp(display_name="standard_4k", heatmap="raw", device=DEV)
+    jod, stats = m.predict(_t(tst), _t(ref), frames_per_second=30)
+    jod_o, stats_o = O.predict(tst, ref, "BCFHW", 30, "standard_4k", heatmap="raw")
+    assert np.max(np.abs(stats["heatmap"].float().numpy() - stats_o["heatmap"].astype(np.float32))) <= gu.HEATMAP_ATOL
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"])
+
+
+def test_identical_pair_is_exactly_10_at_full_hd():
+    _, ref = synth.make_pair_u8(42, 4, 1080, 1920)
+    m = cv.cvvdp(display_name="standard_fhd", device=DEV)
+    r = _t(ref)
+    jod, stats = m.predict(r, r, frames_per_second=30)
+    assert float(jod) == 10.0 and np.all(stats["Q_per_ch"] == 0)
+
+
+def test_partition_independence_full_hd():
+    """Frame blocks, frame shards and host/device residency give bit-identical Q_per_ch at 1080p."""
+    tst, ref = synth.make_pair_u8(43, 12, 1080, 1920)
+    m = cv.cvvdp(display_name="standard_fhd", device=DEV)
+    t, r = _t(tst), _t(ref)
+    _, full = m.predict(t, r, frames_per_second=30)
+    small = cv.cvvdp(display_name="standard_fhd", device=DEV, gpu_mem=0.5)
+    _, blk = small.predict(t, r, frames_per_second=30)
+    assert small._info.block_frames < m._info.block_frames
+    assert np.array_equal(full["Q_per_ch"], blk["Q_per_ch"])
+    _, host = m.predict(tst, ref, frames_per_second=30)
+    assert np.array_equal(full["Q_per_ch"], host["Q_per_ch"])
+    vs = cv.video_source_array(t, r, 30, display_photometry=m.display_photometry)
+    Qa, _ = m.compute_q_per_ch(vs, (0, 5))
+    Qb, _ = m.compute_q_per_ch(vs, (5, 12))
+    assert np.array_equal((Qa + Qb).cpu().numpy(), full["Q_per_ch"])
+    # monotonicity: more noise -> lower JOD
+    tst2 = np.clip(tst.astype(np.int16) + (np.random.default_rng(0).integers(-12, 13, tst.shape)), 0, 255).astype(np.uint8)
+    j2, _ = m.predict(_t(tst2), r, frames_per_second=30)
+    j1 = m.do_pooling_and_jods(full["Q_per_ch"])
+    assert float(j2) < float(j1) < 10.0
+
+
+def test_4k_block_matches_oracle_on_one_frame():
+    """BASELINE config 3 shape (3840x2160, 60 fps, standard_4k): the oracle is too slow for the clip, so
+    one late frame is checked (needs 17 frames of history)."""
+    tst, ref = synth.make_pair_u8(44, 18, 2160, 3840)
+    m = cv.cvvdp(display_name="standard_4k", device=DEV)
+    vs = cv.video_source_array(_t(tst), _t(ref), 60, display_photometry=m.display_photometry)
+    Q, _ = m.compute_q_per_ch(vs, (17, 18))
+    _, so = O.predict(tst, ref, "BCFHW", 60, "standard_4k", frame_range=(17, 18))
+    gu.assert_q_close(Q.cpu().numpy()[:, :, 17:18], so["Q_per_ch"][:, :, 17:18], "4k frame 17")
+
+
+def test_display_model_plugin_surface():
+    rng = np.random.default_rng(2)
+    V = rng.random((1, 3, 1, 64, 80), dtype=np.float32)
+    for name in ("standard_4k", "standard_hdr_pq", "standard_hdr_linear", "standard_hdr_hlg"):
+        dm = cv.vvdp_display_photometry.load(name, [])
+        odm = O.Display(name)
+        L = dm.forward(torch.from_numpy(V).to(DEV)).cpu().numpy()
+        L_ref = O.eotf_forward(V[:, :, 0], odm)
+        assert np.max(np.abs(L[:, :, 0] - L_ref) / np.abs(L_ref)) < 1e-4, name
+        D = dm.source_2_target_colorspace(torch.from_numpy(V).to(DEV), "DKLd65").cpu().numpy()
+        D_ref = O.frontend(V[:, :, 0], odm)
+        assert np.max(np.abs(D[:, :, 0] - D_ref)) < 1e-4 * np.abs(D_ref).max(), name
+    vs = cv.video_source_array(V, V, 0, display_photometry="standard_4k")
+    fr = vs.get_test_frame(0, DEV, "DKLd65")
+    assert tuple(fr.shape) == (1, 3, 1, 64, 80) and fr.dtype == torch.float32 and fr.is_cuda
+
+
+def test_plugin_source_and_pooling_entry():
+    tst, ref = synth.make_pair_u8(45, 11, 90, 120)
+    m = cv.cvvdp(display_name="standard_fhd", device=DEV)
+    jod, fast = m.predict(_t(tst), _t(ref), frames_per_second=30)
+
+    class Wrapped(cv.video_source):  # a third-party source built on the display-model plugin surface
+        def __init__(self):
+            self.inner = cv.video_source_array(tst, ref, 30, display_photometry="standard_fhd")
+
+        def get_video_size(self):
+            return self.inner.get_video_size()
+
+        def get_frames_per_second(self):
+            return 30
+
+        def get_test_frame(self, f, device, colorspace):
+            return self.inner.get_test_frame(f, device, colorspace)
+
+        def get_reference_frame(self, f, device, colorspace):
+            return self.inner.get_reference_frame(f, device, colorspace)
+
+    jod_p, plug = m.predict_video_source(Wrapped())
+    gu.assert_q_close(plug["Q_per_ch"], fast["Q_per_ch"], "plugin vs fused front end")
+    assert abs(float(jod_p) - float(jod)) <= 1e-4
+    P = O.Params()
+    assert abs(float(m.do_pooling_and_jods(fast["Q_per_ch"])) - float(O.do_pooling_and_jods(fast["Q_per_ch"], P))) < 2e-5
