@@ -23,7 +23,8 @@ struct LevelBuf {
     float *partials = nullptr;  // [B*nb][tiles][4]
     float *hm = nullptr;        // [nb][h*w] (heat map only)
     float4 *lut = nullptr;      // [32]
-    int tiles_x = 0, tiles_y = 0;
+    int tiles_x = 0, tiles_y = 0;  // band kernel grid: column strips x row segments
+    int seg_rows = 0;
     int do_blur = 0;
 };
 
@@ -327,12 +328,39 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         const long long npix = (long long)job.height * job.width;
         dim3 grid((unsigned)((npix + CVVDP_TEMPORAL_THREADS - 1) / CVVDP_TEMPORAL_THREADS), (unsigned)(B * 2));
         const size_t smem = (size_t)info.filter_len * 3 * CVVDP_TEMPORAL_THREADS * sizeof(float);
-        auto kfn = k_temporal;
         int wlo, whi;
         needed_frames(ctx, f0, f1, &wlo, &whi);
         const double bytes = (double)npix * B * 2 * ((double)(whi - wlo) * job.in_channels * dtype_size(job.dtype) + 16.0 * n);
         LaunchScope ls(ctx, st, CVVDP_K_TEMPORAL, 0, bytes);
-        CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
+        const int e = ctx->disp.eotf;
+        const bool use_lut = job.dtype == CVVDP_DTYPE_U8 &&
+                             (e == CVVDP_EOTF_SRGB || e == CVVDP_EOTF_PQ || e == CVVDP_EOTF_LINEAR || e == CVVDP_EOTF_GAMMA);
+#define CVVDP_TEMPORAL_CASE(FLV)                                                              \
+    case FLV: {                                                                               \
+        if (use_lut) {                                                                        \
+            auto kfn = k_temporal_reg<FLV, true>;                                             \
+            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
+        } else {                                                                              \
+            auto kfn = k_temporal_reg<FLV, false>;                                            \
+            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
+        }                                                                                     \
+    } break;
+        switch (info.filter_len) {
+            CVVDP_TEMPORAL_CASE(1)
+            CVVDP_TEMPORAL_CASE(3)
+            CVVDP_TEMPORAL_CASE(5)
+            CVVDP_TEMPORAL_CASE(7)
+            CVVDP_TEMPORAL_CASE(9)
+            CVVDP_TEMPORAL_CASE(11)
+            CVVDP_TEMPORAL_CASE(13)
+            CVVDP_TEMPORAL_CASE(15)
+            CVVDP_TEMPORAL_CASE(17)
+            default: {  // long filters (> 64 fps): generic shared-memory ring
+                auto kfn = k_temporal;
+                CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
+            }
+        }
+#undef CVVDP_TEMPORAL_CASE
     }
     // ---- Gaussian pyramid ----
     for (int i = 0; i + 1 < L; ++i) {
@@ -384,12 +412,13 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         for (int c = 0; c < 4; ++c) ba.hm_w[c] = ch_w[c] * t_int;
         ba.hm_beta = P.beta_tch;
         ba.hm_scale = (i == 0) ? 1.f : 0.5f;
+        ba.seg_rows = lv.seg_rows;
         dim3 grid(lv.tiles_x, lv.tiles_y, pairs);
-        auto kfn = k_band;
+        auto kfn = k_band2;
         LaunchScope ls(ctx, st, CVVDP_K_BAND, i,
                        (double)pairs * 2 * 16.0 * ((double)ba.h * ba.w + (double)ba.hc * ba.wc) +
                            (do_hm ? (double)pairs * 4.0 * ba.h * ba.w : 0.0));
-        CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_BAND_THREADS), sizeof(BandSmem), st, ba);
+        CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Band2Smem), st, ba);
     }
     {
         BasebandArgs bb;
@@ -541,8 +570,8 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
         cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming);
     }
-    auto kb = k_band;
-    cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BandSmem));
+    auto kb = k_band2;
+    cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
     auto kt = k_temporal;
     cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          std::min(ctx->max_smem_optin, 227 * 1024));
@@ -618,15 +647,15 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         const size_t npix = (size_t)info.band_height[i] * info.band_width[i];
         per_frame += align_up(B * 2 * npix * sizeof(float4), 256);
         const size_t tiles = (i == L - 1) ? 1
-                                          : (size_t)((info.band_width[i] + CVVDP_BTX - 1) / CVVDP_BTX) *
-                                                ((info.band_height[i] + CVVDP_BTY - 1) / CVVDP_BTY);
+                                          : (size_t)((info.band_width[i] + CVVDP_B2_SW - 1) / CVVDP_B2_SW) *
+                                                (info.band_height[i] / 16 + 1);  // upper bound
         per_frame += align_up(B * tiles * 4 * sizeof(float), 256);
         if (do_hm) per_frame += align_up(npix * sizeof(float), 256);
     }
-    size_t limit = job->workspace_limit_bytes > 0 ? (size_t)job->workspace_limit_bytes : (size_t)12 << 30;
+    size_t limit = job->workspace_limit_bytes > 0 ? (size_t)job->workspace_limit_bytes : (size_t)40 << 30;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) limit = std::min(limit, free_b / 2);
-    int nb = (int)std::min<size_t>(std::max<size_t>(limit / std::max<size_t>(per_frame, 1), 1), 32);
+    int nb = (int)std::min<size_t>(std::max<size_t>(limit / std::max<size_t>(per_frame, 1), 1), 64);
     if (job->max_block_frames > 0) nb = std::min(nb, job->max_block_frames);
     nb = std::min(nb, job->n_frames);
     if ((long long)B * nb * 2 > 65535) nb = std::max(1, (int)(65535 / (B * 2)));
@@ -640,8 +669,15 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         LevelBuf &lv = ctx->lv[i];
         lv.h = info.band_height[i];
         lv.w = info.band_width[i];
-        lv.tiles_x = (lv.w + CVVDP_BTX - 1) / CVVDP_BTX;
-        lv.tiles_y = (lv.h + CVVDP_BTY - 1) / CVVDP_BTY;
+        {   // strips of 52 columns; split the rows into segments only when there are too few CTAs
+            lv.tiles_x = (lv.w + CVVDP_B2_SW - 1) / CVVDP_B2_SW;
+            // the split depends on the level geometry only, never on the batch or block size, so that
+            // the summation order (hence every bit of Q_per_ch) is independent of how frames are
+            // partitioned into blocks, shards or ranks
+            int nseg = std::min(std::max((256 + lv.tiles_x - 1) / lv.tiles_x, 1), std::max(1, lv.h / 64));
+            lv.seg_rows = (((lv.h + nseg - 1) / nseg) + 7) / 8 * 8;
+            lv.tiles_y = (lv.h + lv.seg_rows - 1) / lv.seg_rows;
+        }
         lv.do_blur = (ctx->blur_pad > 0 && lv.h > ctx->blur_pad && lv.w > ctx->blur_pad) ? 1 : 0;  // cvvdp_metric.py:965
         const size_t npix = (size_t)lv.h * lv.w;
         off_g[i] = off;

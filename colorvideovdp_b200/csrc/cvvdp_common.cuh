@@ -88,6 +88,26 @@ __device__ __forceinline__ unsigned short float_to_half_bits(float f) {
 #endif
 }
 
+// ---- Ampere-style asynchronous global->shared copies (LDGSTS), 16 bytes each ---------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+#ifdef __CUDA_ARCH__
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+#else
+    memcpy(smem_dst, gmem_src, 16);
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // ---- float4 arithmetic ------------------------------------------------------------------------
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
 __device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }

@@ -18,7 +18,7 @@ namespace cvvdp {
 __device__ __forceinline__ float load_unpack(const void *base, long long off, int dtype) {
     switch (dtype) {
         case CVVDP_DTYPE_U8: return (float)((const unsigned char *)base)[off] / 255.0f;
-        case CVVDP_DTYPE_U16: return (float)((const unsigned short *)base)[off] / 65535.0f;
+        case CVVDP_DTYPE_U16: return (float)((const unsigned short *)base)[off] * (1.0f / 65535.0f);
         case CVVDP_DTYPE_F16: return half_bits_to_float(((const unsigned short *)base)[off]);
         default: return ((const float *)base)[off];
     }
@@ -27,7 +27,7 @@ __device__ __forceinline__ float load_unpack(const void *base, long long off, in
 __device__ __forceinline__ float clamp01_keepnan(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }
 
 __device__ __forceinline__ float srgb2lin(float p) {  // display_model.py:78-80
-    return p > 0.04045f ? f_pow((p + 0.055f) / 1.055f, 2.4f) : p / 12.92f;
+    return p > 0.04045f ? f_pow((p + 0.055f) * (1.0f / 1.055f), 2.4f) : p * (1.0f / 12.92f);
 }
 __device__ __forceinline__ float pq2lin(float V) {  // display_model.py:58-70
     const float c1 = 0.8359375f, c2 = 18.8515625f, c3 = 18.6875f;
@@ -203,6 +203,148 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
     }
 }
 
+// Fast variant for the common filter lengths (fl = 2*ceil(fps/8)+1 <= 17, i.e. up to 64 fps): the
+// ring lives in registers (the time loop is unrolled by one ring period, so every index is static
+// and the taps are constant-bank FFMA operands), 8-bit inputs go through a 256-entry EOTF table in
+// shared memory built with the exact arithmetic, and the raw values of frame t+1 are prefetched
+// while frame t is filtered.  k_temporal above stays as the generic fallback (any fl).
+__device__ __forceinline__ float bits_as_float(unsigned b) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+// Raw element bits of one pixel (1 or 3 channels).  Kept as integers so that the load of frame t+1
+// can stay in flight while frame t is filtered: nothing consumes the registers until bits_to_dkl.
+template <bool USE_LUT>
+__device__ __forceinline__ void load_bits(const TemporalArgs &a, const ClipView &cv, long long base, int fidx,
+                                          unsigned bits[3]) {
+    const long long off = base + (long long)fidx * cv.s[2];
+    const long long o1 = a.cin == 3 ? off + cv.s[1] : off, o2 = a.cin == 3 ? off + 2 * cv.s[1] : off;
+    if (USE_LUT || a.dtype == CVVDP_DTYPE_U8) {
+        const unsigned char *p = (const unsigned char *)cv.data;
+        bits[0] = p[off];
+        bits[1] = p[o1];
+        bits[2] = p[o2];
+    } else if (a.dtype == CVVDP_DTYPE_F32) {
+        const unsigned *p = (const unsigned *)cv.data;
+        bits[0] = p[off];
+        bits[1] = p[o1];
+        bits[2] = p[o2];
+    } else {
+        const unsigned short *p = (const unsigned short *)cv.data;
+        bits[0] = p[off];
+        bits[1] = p[o1];
+        bits[2] = p[o2];
+    }
+}
+
+template <bool USE_LUT>
+__device__ __forceinline__ void bits_to_dkl(const TemporalArgs &a, const float *lut, const unsigned bits[3], float &d0,
+                                            float &d1, float &d2) {
+    float v[3];
+    if (USE_LUT) {
+        v[0] = lut[bits[0]];
+        v[1] = lut[bits[1]];
+        v[2] = lut[bits[2]];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            switch (a.dtype) {
+                case CVVDP_DTYPE_U8: v[i] = (float)bits[i] / 255.0f; break;
+                case CVVDP_DTYPE_U16: v[i] = (float)bits[i] * (1.0f / 65535.0f); break;
+                case CVVDP_DTYPE_F16: v[i] = half_bits_to_float((unsigned short)bits[i]); break;
+                default: v[i] = bits_as_float(bits[i]);
+            }
+        }
+        eotf_forward(v, a.cin, a.dd);
+    }
+    if (a.cin == 3) {
+        d0 = (v[0] * a.dd.M[0] + v[1] * a.dd.M[1]) + v[2] * a.dd.M[2];
+        d1 = (v[0] * a.dd.M[3] + v[1] * a.dd.M[4]) + v[2] * a.dd.M[5];
+        d2 = (v[0] * a.dd.M[6] + v[1] * a.dd.M[7]) + v[2] * a.dd.M[8];
+    } else {
+        d0 = d1 = d2 = v[0];
+    }
+}
+
+__device__ __forceinline__ int temporal_source_frame(const TemporalArgs &a, int t) {
+    if (t >= 0) return t;
+    return (a.padding == CVVDP_PAD_REPLICATE) ? 0 : symmetric_frame_index(t, a.F_total);
+}
+
+template <int FL, bool USE_LUT>
+__global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_reg(const TemporalArgs a) {
+    __shared__ float s_lut[256];
+    const int tid = threadIdx.x;
+    if (USE_LUT) {  // exact per-code EOTF: same arithmetic as the per-pixel path
+        float v[1] = {(float)tid / 255.0f};
+        eotf_forward(v, 1, a.dd);
+        s_lut[tid] = v[0];
+        __syncthreads();
+    }
+    const long long npix = (long long)a.H * a.W;
+    const long long p = (long long)blockIdx.x * CVVDP_TEMPORAL_THREADS + tid;
+    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
+    if (p >= npix) return;
+    const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
+    const ClipView &cv = a.clip[v];
+    const long long base = b * cv.s[0] + y * cv.s[3] + x * cv.s[4] - (long long)cv.frame0 * cv.s[2];
+    const int n = a.f1 - a.f0;
+    float4 *out = a.out + ((long long)b * n * 2 + v) * npix + p;
+    float r0[FL], r1[FL], r2[FL];
+    unsigned bits[3];
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    // ---- warm-up: the FL-1 frames before f0 (temporal padding before frame 0) fill slots 0..FL-2 ----
+    int src = temporal_source_frame(a, a.f0 - (FL - 1)), last_src = -1;
+    load_bits<USE_LUT>(a, cv, base, src, bits);
+#pragma unroll
+    for (int s = 0; s < FL - 1; ++s) {
+        if (src != last_src) {
+            bits_to_dkl<USE_LUT>(a, s_lut, bits, d0, d1, d2);
+            last_src = src;
+        }
+        const int nsrc = temporal_source_frame(a, a.f0 - (FL - 1) + s + 1);
+        if (nsrc != src) load_bits<USE_LUT>(a, cv, base, nsrc, bits);
+        src = nsrc;
+        r0[s] = d0;
+        r1[s] = d1;
+        r2[s] = d2;
+    }
+    // ---- steady state: frame t = f0 + j goes to slot (FL-1+j) mod FL; `bits` holds frame t ----
+    for (int tb = a.f0; tb < a.f1; tb += FL) {
+#pragma unroll
+        for (int j = 0; j < FL; ++j) {
+            const int t = tb + j;
+            if (t < a.f1) {  // uniform
+                const int s = (FL - 1 + j) % FL;
+                if (FL == 1 || src != last_src) bits_to_dkl<USE_LUT>(a, s_lut, bits, r0[s], r1[s], r2[s]);
+                else {  // the clip's frame 0 repeated by replicate padding (only right after the warm-up)
+                    r0[s] = d0;
+                    r1[s] = d1;
+                    r2[s] = d2;
+                }
+                last_src = -1;
+                if (t + 1 < a.f1) load_bits<USE_LUT>(a, cv, base, t + 1, bits);  // prefetch
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < FL; ++k) {  // tap k <-> frame t-(FL-1)+k <-> slot (s+1+k) mod FL
+                    const int sl = (s + 1 + k) % FL;
+                    o0 = fmaf(a.taps[0][k], r0[sl], o0);
+                    o1 = fmaf(a.taps[1][k], r1[sl], o1);
+                    o2 = fmaf(a.taps[2][k], r2[sl], o2);
+                    o3 = fmaf(a.taps[3][k], r0[sl], o3);
+                }
+                out[(long long)(t - a.f0) * 2 * npix] = make_float4(o0, o1, o2, o3);
+            }
+        }
+    }
+}
+
 // =================================================================================================
 // Gaussian pyramid reduce  (lpyr_dec.py:186-211): zero-padded 5-tap stride-2 passes (rows, then
 // columns) with the reference's edge fix-ups, including the parity quirk at line 206 (the ROW count
@@ -327,6 +469,7 @@ struct BandArgs {
     float beta;
     float hm_w[4];         // heat map: channel weights (x image_int)
     float hm_beta, hm_scale;  // beta_tch, 1/band_mul (lpyr_dec.py:308-314)
+    int seg_rows;          // k_band2: rows per vertical segment (multiple of 8)
 };
 
 struct BandSmem {
@@ -349,7 +492,7 @@ __device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lu
                                            float4 er, float4 &mm, float4 &df) {
     const float4 lt = gt - et, lr = gr - er;  // Laplacian (lpyr_dec.py:387)
     const float Lt = fmaxf(et.x, 0.01f), Lr = fmaxf(er.x, 0.01f);  // l.394
-    const float it = a.mul / Lt, ir = a.mul / Lr;
+    const float it = a.mul * f_rcp(Lt), ir = a.mul * f_rcp(Lr);
     const float cl = 1000.0f * a.mul;  // clamp(max=1000) before the band multiplier
     const float4 ct = make_float4(fminf(lt.x * it, cl), fminf(lt.y * it, cl), fminf(lt.z * it, cl), fminf(lt.w * it, cl));
     const float4 cr = make_float4(fminf(lr.x * ir, cl), fminf(lr.y * ir, cl), fminf(lr.z * ir, cl), fminf(lr.w * ir, cl));
@@ -553,6 +696,240 @@ __global__ void __launch_bounds__(CVVDP_BAND_THREADS) k_band(const BandArgs a) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < CVVDP_BAND_THREADS / 32; ++w) s += sm.red[w][tid];
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
+        a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
+    }
+}
+
+// =================================================================================================
+// Fused band kernel, strip-marching version.  Same arithmetic as k_band; different decomposition:
+// a CTA owns a vertical strip of 52 columns (64 with the +-6 halo) of one (item, frame) and marches
+// down a segment of rows, 8 rows per step, keeping rolling windows in shared memory:
+//   mm  : min(|T'|,|R'|) of the 8 rows of this step (64 columns)
+//   hb  : ring of the last 32 rows of the horizontally blurred mm (52 columns)
+//   df  : ring of the last 16 rows of |T'-R'| waiting for their blurred mask
+// so the 13x13 Gaussian costs 13+13 taps, the vertical halo is paid once per segment instead of once
+// per 32-row tile, and a CTA needs 56 KB of shared memory (4 CTAs/SM) instead of 89 KB.
+// Step k: rows A = [a0, a0+8) get contrast/CSF/mm/df (2x2 quads, one per thread) and their horizontal
+// blur; rows C = [a0-6, a0+2) -- whose 13-row window is now complete -- get the vertical blur,
+// masking, clamp and pooling.
+// =================================================================================================
+#define CVVDP_B2_SW 52
+#define CVVDP_B2_EW 64
+#define CVVDP_B2_RB 8
+#define CVVDP_B2_THREADS 128
+#define CVVDP_B2_HBR 32
+#define CVVDP_B2_DFR 16
+#define CVVDP_B2_CR (CVVDP_B2_RB / 2 + 2)  // 6 coarse rows per step
+#define CVVDP_B2_CC (CVVDP_B2_EW / 2 + 2)  // 34 coarse columns
+
+struct Band2Smem {
+    float4 lut[CVVDP_CSF_LUT_N];
+    float4 crs[2][CVVDP_B2_CR][CVVDP_B2_CC];          // coarse rows of the current step (cp.async stage)
+    float4 fine[2][CVVDP_B2_RB][CVVDP_B2_EW];         // fine rows of the current step (cp.async stage)
+    float4 mm[CVVDP_B2_RB][CVVDP_B2_EW + 1];
+    float4 hb[CVVDP_B2_HBR][CVVDP_B2_SW + 1];
+    float4 df[CVVDP_B2_DFR][CVVDP_B2_SW];
+    float red[CVVDP_B2_THREADS / 32][4];
+};
+
+// Asynchronous stage of one step: the 8 fine rows [a0, a0+8) x 64 columns of both videos and the 6
+// coarse rows under them (replicate-clamped, lpyr_dec.py:136-141).  Issued one step ahead.
+__device__ __forceinline__ void band2_stage(const BandArgs &a, Band2Smem &sm, const float4 *fine_t, const float4 *crs_g,
+                                            long long npix, long long ncpix, int a0, int a_end, int ex0, int tid) {
+    const int cy0 = a0 / 2 - 1, cx0 = ex0 / 2 - 1;
+    for (int i = tid; i < 2 * CVVDP_B2_CR * CVVDP_B2_CC; i += CVVDP_B2_THREADS) {
+        const int v = i / (CVVDP_B2_CR * CVVDP_B2_CC), rem = i - v * (CVVDP_B2_CR * CVVDP_B2_CC);
+        const int r = rem / CVVDP_B2_CC, c = rem - r * CVVDP_B2_CC;
+        const int cy = min(max(cy0 + r, 0), a.hc - 1), cx = min(max(cx0 + c, 0), a.wc - 1);
+        cp_async16(&sm.crs[v][r][c], crs_g + v * ncpix + (long long)cy * a.wc + cx);
+    }
+    const int c = tid & (CVVDP_B2_EW - 1), r0 = tid / CVVDP_B2_EW;  // 128 threads: 2 rows x 64 columns
+    const int gx = ex0 + c;
+    if (gx >= 0 && gx < a.w) {
+#pragma unroll
+        for (int i = 0; i < CVVDP_B2_RB / 2; ++i) {
+            const int r = r0 + 2 * i, gy = a0 + r;
+            if (gy < a_end) {
+                const float4 *src = fine_t + (long long)gy * a.w + gx;
+                cp_async16(&sm.fine[0][r][c], src);
+                cp_async16(&sm.fine[1][r][c], src + npix);
+            }
+        }
+    }
+    cp_async_commit();
+}
+
+__global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const BandArgs a) {
+    CVVDP_DYN_SMEM(smem_raw);
+    Band2Smem &sm = *reinterpret_cast<Band2Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.z;
+    const int hal = a.do_blur ? CVVDP_BHALO : 0;
+    const int x0 = blockIdx.x * CVVDP_B2_SW, ex0 = x0 - hal;  // even
+    const int ys = blockIdx.y * a.seg_rows, ye = min(ys + a.seg_rows, a.h);
+    const int y_begin = max(ys - hal, 0);                     // even
+    const int a_end = min(ye + hal, a.h);                     // rows [y_begin, a_end) feed this segment
+    const long long npix = (long long)a.h * a.w, ncpix = (long long)a.hc * a.wc;
+    const float4 *fine_t = a.fine + (long long)pair * 2 * npix;
+    const float4 *crs_g = a.coarse + (long long)pair * 2 * ncpix;
+    const bool x_edge = (ex0 < 0) || (x0 + CVVDP_B2_SW + hal > a.w);  // strip touches the left/right border
+
+    band2_stage(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid);
+    if (tid < CVVDP_CSF_LUT_N) sm.lut[tid] = a.lut[tid];
+    float eps_q[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) eps_q[c] = f_pow(a.eps, a.q[c]);
+    const float eps_p = f_pow(a.eps, a.p);
+    const float eps_b = (a.beta == 2.0f) ? 0.f : f_pow(a.eps, a.beta);
+    float4 acc = f4(0.f);
+    // loop-invariant thread roles
+    const int qy = tid / (CVVDP_B2_EW / 2), qx = tid - qy * (CVVDP_B2_EW / 2);  // phase A: one 2x2 quad
+    const int b_r = tid % CVVDP_B2_RB, b_xg = tid / CVVDP_B2_RB;               // phase B: row, group of 4 columns
+    const int c_ix = tid % CVVDP_B2_SW, c_rg = tid / CVVDP_B2_SW;              // phase C: column, group of 4 rows
+    const int a_gx = ex0 + 2 * qx;
+    const bool a_cols = a_gx + 1 >= 0 && a_gx < a.w;
+
+    for (int a0 = y_begin; a0 - hal < ye; a0 += CVVDP_B2_RB) {
+        const bool have_a = a0 < a_end;
+        cp_async_wait_all();
+        __syncthreads();  // the stage of this step has landed; previous phase C is complete
+        // ---- phase A: one 2x2 quad per thread: expand, contrast, CSF -> mm, df ----
+        if (have_a) {
+            const int gy = a0 + 2 * qy;
+            if (gy < a_end && a_cols) {
+                float4 e[2][4];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    float4 ve[3], vo[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 c0 = sm.crs[v][qy][qx + c], c1 = sm.crs[v][qy + 1][qx + c], c2 = sm.crs[v][qy + 2][qx + c];
+                        ve[c] = fma4(0.1f, c2, fma4(0.8f, c1, 0.1f * c0));
+                        vo[c] = fma4(0.5f, c2, 0.5f * c1);
+                    }
+                    e[v][0] = fma4(0.1f, ve[2], fma4(0.8f, ve[1], 0.1f * ve[0]));
+                    e[v][1] = fma4(0.5f, ve[2], 0.5f * ve[1]);
+                    e[v][2] = fma4(0.1f, vo[2], fma4(0.8f, vo[1], 0.1f * vo[0]));
+                    e[v][3] = fma4(0.5f, vo[2], 0.5f * vo[1]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
+                    const int py = a0 + ry, px = ex0 + rx;
+                    if (py >= a_end || px < 0 || px >= a.w) continue;
+                    float4 mm, df;
+                    band_pixel(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm, df);
+                    sm.mm[ry][rx] = mm;
+                    const int ix = px - x0;
+                    if (ix >= 0 && ix < CVVDP_B2_SW) sm.df[py & (CVVDP_B2_DFR - 1)][ix] = df;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- prefetch the next step's stage while phases B and C run ----
+        if (a0 + CVVDP_B2_RB < a_end) band2_stage(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B2_RB, a_end, ex0, tid);
+        // ---- phase B: horizontal pass of the phase-uncertainty Gaussian for the new rows ----
+        if (have_a && a.do_blur && tid < CVVDP_B2_RB * (CVVDP_B2_SW / 4)) {
+            const int gy = a0 + b_r, gxb = x0 + b_xg * 4;
+            if (gy < a_end && gxb < a.w) {
+                float4 win[2 * CVVDP_BHALO + 4];
+                if (x_edge) {
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                        int lx = reflect_idx(gxb + j - CVVDP_BHALO, a.w) - ex0;
+                        lx = min(max(lx, 0), CVVDP_B2_EW - 1);  // only for outputs beyond the image (discarded)
+                        win[j] = sm.mm[b_r][lx];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) win[j] = sm.mm[b_r][b_xg * 4 + j];
+                }
+                float4 *dst = &sm.hb[gy & (CVVDP_B2_HBR - 1)][b_xg * 4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    float4 s = f4(0.f);
+#pragma unroll
+                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) s = fma4(a.kern[k], win[o + k], s);
+                    dst[o] = s;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase C: vertical pass, masking, clamp, pooling for the rows whose window is complete ----
+        if (tid < 2 * CVVDP_B2_SW) {
+            const int gx = x0 + c_ix;
+            const int cyb = a0 - hal + c_rg * 4;  // 4 consecutive rows per thread
+            if (gx < a.w && cyb + 3 >= ys && cyb < ye) {
+                float4 win[2 * CVVDP_BHALO + 4];
+                if (a.do_blur) {
+                    const bool y_edge = (cyb - CVVDP_BHALO < 0) || (cyb + 3 + CVVDP_BHALO >= a.h);
+                    if (y_edge) {
+#pragma unroll
+                        for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                            int yy = reflect_idx(cyb + j - CVVDP_BHALO, a.h);
+                            yy = min(max(yy, 0), a.h - 1);
+                            win[j] = sm.hb[yy & (CVVDP_B2_HBR - 1)][c_ix];
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j)
+                            win[j] = sm.hb[(cyb + j - CVVDP_BHALO) & (CVVDP_B2_HBR - 1)][c_ix];
+                    }
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int gy = cyb + o;
+                    if (gy < ys || gy >= ye) continue;
+                    float4 m;
+                    if (a.do_blur) {
+                        m = f4(0.f);
+#pragma unroll
+                        for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) m = fma4(a.kern[k], win[o + k], m);
+                    } else {
+                        m = sm.mm[gy - a0][gx - ex0];
+                    }
+                    const float4 D = band_mask(a, m, sm.df[gy & (CVVDP_B2_DFR - 1)][c_ix], eps_q, eps_p);
+                    if (a.beta == 2.0f) {
+                        acc.x = fmaf(D.x, D.x + 2.f * a.eps, acc.x);
+                        acc.y = fmaf(D.y, D.y + 2.f * a.eps, acc.y);
+                        acc.z = fmaf(D.z, D.z + 2.f * a.eps, acc.z);
+                        acc.w = fmaf(D.w, D.w + 2.f * a.eps, acc.w);
+                    } else {
+                        acc.x += f_pow(D.x + a.eps, a.beta) - eps_b;
+                        acc.y += f_pow(D.y + a.eps, a.beta) - eps_b;
+                        acc.z += f_pow(D.z + a.eps, a.beta) - eps_b;
+                        acc.w += f_pow(D.w + a.eps, a.beta) - eps_b;
+                    }
+                    if (a.hm) {
+                        const float eb = f_pow(a.eps, a.hm_beta);
+                        float s = (f_pow(D.x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D.y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
+                                  (f_pow(D.z * a.hm_w[2] + a.eps, a.hm_beta) - eb) + (f_pow(D.w * a.hm_w[3] + a.eps, a.hm_beta) - eb);
+                        const float ib = 1.f / a.hm_beta;
+                        a.hm[(long long)pair * npix + (long long)gy * a.w + gx] = (f_pow(s + a.eps, ib) - f_pow(a.eps, ib)) * a.hm_scale;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if ((tid & 31) == 0) {
+        sm.red[tid >> 5][0] = acc.x;
+        sm.red[tid >> 5][1] = acc.y;
+        sm.red[tid >> 5][2] = acc.z;
+        sm.red[tid >> 5][3] = acc.w;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < CVVDP_B2_THREADS / 32; ++w) s += sm.red[w][tid];
         const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
         a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
     }
