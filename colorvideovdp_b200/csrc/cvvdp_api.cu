@@ -806,8 +806,12 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
                     "host clips must store each frame densely (dims with a stride below the frame stride must tile it)");
     const cvvdp_b200_clip *clips[2] = {test, ref};
     const size_t esz = dtype_size(job.dtype);
-    const int nb = ctx->info.block_frames, fl = ctx->info.filter_len;
-    const int cap_frames = nb + fl - 1 + fl;  // block + history (+ symmetric look-ahead of the first block)
+    // The upload is pipelined in chunks smaller than the device-resident block size so that compute
+    // starts after the first few frames have arrived; the fl-1 history frames of a chunk are copied
+    // device-to-device from the previous staging buffer instead of being uploaded again.
+    const int fl = ctx->info.filter_len;
+    const int nb = std::min(ctx->info.block_frames, std::max(16, fl - 1));
+    const int cap_frames = nb + fl - 1 + fl;  // chunk + history (+ symmetric look-ahead of the first chunk)
 
     // staging buffers: [outer index][cap_frames][frame]
     size_t need[2];
@@ -847,7 +851,7 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         ctx->hm_dev_bytes = hm_bytes;
     }
 
-    int blk = 0;
+    int blk = 0, pwlo = 0, pwhi = 0;  // window held by the previous staging buffer
     for (int f0 = frame_begin; f0 < frame_end; f0 += nb, ++blk) {
         const int f1 = std::min(f0 + nb, frame_end);
         Staging &sg = ctx->stage[blk & 1];
@@ -876,16 +880,25 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
                 ostride *= hl[v].extent[order[k]];
             }
             for (int d = 0; d < 5; ++d) dev_clip[v].stride[d] = dstr[d];
-            // copy one contiguous span of (whi - wlo) frames per outer index
+            // per outer index: frames already resident in the previous staging buffer move device to
+            // device, the rest is one contiguous host-to-device span
+            const int reuse_hi = (blk > 0 && wlo >= pwlo && wlo < pwhi) ? std::min(whi, pwhi) : wlo;
+            const Staging &prev = ctx->stage[(blk & 1) ^ 1];
             long long idx[4] = {0, 0, 0, 0};
             for (long long oi = 0; oi < n_outer_idx[v]; ++oi) {
-                long long hoff = (long long)(wlo - c->frame0) * sF, doff = 0;
+                long long hoff = (long long)(reuse_hi - c->frame0) * sF, doff = 0;
                 for (int k = 0; k < hl[v].n_outer; ++k) {
                     hoff += idx[k] * c->stride[order[k]];
                     doff += idx[k] * dstr[order[k]];
                 }
-                CU_CHECK(ctx, cudaMemcpyAsync((char *)sg.buf[v] + doff * esz, (const char *)c->data + hoff * esz,
-                                              (size_t)(whi - wlo) * sF * esz, cudaMemcpyHostToDevice, ctx->copy_stream));
+                if (reuse_hi > wlo)
+                    CU_CHECK(ctx, cudaMemcpyAsync((char *)sg.buf[v] + doff * esz,
+                                                  (const char *)prev.buf[v] + (doff + (long long)(wlo - pwlo) * sF) * esz,
+                                                  (size_t)(reuse_hi - wlo) * sF * esz, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+                if (whi > reuse_hi)
+                    CU_CHECK(ctx, cudaMemcpyAsync((char *)sg.buf[v] + (doff + (long long)(reuse_hi - wlo) * sF) * esz,
+                                                  (const char *)c->data + hoff * esz, (size_t)(whi - reuse_hi) * sF * esz,
+                                                  cudaMemcpyHostToDevice, ctx->copy_stream));
                 for (int k = 0; k < hl[v].n_outer; ++k) {
                     if (++idx[k] < hl[v].extent[order[k]]) break;
                     idx[k] = 0;
@@ -897,6 +910,8 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         if ((rc = run_block(ctx, &dev_clip[0], &dev_clip[1], f0, f1, ctx->q_dev, ctx->hm_dev, ctx->work_stream)) != CVVDP_OK)
             return rc;
         CU_CHECK(ctx, cudaEventRecord(sg.consumed, ctx->work_stream));
+        pwlo = wlo;
+        pwhi = whi;
     }
     CU_CHECK(ctx, cudaMemcpyAsync(q_per_ch_host, ctx->q_dev, q_bytes, cudaMemcpyDeviceToHost, ctx->work_stream));
     if (do_hm) {

@@ -263,7 +263,7 @@ class cvvdp(vq_metric):
         return self.q_per_ch_from_tensors(vs.test_video, vs.reference_video, F, fps, (f0, f1), 0, vs.dm_photometry)
 
     def q_per_ch_from_tensors(self, test, ref, n_frames_total, frames_per_second, frame_range=None, first_frame=0,
-                              photometry=None):
+                              photometry=None, _resident=None):
         """Q_per_ch for BCFHW tensors that hold clip frames [first_frame, first_frame + test.shape[2]) of a
         clip with `n_frames_total` frames (a window is enough as long as it covers the temporal support
         of `frame_range`).  Device tensors go through process_device, host tensors through the streaming
@@ -281,7 +281,8 @@ class cvvdp(vq_metric):
         f0, f1 = (0, F) if frame_range is None else frame_range
         info = self._plan(B, H, W, F, fps, test.shape[1], _TORCH_DTYPES[test.dtype], photo)
         C, L = info.n_channels, info.n_bands
-        if test.device.type != "cpu" or ref.device.type != "cpu":
+        resident = (test.device.type != "cpu" or ref.device.type != "cpu") if _resident is None else _resident
+        if resident:  # (_resident is a test hook: on the mock device every tensor is a CPU tensor)
             test, ref = test.to(self.device), ref.to(self.device)
             Q, hm = self._alloc_outputs(B, C, F, L, H, W)
             self._ctx.process_device(_clip_of(test, B, first_frame), _clip_of(ref, B, first_frame), f0, f1,

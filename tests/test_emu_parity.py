@@ -151,3 +151,25 @@ def test_error_behaviour(mock_device):
         bad.predict(a, a, frames_per_second=30)
     with pytest.raises(RuntimeError, match="Display model not found"):
         cv.cvvdp(display_name="no_such_display")
+
+
+def test_host_streaming_chunks_match_resident_path(mock_device):
+    """process_host uploads in chunks and moves the history frames device-to-device between its two
+    staging buffers; the result must be bit-identical to the resident path (process_device)."""
+    tst, ref = synth.make_pair_u8(8, 40, 24, 40)
+    for padding in ("replicate", "symmetric"):
+        m = cv.cvvdp(display_name="standard_fhd", temp_padding=padding)
+        t, r = torch.from_numpy(tst), torch.from_numpy(ref)
+        Qh, _ = m.q_per_ch_from_tensors(t, r, 40, 30, _resident=False)   # 3 chunks of 16 frames
+        Qd, _ = m.q_per_ch_from_tensors(t, r, 40, 30, _resident=True)
+        assert torch.equal(Qh, Qd)
+        # a frame shard from a window of the clip, host path
+        Qw, _ = m.q_per_ch_from_tensors(t[:, :, 10:40], r[:, :, 10:40], 40, 30, (20, 40), 10, _resident=False)
+        assert torch.equal(Qw[:, :, 20:], Qd[:, :, 20:]) and bool((Qw[:, :, :20] == 0).all())
+    # non-BCFHW host layout (frames outermost): FCHW view
+    fchw_t = np.ascontiguousarray(tst[0].transpose(1, 0, 2, 3))
+    fchw_r = np.ascontiguousarray(ref[0].transpose(1, 0, 2, 3))
+    m = cv.cvvdp(display_name="standard_fhd")
+    _, s1 = m.predict(fchw_t, fchw_r, dim_order="FCHW", frames_per_second=30)
+    _, s2 = m.predict(tst, ref, frames_per_second=30)
+    assert np.array_equal(s1["Q_per_ch"], s2["Q_per_ch"])
