@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -285,12 +286,13 @@ ClipView to_view(const cvvdp_b200_clip *c) {
     for (int i = 0; i < 5; ++i) v.s[i] = c->stride[i];
     v.frame0 = c->frame0;
     v.n_frames = c->n_frames;
+    v.ring = 0;
     return v;
 }
 
 // One block of frames [f0, f1) (f1 - f0 <= block_frames), inputs resident on the device.
 int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref, int f0, int f1,
-              float *q_dev, void *hm_dev, cudaStream_t st) {
+              float *q_dev, void *hm_dev, cudaStream_t st, int ring = 0) {
     const cvvdp_b200_job &job = ctx->job;
     const cvvdp_b200_plan_info &info = ctx->info;
     const cvvdp_b200_params &P = ctx->P;
@@ -305,6 +307,7 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         memset(&ta, 0, sizeof(ta));
         ta.clip[0] = to_view(test);
         ta.clip[1] = to_view(ref);
+        ta.clip[0].ring = ta.clip[1].ring = ring;
         // frames that already are DKLd65 (plugin sources) pass through with an identity matrix
         to_display_dev(ctx->disp, &ta.dd, ctx->disp.eotf == CVVDP_EOTF_NONE ? CVVDP_CS_RGB_LINEAR : CVVDP_CS_DKLD65);
         ta.dtype = job.dtype;
@@ -807,21 +810,23 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
     const cvvdp_b200_clip *clips[2] = {test, ref};
     const size_t esz = dtype_size(job.dtype);
     // The upload is pipelined in chunks smaller than the device-resident block size so that compute
-    // starts after the first few frames have arrived; the fl-1 history frames of a chunk are copied
-    // device-to-device from the previous staging buffer instead of being uploaded again.
+    // starts after the first few frames have arrived.  The staging area is a RING of frames (frame f at
+    // slot f % ring): the fl-1 history frames of a chunk are simply still there, so every input byte
+    // crosses PCIe exactly once and no device-to-device shuffling competes with the kernels.
     const int fl = ctx->info.filter_len;
     const int nb = std::min(ctx->info.block_frames, std::max(16, fl - 1));
-    const int cap_frames = nb + fl - 1 + fl;  // chunk + history (+ symmetric look-ahead of the first chunk)
+    const int ring = 2 * nb + 2 * fl;  // chunk k-1 (being computed) + chunk k (being uploaded) + history/look-ahead
 
-    // staging buffers: [outer index][cap_frames][frame]
+    // staging ring: [outer index][ring][frame]
     size_t need[2];
     long long n_outer_idx[2];
     for (int v = 0; v < 2; ++v) {
         n_outer_idx[v] = 1;
         for (int k = 0; k < hl[v].n_outer; ++k) n_outer_idx[v] *= hl[v].extent[hl[v].outer_dims[k]];
-        need[v] = (size_t)n_outer_idx[v] * cap_frames * (size_t)clips[v]->stride[2] * esz;
+        need[v] = (size_t)n_outer_idx[v] * ring * (size_t)clips[v]->stride[2] * esz;
     }
-    for (auto &s : ctx->stage) {
+    {
+        Staging &s = ctx->stage[0];
         if (s.bytes < std::max(need[0], need[1])) {
             for (auto &b : s.buf) {
                 if (b) cudaFree(b);
@@ -851,67 +856,87 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         ctx->hm_dev_bytes = hm_bytes;
     }
 
-    int blk = 0, pwlo = 0, pwhi = 0;  // window held by the previous staging buffer
-    for (int f0 = frame_begin; f0 < frame_end; f0 += nb, ++blk) {
-        const int f1 = std::min(f0 + nb, frame_end);
-        Staging &sg = ctx->stage[blk & 1];
+    // device views of the two rings: inner dims + frame stride as on the host, outer dims compacted
+    cvvdp_b200_clip dev_clip[2];
+    int order[2][4];
+    long long dstr[2][5];
+    for (int v = 0; v < 2; ++v) {
+        const cvvdp_b200_clip *c = clips[v];
+        for (int k = 0; k < hl[v].n_outer; ++k) order[v][k] = hl[v].outer_dims[k];
+        std::sort(order[v], order[v] + hl[v].n_outer, [&](int a, int b) { return c->stride[a] < c->stride[b]; });
+        for (int d = 0; d < 5; ++d) dstr[v][d] = c->stride[d];
+        long long ostride = (long long)ring * c->stride[2];
+        for (int k = 0; k < hl[v].n_outer; ++k) {
+            dstr[v][order[v][k]] = ostride;
+            ostride *= hl[v].extent[order[v][k]];
+        }
+        dev_clip[v] = *c;
+        dev_clip[v].data = ctx->stage[0].buf[v];
+        dev_clip[v].frame0 = 0;
+        dev_clip[v].n_frames = ring;
+        for (int d = 0; d < 5; ++d) dev_clip[v].stride[d] = dstr[v][d];
+    }
+
+    static const bool dbg_tl = getenv("CVVDP_B200_DEBUG_TIMELINE") != nullptr;
+    static const bool skip_compute = getenv("CVVDP_B200_DEBUG_SKIP_COMPUTE") != nullptr;  // upload-only timing probe
+    std::vector<cudaEvent_t> tl;  // per chunk: copy begin, copy end, compute begin, compute end
+    auto tl_mark = [&](cudaStream_t s) {
+        if (!dbg_tl) return;
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, 0);
+        cudaEventRecord(e, s);
+        tl.push_back(e);
+    };
+    int blk = 0, up_lo = 0, up_hi = 0;  // frames [up_lo, up_hi) are resident in the ring
+    for (int f0 = frame_begin, f1; f0 < frame_end; f0 = f1, ++blk) {
+        // full chunks, then a tapered tail (8, 4, 4 frames) so that little compute is left once the last
+        // byte has arrived
+        const int rem = frame_end - f0;
+        f1 = f0 + (rem > nb ? nb : (rem > 4 ? (rem + 1) / 2 : rem));
+        Staging &sg = ctx->stage[blk & 1];  // events only; the data lives in the ring of stage[0]
         int wlo, whi;
         needed_frames(ctx, f0, f1, &wlo, &whi);
-        if (whi - wlo > cap_frames) return fail(ctx, CVVDP_ERR_STATE, "internal: staging window too small");
+        if (whi - wlo > ring - nb) return fail(ctx, CVVDP_ERR_STATE, "internal: staging ring too small");
+        // uploading this chunk overwrites slots last read by the chunk two steps back
         if (blk >= 2) CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, sg.consumed, 0));
-        cvvdp_b200_clip dev_clip[2];
+        tl_mark(ctx->copy_stream);
+        const int new_lo = (blk > 0 && wlo >= up_lo && wlo <= up_hi) ? std::min(up_hi, whi) : wlo;
         for (int v = 0; v < 2; ++v) {
             const cvvdp_b200_clip *c = clips[v];
             const long long sF = c->stride[2];
-            dev_clip[v] = *c;
-            dev_clip[v].data = sg.buf[v];
-            dev_clip[v].frame0 = wlo;
-            dev_clip[v].n_frames = whi - wlo;
-            // device strides: inner dims + frame stride unchanged, outer dims compacted
-            long long ostride = (long long)cap_frames * sF;
-            // outer dims ordered by ascending host stride get ascending device strides
-            int order[4];
-            for (int k = 0; k < hl[v].n_outer; ++k) order[k] = hl[v].outer_dims[k];
-            std::sort(order, order + hl[v].n_outer, [&](int a, int b) { return c->stride[a] < c->stride[b]; });
-            long long dstr[5];
-            for (int d = 0; d < 5; ++d) dstr[d] = c->stride[d];
-            for (int k = 0; k < hl[v].n_outer; ++k) {
-                dstr[order[k]] = ostride;
-                ostride *= hl[v].extent[order[k]];
-            }
-            for (int d = 0; d < 5; ++d) dev_clip[v].stride[d] = dstr[d];
-            // per outer index: frames already resident in the previous staging buffer move device to
-            // device, the rest is one contiguous host-to-device span
-            const int reuse_hi = (blk > 0 && wlo >= pwlo && wlo < pwhi) ? std::min(whi, pwhi) : wlo;
-            const Staging &prev = ctx->stage[(blk & 1) ^ 1];
             long long idx[4] = {0, 0, 0, 0};
             for (long long oi = 0; oi < n_outer_idx[v]; ++oi) {
-                long long hoff = (long long)(reuse_hi - c->frame0) * sF, doff = 0;
+                long long hbase = 0, dbase = 0;
                 for (int k = 0; k < hl[v].n_outer; ++k) {
-                    hoff += idx[k] * c->stride[order[k]];
-                    doff += idx[k] * dstr[order[k]];
+                    hbase += idx[k] * c->stride[order[v][k]];
+                    dbase += idx[k] * dstr[v][order[v][k]];
                 }
-                if (reuse_hi > wlo)
-                    CU_CHECK(ctx, cudaMemcpyAsync((char *)sg.buf[v] + doff * esz,
-                                                  (const char *)prev.buf[v] + (doff + (long long)(wlo - pwlo) * sF) * esz,
-                                                  (size_t)(reuse_hi - wlo) * sF * esz, cudaMemcpyDeviceToDevice, ctx->copy_stream));
-                if (whi > reuse_hi)
-                    CU_CHECK(ctx, cudaMemcpyAsync((char *)sg.buf[v] + (doff + (long long)(reuse_hi - wlo) * sF) * esz,
-                                                  (const char *)c->data + hoff * esz, (size_t)(whi - reuse_hi) * sF * esz,
-                                                  cudaMemcpyHostToDevice, ctx->copy_stream));
+                // frames [new_lo, whi) go to slots f % ring: at most two contiguous runs
+                for (int fa = new_lo; fa < whi;) {
+                    const int slot = fa % ring;
+                    const int run = std::min(whi - fa, ring - slot);
+                    CU_CHECK(ctx, cudaMemcpyAsync((char *)ctx->stage[0].buf[v] + (dbase + (long long)slot * sF) * esz,
+                                                  (const char *)c->data + (hbase + (long long)(fa - c->frame0) * sF) * esz,
+                                                  (size_t)run * sF * esz, cudaMemcpyHostToDevice, ctx->copy_stream));
+                    fa += run;
+                }
                 for (int k = 0; k < hl[v].n_outer; ++k) {
-                    if (++idx[k] < hl[v].extent[order[k]]) break;
+                    if (++idx[k] < hl[v].extent[order[v][k]]) break;
                     idx[k] = 0;
                 }
             }
         }
+        up_lo = (new_lo == wlo) ? wlo : std::max(up_lo, whi - ring);
+        up_hi = whi;
         CU_CHECK(ctx, cudaEventRecord(sg.copied, ctx->copy_stream));
+        tl_mark(ctx->copy_stream);
         CU_CHECK(ctx, cudaStreamWaitEvent(ctx->work_stream, sg.copied, 0));
-        if ((rc = run_block(ctx, &dev_clip[0], &dev_clip[1], f0, f1, ctx->q_dev, ctx->hm_dev, ctx->work_stream)) != CVVDP_OK)
+        tl_mark(ctx->work_stream);
+        if (!skip_compute &&
+            (rc = run_block(ctx, &dev_clip[0], &dev_clip[1], f0, f1, ctx->q_dev, ctx->hm_dev, ctx->work_stream, ring)) != CVVDP_OK)
             return rc;
         CU_CHECK(ctx, cudaEventRecord(sg.consumed, ctx->work_stream));
-        pwlo = wlo;
-        pwhi = whi;
+        tl_mark(ctx->work_stream);
     }
     CU_CHECK(ctx, cudaMemcpyAsync(q_per_ch_host, ctx->q_dev, q_bytes, cudaMemcpyDeviceToHost, ctx->work_stream));
     if (do_hm) {
@@ -921,6 +946,14 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
     }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->work_stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (dbg_tl) {
+        for (size_t i = 0; i + 3 < tl.size(); i += 4) {
+            float t[4];
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tl[0], tl[i + k]);
+            fprintf(stderr, "[cvvdp timeline] chunk %zu: copy %.2f-%.2f ms, compute %.2f-%.2f ms\n", i / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (auto e : tl) cudaEventDestroy(e);
+    }
     return CVVDP_OK;
 }
 

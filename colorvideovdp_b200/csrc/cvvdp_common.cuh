@@ -122,7 +122,9 @@ struct ClipView {
     const void *data;
     long long s[5];  // element strides B, C, F, H, W
     int frame0, n_frames;
+    int ring;  // > 0: frames live in a ring of that many slots (frame f at slot f % ring); 0: linear view
 };
+__device__ __forceinline__ int frame_slot(const ClipView &cv, int f) { return cv.ring > 0 ? f % cv.ring : f - cv.frame0; }
 
 struct DisplayDev {
     int eotf;

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
         int s = t;
         if (s < 0) s = (a.padding == CVVDP_PAD_REPLICATE) ? 0 : symmetric_frame_index(s, a.F_total);
         if (s != last_s) {
-            pixel_to_dkl(cv, base, s - cv.frame0, a.cin, a.dtype, a.dd, d0, d1, d2);
+            pixel_to_dkl(cv, base, frame_slot(cv, s), a.cin, a.dtype, a.dd, d0, d1, d2);
             last_s = s;
         }
         ring[(slot * 3 + 0) * CVVDP_TEMPORAL_THREADS + tid] = d0;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_reg(const T
     if (p >= npix) return;
     const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
     const ClipView &cv = a.clip[v];
-    const long long base = b * cv.s[0] + y * cv.s[3] + x * cv.s[4] - (long long)cv.frame0 * cv.s[2];
+    const long long base = b * cv.s[0] + y * cv.s[3] + x * cv.s[4];
     const int n = a.f1 - a.f0;
     float4 *out = a.out + ((long long)b * n * 2 + v) * npix + p;
     float r0[FL], r1[FL], r2[FL];
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_reg(const T
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
     // ---- warm-up: the FL-1 frames before f0 (temporal padding before frame 0) fill slots 0..FL-2 ----
     int src = temporal_source_frame(a, a.f0 - (FL - 1)), last_src = -1;
-    load_bits<USE_LUT>(a, cv, base, src, bits);
+    load_bits<USE_LUT>(a, cv, base, frame_slot(cv, src), bits);
 #pragma unroll
     for (int s = 0; s < FL - 1; ++s) {
         if (src != last_src) {
@@ -309,13 +309,15 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_reg(const T
             last_src = src;
         }
         const int nsrc = temporal_source_frame(a, a.f0 - (FL - 1) + s + 1);
-        if (nsrc != src) load_bits<USE_LUT>(a, cv, base, nsrc, bits);
+        if (nsrc != src) load_bits<USE_LUT>(a, cv, base, frame_slot(cv, nsrc), bits);
         src = nsrc;
         r0[s] = d0;
         r1[s] = d1;
         r2[s] = d2;
     }
     // ---- steady state: frame t = f0 + j goes to slot (FL-1+j) mod FL; `bits` holds frame t ----
+    int nslot = frame_slot(cv, a.f0);  // slot of the frame held in `bits`, advanced incrementally
+    const int slots = cv.ring > 0 ? cv.ring : 0x7fffffff;
     for (int tb = a.f0; tb < a.f1; tb += FL) {
 #pragma unroll
         for (int j = 0; j < FL; ++j) {
@@ -329,7 +331,8 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_reg(const T
                     r2[s] = d2;
                 }
                 last_src = -1;
-                if (t + 1 < a.f1) load_bits<USE_LUT>(a, cv, base, t + 1, bits);  // prefetch
+                nslot = nslot + 1 == slots ? 0 : nslot + 1;
+                if (t + 1 < a.f1) load_bits<USE_LUT>(a, cv, base, nslot, bits);  // prefetch
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
 #pragma unroll
                 for (int k = 0; k < FL; ++k) {  // tap k <-> frame t-(FL-1)+k <-> slot (s+1+k) mod FL
