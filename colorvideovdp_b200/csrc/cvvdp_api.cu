@@ -27,6 +27,9 @@ struct LevelBuf {
     int tiles_x = 0, tiles_y = 0;  // band kernel grid: column strips x row segments
     int seg_rows = 0;
     int do_blur = 0;
+    TensorMap3D tm;  // fp32 view [planes][h][4w] of g; box depends on the role (see make_tensor_map)
+    TensorMap3D tm_as_coarse;
+    bool tm_ok = false;
 };
 
 struct Staging {
@@ -90,6 +93,41 @@ int fail(cvvdp_b200_ctx *ctx, int code, const char *fmt, ...) {
     } while (0)
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Tiled tensor map over `planes` float4 planes of h x w pixels, viewed as fp32 [planes][h][4w].
+bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int planes, int box_px, int box_rows) {
+#ifdef CVVDP_EMU
+    m->base = (const float *)base;
+    m->dim[0] = 4 * w;
+    m->dim[1] = h;
+    m->dim[2] = planes;
+    m->stride[0] = 1;
+    m->stride[1] = 4LL * w;
+    m->stride[2] = 4LL * w * h;
+    m->box[0] = 4 * box_px;
+    m->box[1] = box_rows;
+    m->box[2] = 2;
+    return true;
+#else
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+        encode = (EncodeFn)fn;
+    }
+    if (4 * box_px > 256 || box_rows > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)4 * w, (cuuint64_t)h, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)w * 16, (cuuint64_t)w * h * 16};  // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)(4 * box_px), (cuuint32_t)box_rows, 2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+#endif
+}
 
 // Brackets one kernel launch with events when profiling is on; always counts the launch.
 struct LaunchScope {
@@ -338,9 +376,25 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         const int e = ctx->disp.eotf;
         const bool use_lut = job.dtype == CVVDP_DTYPE_U8 &&
                              (e == CVVDP_EOTF_SRGB || e == CVVDP_EOTF_PQ || e == CVVDP_EOTF_LINEAR || e == CVVDP_EOTF_GAMMA);
+        // staged (cp.async) variant: dense, 16-byte aligned planes and whole warps
+        bool staged = npix % 32 == 0 && job.in_channels <= 3;
+        static const bool no_stage = getenv("CVVDP_B200_NO_TSTAGE") != nullptr;
+        if (no_stage) staged = false;
+        for (int v = 0; v < 2 && staged; ++v) {
+            const ClipView &cvw = ta.clip[v];
+            const long long es = (long long)dtype_size(job.dtype);
+            if (cvw.s[4] != 1 || cvw.s[3] != job.width) staged = false;
+            if (((uintptr_t)cvw.data) % 16 || (cvw.s[0] * es) % 16 || (cvw.s[1] * es) % 16 || (cvw.s[2] * es) % 16) staged = false;
+        }
 #define CVVDP_TEMPORAL_CASE(FLV)                                                              \
     case FLV: {                                                                               \
-        if (use_lut) {                                                                        \
+        if (staged && use_lut) {                                                              \
+            auto kfn = k_temporal_stg<FLV, true>;                                             \
+            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
+        } else if (staged) {                                                                  \
+            auto kfn = k_temporal_stg<FLV, false>;                                            \
+            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
+        } else if (use_lut) {                                                                 \
             auto kfn = k_temporal_reg<FLV, true>;                                             \
             CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
         } else {                                                                              \
@@ -416,6 +470,12 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ba.hm_beta = P.beta_tch;
         ba.hm_scale = (i == 0) ? 1.f : 0.5f;
         ba.seg_rows = lv.seg_rows;
+        static const bool no_tma = getenv("CVVDP_B200_NO_TMA") != nullptr;  // A/B switch: cp.async staging instead
+        ba.use_tma = (lv.tm_ok && ctx->lv[i + 1].tm_ok && !no_tma) ? 1 : 0;
+        if (ba.use_tma) {
+            ba.tm_fine = lv.tm;
+            ba.tm_coarse = ctx->lv[i + 1].tm_as_coarse;
+        }
         dim3 grid(lv.tiles_x, lv.tiles_y, pairs);
         auto kfn = k_band2;
         LaunchScope ls(ctx, st, CVVDP_K_BAND, i,
@@ -713,6 +773,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.partials = (float *)(base + off_p[i]);
         lv.hm = do_hm ? (float *)(base + off_h[i]) : nullptr;
         lv.lut = (float4 *)(base + off_l[i]);
+        lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_EW, CVVDP_B2_RB) &&
+                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_CC, CVVDP_B2_CR);
         float rows[4][CVVDP_CSF_LUT_N];
         for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
         float packed[CVVDP_CSF_LUT_N][4];

@@ -7,9 +7,10 @@
 #define CVVDP_LAUNCH(kfn, grid, block, smem, stream, ...) \
     emu::launch(grid, block, smem, [&]() { kfn(__VA_ARGS__); })
 #else
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
-#define CVVDP_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define CVVDP_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
 #define CVVDP_LAUNCH(kfn, grid, block, smem, stream, ...) kfn<<<grid, block, smem, stream>>>(__VA_ARGS__)
 #endif
 
@@ -102,20 +103,126 @@ __device__ __forceinline__ void cp_async_commit() {
     asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
 }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_n() {  // at most N of this thread's groups still in flight
+#ifdef __CUDA_ARCH__
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async_wait_all() {
 #ifdef __CUDA_ARCH__
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 #endif
 }
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier ---------------------------------------------------------
+// A 3-D tiled tensor map over an array of float4 planes viewed as fp32 [plane][row][4*w].
+#ifdef CVVDP_EMU
+struct TensorMap3D {
+    const float *base;
+    int dim[3];          // 4*w, h, planes
+    long long stride[3]; // in floats
+    int box[3];
+};
+#else
+typedef CUtensorMap TensorMap3D;
+#endif
+
+#ifdef CVVDP_EMU
+// mock device: the copy is synchronous; *bar counts completed phases
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int) { *bar = 0; }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *, unsigned) {}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    while (((*(volatile unsigned long long *)bar) & 1ull) == parity) emu::yield_runnable();
+}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const TensorMap3D *map, int c0, int c1, int c2,
+                                            unsigned long long *) {
+    float *dst = (float *)smem_dst;
+    for (int z = 0; z < map->box[2]; ++z)
+        for (int y = 0; y < map->box[1]; ++y)
+            for (int x = 0; x < map->box[0]; ++x) {
+                const int gx = c0 + x, gy = c1 + y, gz = c2 + z;
+                const bool in = gx >= 0 && gx < map->dim[0] && gy >= 0 && gy < map->dim[1] && gz >= 0 && gz < map->dim[2];
+                dst[((long long)z * map->box[1] + y) * map->box[0] + x] =
+                    in ? map->base[gz * map->stride[2] + gy * map->stride[1] + gx * map->stride[0]] : 0.f;
+            }
+}
+__device__ __forceinline__ void mbar_emu_complete(unsigned long long *bar) { *bar += 1; }
+#else
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Tile load: box at element coordinates (c0, c1, c2) = (4*x, row, plane); out-of-bounds elements are
+// zero-filled; completion is signalled on `bar` with the full box byte count.
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const TensorMap3D *map, int c0, int c1, int c2,
+                                            unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            (unsigned)__cvta_generic_to_shared(smem_dst)),
+        "l"(map), "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_emu_complete(unsigned long long *) {}
+#endif
+
 // ---- float4 arithmetic ------------------------------------------------------------------------
+// On sm_100 the four lanes of a pixel are processed as two packed fp32x2 operations (FFMA2 / FADD2 /
+// FMUL2, PTX fma.rn.f32x2): same IEEE results per lane, half the issue slots -- these kernels are
+// bound by instruction issue, not by the FP32 lanes.
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+#if defined(__CUDA_ARCH__) && !defined(CVVDP_NO_F32X2)
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) {
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 operator-(float4 a, float4 b) {
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(-b.x, -b.y));
+    const float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(-b.z, -b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 operator*(float s, float4 a) {
+    const float2 ss = make_float2(s, s);
+    const float2 lo = __fmul2_rn(ss, make_float2(a.x, a.y)), hi = __fmul2_rn(ss, make_float2(a.z, a.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 fma4(float s, float4 a, float4 acc) {
+    const float2 ss = make_float2(s, s);
+    const float2 lo = __ffma2_rn(ss, make_float2(a.x, a.y), make_float2(acc.x, acc.y));
+    const float2 hi = __ffma2_rn(ss, make_float2(a.z, a.w), make_float2(acc.z, acc.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+#else
 __device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
 __device__ __forceinline__ float4 operator*(float s, float4 a) { return make_float4(s * a.x, s * a.y, s * a.z, s * a.w); }
 __device__ __forceinline__ float4 fma4(float s, float4 a, float4 acc) {
     return make_float4(fmaf(s, a.x, acc.x), fmaf(s, a.y, acc.y), fmaf(s, a.z, acc.z), fmaf(s, a.w, acc.w));
 }
+#endif
 
 // ---- kernel argument structures ----------------------------------------------------------------
 struct ClipView {

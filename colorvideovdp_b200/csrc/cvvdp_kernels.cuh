@@ -296,9 +296,15 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_reg(const T
     const long long base = b * cv.s[0] + y * cv.s[3] + x * cv.s[4];
     const int n = a.f1 - a.f0;
     float4 *out = a.out + ((long long)b * n * 2 + v) * npix + p;
-    float r0[FL], r1[FL], r2[FL];
+    // ring period RP = FL + 1 (even): one spare slot keeps the parity of the unrolled position static,
+    // so the two raw-value register sets (even/odd frames) never have to be moved while a load is in flight
+    constexpr int RP = FL + 1;
+    float r0[RP], r1[RP], r2[RP];
+#pragma unroll
+    for (int i = 0; i < RP; ++i) r0[i] = r1[i] = r2[i] = 0.f;
     unsigned bits[3];
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    (void)n;
     // ---- warm-up: the FL-1 frames before f0 (temporal padding before frame 0) fill slots 0..FL-2 ----
     int src = temporal_source_frame(a, a.f0 - (FL - 1)), last_src = -1;
     load_bits<USE_LUT>(a, cv, base, frame_slot(cv, src), bits);
@@ -315,37 +321,148 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_reg(const T
         r1[s] = d1;
         r2[s] = d2;
     }
-    // ---- steady state: frame t = f0 + j goes to slot (FL-1+j) mod FL; `bits` holds frame t ----
-    int nslot = frame_slot(cv, a.f0);  // slot of the frame held in `bits`, advanced incrementally
+    // ---- steady state: frame t = f0 + j goes to ring slot (FL-1+j) mod RP.  Frames at even j use the raw
+    // set `bits`, odd j the set `bitsB`; the load of frame t+2 is issued into the set that frame t has
+    // just vacated, so every load has two full iterations (~250 instructions of this warp) to land.
+    int nslot = frame_slot(cv, a.f0);  // clip slot of the frame being prefetched, advanced incrementally
     const int slots = cv.ring > 0 ? cv.ring : 0x7fffffff;
-    for (int tb = a.f0; tb < a.f1; tb += FL) {
+    unsigned bitsB[3] = {0u, 0u, 0u};
+    nslot = nslot + 1 == slots ? 0 : nslot + 1;
+    if (a.f0 + 1 < a.f1) load_bits<USE_LUT>(a, cv, base, nslot, bitsB);
+    float4 *outp = out;
+    const long long ostep = 2 * npix;
+    for (int tb = a.f0; tb < a.f1; tb += RP) {
 #pragma unroll
-        for (int j = 0; j < FL; ++j) {
+        for (int j = 0; j < RP; ++j) {
             const int t = tb + j;
             if (t < a.f1) {  // uniform
-                const int s = (FL - 1 + j) % FL;
-                if (FL == 1 || src != last_src) bits_to_dkl<USE_LUT>(a, s_lut, bits, r0[s], r1[s], r2[s]);
-                else {  // the clip's frame 0 repeated by replicate padding (only right after the warm-up)
-                    r0[s] = d0;
-                    r1[s] = d1;
-                    r2[s] = d2;
-                }
-                last_src = -1;
+                const int s = (FL - 1 + j) % RP;
                 nslot = nslot + 1 == slots ? 0 : nslot + 1;
-                if (t + 1 < a.f1) load_bits<USE_LUT>(a, cv, base, nslot, bits);  // prefetch
+                if ((j & 1) == 0) {
+                    bits_to_dkl<USE_LUT>(a, s_lut, bits, r0[s], r1[s], r2[s]);
+                    if (t + 2 < a.f1) load_bits<USE_LUT>(a, cv, base, nslot, bits);  // prefetch, distance 2
+                } else {
+                    bits_to_dkl<USE_LUT>(a, s_lut, bitsB, r0[s], r1[s], r2[s]);
+                    if (t + 2 < a.f1) load_bits<USE_LUT>(a, cv, base, nslot, bitsB);
+                }
                 float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
 #pragma unroll
-                for (int k = 0; k < FL; ++k) {  // tap k <-> frame t-(FL-1)+k <-> slot (s+1+k) mod FL
-                    const int sl = (s + 1 + k) % FL;
+                for (int k = 0; k < FL; ++k) {  // tap k <-> frame t-(FL-1)+k <-> slot (s-(FL-1)+k) mod RP
+                    const int sl = (s + RP - (FL - 1) + k) % RP;
                     o0 = fmaf(a.taps[0][k], r0[sl], o0);
                     o1 = fmaf(a.taps[1][k], r1[sl], o1);
                     o2 = fmaf(a.taps[2][k], r2[sl], o2);
                     o3 = fmaf(a.taps[3][k], r0[sl], o3);
                 }
-                out[(long long)(t - a.f0) * 2 * npix] = make_float4(o0, o1, o2, o3);
+                *outp = make_float4(o0, o1, o2, o3);
+                outp += ostep;
             }
         }
     }
+}
+
+// Staged variant: the raw pixels reach the thread through a per-warp ring in shared memory that is
+// filled with cp.async (LDGSTS) CVVDP_TSTG_DEPTH-1 frames ahead, so the prefetch distance is set by
+// `cp.async.wait_group`, not by how the compiler schedules loads and scoreboards.  A warp owns 32
+// consecutive pixels; for every frame a few lanes each copy one 16-byte piece of the warp's
+// (channel, frame) row segment.  Needs dense planes (stride_W = 1, stride_H = W), H*W % 32 == 0 and
+// 16-byte aligned planes -- the host checks that and otherwise launches k_temporal_reg.
+#define CVVDP_TSTG_DEPTH 4
+template <int FL, bool USE_LUT>
+__global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_stg(const TemporalArgs a) {
+    __shared__ float s_lut[256];
+    __shared__ __align__(16) unsigned char s_stage[(CVVDP_TEMPORAL_THREADS / 32) * CVVDP_TSTG_DEPTH * 3 * 32 * 4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (USE_LUT) {
+        float v[1] = {(float)tid / 255.0f};
+        eotf_forward(v, 1, a.dd);
+        s_lut[tid] = v[0];
+        __syncthreads();
+    }
+    const long long npix = (long long)a.H * a.W;
+    const long long p = (long long)blockIdx.x * CVVDP_TEMPORAL_THREADS + tid;
+    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
+    if (p - lane >= npix) return;  // whole warps only (npix % 32 == 0)
+    const ClipView &cv = a.clip[v];
+    const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
+    const int row_bytes = 32 * esz;            // one (channel, frame) segment of this warp
+    const int frame_bytes = a.cin * row_bytes;  // <= 384
+    const int cpc = row_bytes / 16;             // 16-byte pieces per channel segment
+    const int npieces = a.cin * cpc;            // lanes that copy
+    unsigned char *wst = s_stage + warp * (CVVDP_TSTG_DEPTH * 3 * 32 * 4);
+    // this lane's piece: source byte offset (without the frame term) and destination offset in a stage slot
+    const int pch = lane / cpc, ppart = lane - pch * cpc;
+    const long long wbase = b * cv.s[0] + (p - lane);  // element offset of the warp's first pixel (dense plane)
+    const unsigned char *psrc = (const unsigned char *)cv.data + (wbase + (long long)pch * cv.s[1]) * esz + ppart * 16;
+    const int pdst = pch * row_bytes + ppart * 16;
+    const long long fstride = cv.s[2] * esz;
+    const int n = a.f1 - a.f0;
+    const int NI = (FL - 1) + n;  // iterations: warm-up frames, then the block's frames
+    float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + p;
+    const long long ostep = 2 * npix;
+    constexpr int RP = FL + 1;
+    float r0[RP], r1[RP], r2[RP];
+#pragma unroll
+    for (int i = 0; i < RP; ++i) r0[i] = r1[i] = r2[i] = 0.f;
+
+    // issue the copies of iteration `it` (frame t = f0-(FL-1)+it, padded before frame 0) into stage slot it % DEPTH
+    auto issue = [&](int it) {
+        if (it < NI && lane < npieces) {
+            const int t = a.f0 - (FL - 1) + it;
+            const int slot = frame_slot(cv, temporal_source_frame(a, t));
+            cp_async16(wst + (it & (CVVDP_TSTG_DEPTH - 1)) * (3 * 32 * 4) + pdst, psrc + (long long)slot * fstride);
+        }
+        cp_async_commit();
+    };
+    // wait for iteration `it`, read this lane's raw values
+    auto fetch = [&](int it, unsigned bits[3]) {
+        issue(it + CVVDP_TSTG_DEPTH - 1);
+        cp_async_wait_n<CVVDP_TSTG_DEPTH - 1>();
+        __syncwarp();
+        const unsigned char *q = wst + (it & (CVVDP_TSTG_DEPTH - 1)) * (3 * 32 * 4);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const unsigned char *qc = q + (a.cin == 3 ? c : 0) * row_bytes;
+            if (esz == 1) bits[c] = qc[lane];
+            else if (esz == 2) bits[c] = ((const unsigned short *)qc)[lane];
+            else bits[c] = ((const unsigned *)qc)[lane];
+        }
+        __syncwarp();  // every lane has read the slot before it is refilled
+    };
+#pragma unroll
+    for (int i = 0; i < CVVDP_TSTG_DEPTH - 1; ++i) issue(i);
+    unsigned bits[3];
+    int it = 0;
+    // ---- warm-up: slots 0..FL-2 ----
+#pragma unroll
+    for (int s = 0; s < FL - 1; ++s) {
+        fetch(it++, bits);
+        bits_to_dkl<USE_LUT>(a, s_lut, bits, r0[s], r1[s], r2[s]);
+    }
+    // ---- steady state ----
+    for (int tb = a.f0; tb < a.f1; tb += RP) {
+#pragma unroll
+        for (int j = 0; j < RP; ++j) {
+            const int t = tb + j;
+            if (t < a.f1) {  // uniform
+                const int s = (FL - 1 + j) % RP;
+                fetch(it++, bits);
+                bits_to_dkl<USE_LUT>(a, s_lut, bits, r0[s], r1[s], r2[s]);
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+                for (int k = 0; k < FL; ++k) {
+                    const int sl = (s + RP - (FL - 1) + k) % RP;
+                    o0 = fmaf(a.taps[0][k], r0[sl], o0);
+                    o1 = fmaf(a.taps[1][k], r1[sl], o1);
+                    o2 = fmaf(a.taps[2][k], r2[sl], o2);
+                    o3 = fmaf(a.taps[3][k], r0[sl], o3);
+                }
+                *outp = make_float4(o0, o1, o2, o3);
+                outp += ostep;
+            }
+        }
+    }
+    cp_async_wait_all();
 }
 
 // =================================================================================================
@@ -473,6 +590,9 @@ struct BandArgs {
     float hm_w[4];         // heat map: channel weights (x image_int)
     float hm_beta, hm_scale;  // beta_tch, 1/band_mul (lpyr_dec.py:308-314)
     int seg_rows;          // k_band2: rows per vertical segment (multiple of 8)
+    int use_tma;           // k_band2: stage the rows with TMA (else cp.async)
+    TensorMap3D tm_fine;   // fp32 view [planes][h][4w] of level i,   box {256, 8, 2}
+    TensorMap3D tm_coarse; // fp32 view [planes][hc][4wc] of level i+1, box {136, 6, 2}
 };
 
 struct BandSmem {
@@ -727,20 +847,32 @@ __global__ void __launch_bounds__(CVVDP_BAND_THREADS) k_band(const BandArgs a) {
 #define CVVDP_B2_CC (CVVDP_B2_EW / 2 + 2)  // 34 coarse columns
 
 struct Band2Smem {
-    float4 lut[CVVDP_CSF_LUT_N];
+    float4 lut[CVVDP_CSF_LUT_N];                      // 512 B: keeps the TMA destinations 128-byte aligned
     float4 crs[2][CVVDP_B2_CR][CVVDP_B2_CC];          // coarse rows of the current step (cp.async stage)
     float4 fine[2][CVVDP_B2_RB][CVVDP_B2_EW];         // fine rows of the current step (cp.async stage)
     float4 mm[CVVDP_B2_RB][CVVDP_B2_EW + 1];
     float4 hb[CVVDP_B2_HBR][CVVDP_B2_SW + 1];
     float4 df[CVVDP_B2_DFR][CVVDP_B2_SW];
     float red[CVVDP_B2_THREADS / 32][4];
+    unsigned long long bar;                           // mbarrier of the TMA stage
 };
+#define CVVDP_B2_STAGE_BYTES ((unsigned)(sizeof(float4) * 2 * (CVVDP_B2_CR * CVVDP_B2_CC + CVVDP_B2_RB * CVVDP_B2_EW)))
 
 // Asynchronous stage of one step: the 8 fine rows [a0, a0+8) x 64 columns of both videos and the 6
 // coarse rows under them (replicate-clamped, lpyr_dec.py:136-141).  Issued one step ahead.
 __device__ __forceinline__ void band2_stage(const BandArgs &a, Band2Smem &sm, const float4 *fine_t, const float4 *crs_g,
-                                            long long npix, long long ncpix, int a0, int a_end, int ex0, int tid) {
+                                            long long npix, long long ncpix, int a0, int a_end, int ex0, int tid, int pair) {
     const int cy0 = a0 / 2 - 1, cx0 = ex0 / 2 - 1;
+    if (a.use_tma) {  // two bulk tensor copies issued by one thread; out-of-range elements arrive as zeros
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.bar, CVVDP_B2_STAGE_BYTES);
+            tma_load_3d(&sm.fine[0][0][0], &a.tm_fine, 4 * ex0, a0, 2 * pair, &sm.bar);
+            tma_load_3d(&sm.crs[0][0][0], &a.tm_coarse, 4 * cx0, cy0, 2 * pair, &sm.bar);
+            mbar_emu_complete(&sm.bar);
+        }
+        return;
+    }
     for (int i = tid; i < 2 * CVVDP_B2_CR * CVVDP_B2_CC; i += CVVDP_B2_THREADS) {
         const int v = i / (CVVDP_B2_CR * CVVDP_B2_CC), rem = i - v * (CVVDP_B2_CR * CVVDP_B2_CC);
         const int r = rem / CVVDP_B2_CC, c = rem - r * CVVDP_B2_CC;
@@ -763,7 +895,7 @@ __device__ __forceinline__ void band2_stage(const BandArgs &a, Band2Smem &sm, co
     cp_async_commit();
 }
 
-__global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const BandArgs a) {
+__global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_constant__ BandArgs a) {
     CVVDP_DYN_SMEM(smem_raw);
     Band2Smem &sm = *reinterpret_cast<Band2Smem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -778,7 +910,13 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const BandArgs a)
     const float4 *crs_g = a.coarse + (long long)pair * 2 * ncpix;
     const bool x_edge = (ex0 < 0) || (x0 + CVVDP_B2_SW + hal > a.w);  // strip touches the left/right border
 
-    band2_stage(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid);
+    if (a.use_tma) {
+        if (tid == 0) mbar_init(&sm.bar, 1);
+        __syncthreads();
+    }
+    unsigned tma_phase = 0;
+    const int cx0 = ex0 / 2 - 1;
+    band2_stage(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, pair);
     if (tid < CVVDP_CSF_LUT_N) sm.lut[tid] = a.lut[tid];
     float eps_q[4];
 #pragma unroll
@@ -795,7 +933,26 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const BandArgs a)
 
     for (int a0 = y_begin; a0 - hal < ye; a0 += CVVDP_B2_RB) {
         const bool have_a = a0 < a_end;
-        cp_async_wait_all();
+        if (a.use_tma) {
+            if (have_a) {
+                mbar_wait(&sm.bar, tma_phase);
+                tma_phase ^= 1u;
+                // TMA zero-fills outside the coarse image; the reference pads by replication
+                // (lpyr_dec.py:136-141): patch those entries from the nearest valid row/column
+                const int cy0 = a0 / 2 - 1;
+                if (cy0 < 0 || cy0 + CVVDP_B2_CR > a.hc || cx0 < 0 || cx0 + CVVDP_B2_CC > a.wc) {
+                    for (int i = tid; i < 2 * CVVDP_B2_CR * CVVDP_B2_CC; i += CVVDP_B2_THREADS) {
+                        const int v = i / (CVVDP_B2_CR * CVVDP_B2_CC), rem = i - v * (CVVDP_B2_CR * CVVDP_B2_CC);
+                        const int r = rem / CVVDP_B2_CC, c = rem - r * CVVDP_B2_CC;
+                        const int rr = min(max(cy0 + r, 0), a.hc - 1) - cy0, cc = min(max(cx0 + c, 0), a.wc - 1) - cx0;
+                        if ((rr != r || cc != c) && rr >= 0 && rr < CVVDP_B2_CR && cc >= 0 && cc < CVVDP_B2_CC)
+                            sm.crs[v][r][c] = sm.crs[v][rr][cc];
+                    }
+                }
+            }
+        } else {
+            cp_async_wait_all();
+        }
         __syncthreads();  // the stage of this step has landed; previous phase C is complete
         // ---- phase A: one 2x2 quad per thread: expand, contrast, CSF -> mm, df ----
         if (have_a) {
@@ -831,7 +988,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const BandArgs a)
         }
         __syncthreads();
         // ---- prefetch the next step's stage while phases B and C run ----
-        if (a0 + CVVDP_B2_RB < a_end) band2_stage(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B2_RB, a_end, ex0, tid);
+        if (a0 + CVVDP_B2_RB < a_end) band2_stage(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B2_RB, a_end, ex0, tid, pair);
         // ---- phase B: horizontal pass of the phase-uncertainty Gaussian for the new rows ----
         if (have_a && a.do_blur && tid < CVVDP_B2_RB * (CVVDP_B2_SW / 4)) {
             const int gy = a0 + b_r, gxb = x0 + b_xg * 4;

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+N=${1:-2}
+nvidia-smi -L > gpurun_out/multi_env.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus $N --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/bench_n$N.txt 2> gpurun_out/bench_n$N.err
+echo "rc=$?" >> gpurun_out/bench_n$N.err
+tail -n 5 gpurun_out/bench_n$N.err; tail -c 1500 gpurun_out/bench_n$N.txt

@@ -31,6 +31,7 @@
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
 #define __constant__ static
+#define __grid_constant__
 
 struct dim3 {
     unsigned x, y, z;
@@ -76,6 +77,10 @@ inline void fiber_entry() {
 }
 inline void syncthreads() {
     S().cur->state = WAIT_BLOCK;
+    yield_to_main();
+}
+inline void yield_runnable() {  // spin-wait helper (mbarrier emulation): stay runnable, let others run
+    S().cur->state = RUNNABLE;
     yield_to_main();
 }
 inline void syncwarp() {
