@@ -29,6 +29,7 @@ struct LevelBuf {
     int do_blur = 0;
     TensorMap3D tm;  // fp32 view [planes][h][4w] of g; box depends on the role (see make_tensor_map)
     TensorMap3D tm_as_coarse;
+    TensorMap3D tm_reduce_in;  // box {63 px, 19 rows, 1 plane}
     bool tm_ok = false;
 };
 
@@ -54,6 +55,7 @@ struct cvvdp_b200_ctx {
     float blur_kern[2 * CVVDP_BHALO + 1];
     int blur_pad = 0;
     int max_smem_optin = 0;
+    int num_sms = 148;
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;
     Staging stage[2];
     float *q_dev = nullptr;       // for process_host / pool
@@ -95,7 +97,7 @@ int fail(cvvdp_b200_ctx *ctx, int code, const char *fmt, ...) {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Tiled tensor map over `planes` float4 planes of h x w pixels, viewed as fp32 [planes][h][4w].
-bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int planes, int box_px, int box_rows) {
+bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int planes, int box_px, int box_rows, int box_planes = 2) {
 #ifdef CVVDP_EMU
     m->base = (const float *)base;
     m->dim[0] = 4 * w;
@@ -106,7 +108,7 @@ bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int plane
     m->stride[2] = 4LL * w * h;
     m->box[0] = 4 * box_px;
     m->box[1] = box_rows;
-    m->box[2] = 2;
+    m->box[2] = box_planes;
     return true;
 #else
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -122,7 +124,7 @@ bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int plane
     if (4 * box_px > 256 || box_rows > 256) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)4 * w, (cuuint64_t)h, (cuuint64_t)planes};
     const cuuint64_t strides[2] = {(cuuint64_t)w * 16, (cuuint64_t)w * h * 16};  // bytes, dims 1 and 2
-    const cuuint32_t box[3] = {(cuuint32_t)(4 * box_px), (cuuint32_t)box_rows, 2};
+    const cuuint32_t box[3] = {(cuuint32_t)(4 * box_px), (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     const cuuint32_t estr[3] = {1, 1, 1};
     return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -428,10 +430,26 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ra.w = ctx->lv[i].w;
         ra.hc = ctx->lv[i + 1].h;
         ra.wc = ctx->lv[i + 1].w;
-        dim3 grid((ra.wc + CVVDP_RTX - 1) / CVVDP_RTX, (ra.hc + CVVDP_RTY - 1) / CVVDP_RTY, pairs * 2);
-        auto kfn = k_reduce;
         LaunchScope ls(ctx, st, CVVDP_K_REDUCE, i, (double)pairs * 2 * 16.0 * ((double)ra.h * ra.w + (double)ra.hc * ra.wc));
-        CVVDP_LAUNCH(kfn, grid, dim3(256), 0, st, ra);
+        static const bool no_tma_reduce = getenv("CVVDP_B200_NO_TMA") != nullptr;
+        if (ctx->lv[i].tm_ok && !no_tma_reduce) {  // persistent, TMA-staged, double-buffered
+            Reduce2Args r2;
+            r2.tm_in = ctx->lv[i].tm_reduce_in;
+            r2.out = ra.out;
+            r2.h = ra.h;
+            r2.w = ra.w;
+            r2.hc = ra.hc;
+            r2.wc = ra.wc;
+            r2.planes = pairs * 2;
+            const long long tiles = (long long)((ra.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX) * ((ra.hc + CVVDP_R2_TY - 1) / CVVDP_R2_TY) * r2.planes;
+            const int grid2 = (int)std::min<long long>(tiles, (long long)ctx->num_sms * 4);
+            auto kfn = k_reduce2;
+            CVVDP_LAUNCH(kfn, dim3(grid2), dim3(256), sizeof(Reduce2Smem), st, r2);
+        } else {
+            dim3 grid((ra.wc + CVVDP_RTX - 1) / CVVDP_RTX, (ra.hc + CVVDP_RTY - 1) / CVVDP_RTY, pairs * 2);
+            auto kfn = k_reduce;
+            CVVDP_LAUNCH(kfn, grid, dim3(256), 0, st, ra);
+        }
     }
     // ---- bands ----
     const bool is_image = job.n_frames == 1;
@@ -612,6 +630,7 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
         return fail(nullptr, CVVDP_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     }
     cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     // torchvision _get_gaussian_kernel1d(kernel_size = 4*sigma+1, sigma), cvvdp_metric.py:158
     ctx->blur_pad = (int)(params->pu_dilate * 2);
     if (ctx->blur_pad > 0) {
@@ -635,6 +654,8 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
     }
     auto kb = k_band2;
     cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
+    auto kr2 = k_reduce2;
+    cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem));
     auto kt = k_temporal;
     cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          std::min(ctx->max_smem_optin, 227 * 1024));
@@ -774,7 +795,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.hm = do_hm ? (float *)(base + off_h[i]) : nullptr;
         lv.lut = (float4 *)(base + off_l[i]);
         lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_EW, CVVDP_B2_RB) &&
-                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_CC, CVVDP_B2_CR);
+                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_CC, CVVDP_B2_CR) &&
+                   make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, CVVDP_R2_IH, 1);
         float rows[4][CVVDP_CSF_LUT_N];
         for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
         float packed[CVVDP_CSF_LUT_N][4];

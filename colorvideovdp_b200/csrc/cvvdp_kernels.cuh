@@ -405,18 +405,22 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_stg(const T
 #pragma unroll
     for (int i = 0; i < RP; ++i) r0[i] = r1[i] = r2[i] = 0.f;
 
-    // issue the copies of iteration `it` (frame t = f0-(FL-1)+it, padded before frame 0) into stage slot it % DEPTH
-    auto issue = [&](int it) {
-        if (it < NI && lane < npieces) {
-            const int t = a.f0 - (FL - 1) + it;
-            const int slot = frame_slot(cv, temporal_source_frame(a, t));
-            cp_async16(wst + (it & (CVVDP_TSTG_DEPTH - 1)) * (3 * 32 * 4) + pdst, psrc + (long long)slot * fstride);
+    // issue the copies of the next iteration (frame t = f0-(FL-1)+pf_it, padded before frame 0) into stage
+    // slot pf_it % DEPTH; from frame f0 on the clip slot advances incrementally (no modulo per frame)
+    int pf_it = 0, pf_slot = frame_slot(cv, a.f0);
+    const int slots = cv.ring > 0 ? cv.ring : 0x7fffffff;
+    auto issue = [&]() {
+        if (pf_it < NI && lane < npieces) {
+            const int slot = pf_it < FL - 1 ? frame_slot(cv, temporal_source_frame(a, a.f0 - (FL - 1) + pf_it)) : pf_slot;
+            cp_async16(wst + (pf_it & (CVVDP_TSTG_DEPTH - 1)) * (3 * 32 * 4) + pdst, psrc + (long long)slot * fstride);
         }
+        if (pf_it >= FL - 1) pf_slot = pf_slot + 1 == slots ? 0 : pf_slot + 1;
+        ++pf_it;
         cp_async_commit();
     };
     // wait for iteration `it`, read this lane's raw values
     auto fetch = [&](int it, unsigned bits[3]) {
-        issue(it + CVVDP_TSTG_DEPTH - 1);
+        issue();
         cp_async_wait_n<CVVDP_TSTG_DEPTH - 1>();
         __syncwarp();
         const unsigned char *q = wst + (it & (CVVDP_TSTG_DEPTH - 1)) * (3 * 32 * 4);
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_stg(const T
         __syncwarp();  // every lane has read the slot before it is refilled
     };
 #pragma unroll
-    for (int i = 0; i < CVVDP_TSTG_DEPTH - 1; ++i) issue(i);
+    for (int i = 0; i < CVVDP_TSTG_DEPTH - 1; ++i) issue();
     unsigned bits[3];
     int it = 0;
     // ---- warm-up: slots 0..FL-2 ----
@@ -547,6 +551,113 @@ __global__ void __launch_bounds__(256) k_reduce(const ReduceArgs a) {
             }
         }
         a.out[(long long)plane * a.hc * a.wc + (long long)goy * a.wc + gox] = acc;
+    }
+}
+
+// Persistent TMA version of the reduce: each CTA loops over output tiles of 30x8 pixels; the 63x19
+// input box of the NEXT tile is fetched by one cp.async.bulk.tensor while the current one is filtered
+// (two shared-memory buffers, one mbarrier each).  TMA's zero fill outside the image is exactly the
+// zero padding of the reference's strided conv2d; the edge fix-ups are the same as in k_reduce.
+#define CVVDP_R2_TX 30
+#define CVVDP_R2_TY 8
+#define CVVDP_R2_IW (2 * CVVDP_R2_TX + 3)  // 63 pixels = 252 floats (TMA box limit 256)
+#define CVVDP_R2_IH (2 * CVVDP_R2_TY + 3)  // 19
+#define CVVDP_R2_BUF 1200                  // float4 per buffer: 19*63 = 1197 rounded to a 128-byte multiple
+struct Reduce2Args {
+    TensorMap3D tm_in;  // fp32 view [planes][h][4w], box {252, 19, 1}
+    float4 *out;
+    int h, w, hc, wc, planes;
+};
+struct Reduce2Smem {
+    float4 in[2][CVVDP_R2_BUF];
+    float4 ya[CVVDP_R2_TY][CVVDP_R2_IW + 1];
+    unsigned long long bar[2];
+};
+__global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2Args a) {
+    CVVDP_DYN_SMEM(smem_raw);
+    Reduce2Smem &sm = *reinterpret_cast<Reduce2Smem *>(smem_raw);
+    const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f;
+    const int tid = threadIdx.x;
+    const int ntx = (a.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX, nty = (a.hc + CVVDP_R2_TY - 1) / CVVDP_R2_TY;
+    const long long total = (long long)ntx * nty * a.planes;
+    const bool rows_odd = (a.h & 1) != 0;
+    if (tid == 0) {
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
+    }
+    __syncthreads();
+    auto issue = [&](long long t, int buf) {
+        const int plane = (int)(t / (ntx * nty)), rem = (int)(t - (long long)plane * (ntx * nty));
+        const int ty = rem / ntx, tx = rem - ty * ntx;
+        fence_proxy_async();
+        mbar_expect_tx(&sm.bar[buf], CVVDP_R2_IH * CVVDP_R2_IW * 16);
+        tma_load_3d(&sm.in[buf][0], &a.tm_in, 4 * (2 * tx * CVVDP_R2_TX - 2), 2 * ty * CVVDP_R2_TY - 2, plane, &sm.bar[buf]);
+        mbar_emu_complete(&sm.bar[buf]);
+    };
+    if (tid == 0 && (long long)blockIdx.x < total) issue(blockIdx.x, 0);
+    int k = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++k) {
+        const int buf = k & 1;
+        if (tid == 0 && t + gridDim.x < total) issue(t + gridDim.x, buf ^ 1);
+        mbar_wait(&sm.bar[buf], (unsigned)((k >> 1) & 1));
+        const float4 *in = sm.in[buf];
+        const int plane = (int)(t / (ntx * nty)), rem = (int)(t - (long long)plane * (ntx * nty));
+        const int ty = rem / ntx, tx = rem - ty * ntx;
+        const int ox0 = tx * CVVDP_R2_TX, oy0 = ty * CVVDP_R2_TY;
+        const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
+        for (int i = tid; i < CVVDP_R2_TY * CVVDP_R2_IW; i += 256) {
+            const int oy = i / CVVDP_R2_IW, c = i - oy * CVVDP_R2_IW;
+            const int goy = oy0 + oy;
+            float4 acc = f4(0.f);
+            if (goy < a.hc) {
+                const float4 *col = in + (2 * oy) * CVVDP_R2_IW + c;
+                acc = K0 * col[0];
+                acc = fma4(K1, col[CVVDP_R2_IW], acc);
+                acc = fma4(K2, col[2 * CVVDP_R2_IW], acc);
+                acc = fma4(K1, col[3 * CVVDP_R2_IW], acc);
+                acc = fma4(K0, col[4 * CVVDP_R2_IW], acc);
+                if (goy == 0) {  // lpyr_dec.py:195
+                    acc = fma4(K1, in[(0 - iy0) * CVVDP_R2_IW + c], acc);
+                    acc = fma4(K0, in[(min(1, a.h - 1) - iy0) * CVVDP_R2_IW + c], acc);
+                }
+                if (goy == a.hc - 1) {  // lpyr_dec.py:196-199
+                    if (rows_odd) {
+                        acc = fma4(K1, in[(a.h - 1 - iy0) * CVVDP_R2_IW + c], acc);
+                        acc = fma4(K0, in[(max(a.h - 2, 0) - iy0) * CVVDP_R2_IW + c], acc);
+                    } else {
+                        acc = fma4(K0, in[(a.h - 1 - iy0) * CVVDP_R2_IW + c], acc);
+                    }
+                }
+            }
+            sm.ya[oy][c] = acc;
+        }
+        __syncthreads();
+        if (tid < CVVDP_R2_TX * CVVDP_R2_TY) {
+            const int ox = tid % CVVDP_R2_TX, oy = tid / CVVDP_R2_TX;
+            const int gox = ox0 + ox, goy = oy0 + oy;
+            if (gox < a.wc && goy < a.hc) {
+                const int c = 2 * ox;
+                float4 acc = K0 * sm.ya[oy][c];
+                acc = fma4(K1, sm.ya[oy][c + 1], acc);
+                acc = fma4(K2, sm.ya[oy][c + 2], acc);
+                acc = fma4(K1, sm.ya[oy][c + 3], acc);
+                acc = fma4(K0, sm.ya[oy][c + 4], acc);
+                if (gox == 0) {  // lpyr_dec.py:205
+                    acc = fma4(K1, sm.ya[oy][0 - ix0], acc);
+                    acc = fma4(K0, sm.ya[oy][min(1, a.w - 1) - ix0], acc);
+                }
+                if (gox == a.wc - 1) {  // lpyr_dec.py:206-209: the parity of the ROW count chooses the rule
+                    if (rows_odd) {
+                        acc = fma4(K1, sm.ya[oy][a.w - 1 - ix0], acc);
+                        acc = fma4(K0, sm.ya[oy][max(a.w - 2, 0) - ix0], acc);
+                    } else {
+                        acc = fma4(K0, sm.ya[oy][a.w - 1 - ix0], acc);
+                    }
+                }
+                a.out[(long long)plane * a.hc * a.wc + (long long)goy * a.wc + gox] = acc;
+            }
+        }
+        __syncthreads();  // ya and in[buf] are free again
     }
 }
 
