@@ -299,7 +299,7 @@ def main():
         q_bytes = n * info.n_channels * F * info.n_bands * 4
         e2e = {"value": round(pix_per_step / 1e6 / (ms_e2e / 1e3), 2), "unit": "Mpix/s",
                "ms_per_step": round(ms_e2e, 3),
-               "h2d_bytes_per_step": int(2 * tst_h.numel() * tst_h.element_size() * n / n),
+               "h2d_bytes_per_step": int(n * (tst_h.numel() * tst_h.element_size() + ref_h.numel() * ref_h.element_size())),
                "d2h_bytes_per_step": int(q_bytes + 4 * n)}
         del tst_h, ref_h
 

@@ -166,19 +166,22 @@ class vvdp_display_photo_eotf(vvdp_display_photometry):
         return d
 
     def _frontend_ctx(self, device):
-        from .cvvdp_metric import _default_native_inputs  # lazy: avoids an import cycle
-        key = (device.index if device.index is not None else torch.cuda.current_device())
-        if self._ctx is None or self._ctx[0] != key:
-            params, lut = _default_native_inputs()
-            self._ctx = (key, N.Context(params, lut, key))
+        from . import cvvdp_metric as cm  # lazy: avoids an import cycle
+        mock = cm._mock_library  # tests only (mock device)
+        key = 0 if mock is not None else (device.index if device.index is not None else torch.cuda.current_device())
+        if self._ctx is None or self._ctx[0] != (key, mock):
+            params, lut = cm._default_native_inputs()
+            self._ctx = ((key, mock), N.Context(params, lut, key, library=mock))
         return self._ctx[1]
 
     def _run_frontend(self, V, colorspace_id, passthrough=False):
-        if not torch.cuda.is_available():
+        from . import cvvdp_metric as cm
+        mock = cm._mock_library is not None
+        if not mock and not torch.cuda.is_available():
             raise RuntimeError("colorvideovdp_b200 needs a CUDA device (no CPU fallback)")
         if V.dim() != 5:
             raise RuntimeError("expected a [B,C,1,H,W] frame")
-        if not V.is_cuda:
+        if not mock and not V.is_cuda:
             V = V.to("cuda")
         if V.dtype != torch.float32:
             V = V.to(torch.float32)
@@ -192,7 +195,7 @@ class vvdp_display_photo_eotf(vvdp_display_photometry):
         clip.frame0, clip.n_frames = 0, F
         flags = torch.zeros(3, dtype=torch.int32, device=V.device)
         out = torch.empty((B, Cc, F, H, W), dtype=torch.float32, device=V.device)
-        stream = torch.cuda.current_stream(V.device).cuda_stream
+        stream = None if mock else torch.cuda.current_stream(V.device).cuda_stream
         for f in range(F):
             dst = out[:, :, f]
             if not dst.is_contiguous():  # F > 1 only

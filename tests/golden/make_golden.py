@@ -121,6 +121,10 @@ def main():
     save("img_u8_64x96_4k_hmraw", t, r, "BCFHW", 0, "standard_4k", heatmap="raw")
     t, r = synth.make_pair_u8(20, 8, 48, 64)
     save("vid_u8_8x48x64_fhd_24_hmraw", t, r, "BCFHW", 24, "standard_fhd", heatmap="raw")
+    # 7b. coloured heat maps of an image (one block in the reference => partition independent)
+    t, r = synth.make_pair_u8(22, 1, 48, 72)
+    save("img_u8_48x72_4k_hmthr", t, r, "BCFHW", 0, "standard_4k", heatmap="threshold")
+    save("img_u8_48x72_4k_hmsupra", t, r, "BCFHW", 0, "standard_4k", heatmap="supra-threshold")
     # 8. HLG + gamma EOTF coverage (fp32 video, 25 fps -> fl=9)
     t, r = synth.make_pair_u8(21, 3, 36, 52)
     tf, rf = (t.astype(np.float32) / 255), (r.astype(np.float32) / 255)

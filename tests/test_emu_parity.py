@@ -27,6 +27,10 @@ def test_golden_cases_on_mock_device(name, mock_device):
         hm = stats["heatmap"]
         assert hm.dtype == torch.float16 and tuple(hm.shape) == z["heatmap"].shape
         assert np.max(np.abs(hm.float().numpy() - z["heatmap"].astype(np.float32))) <= gu.HEATMAP_ATOL
+    elif meta["heatmap"] in ("threshold", "supra-threshold"):  # colour LUT x tone-mapped context image
+        hm = stats["heatmap"]
+        assert hm.dtype == torch.float16 and tuple(hm.shape) == z["heatmap"].shape
+        assert np.max(np.abs(hm.float().numpy() - z["heatmap"].astype(np.float32))) <= gu.COLOR_HEATMAP_ATOL
 
 
 def test_identical_pair_is_exactly_10(mock_device):

@@ -36,6 +36,10 @@ def test_golden_fixtures(name, resident):
         hm = stats["heatmap"]
         assert hm.dtype == torch.float16 and hm.device.type == "cpu"
         assert np.max(np.abs(hm.float().numpy() - z["heatmap"].astype(np.float32))) <= gu.HEATMAP_ATOL
+    elif meta["heatmap"] in ("threshold", "supra-threshold"):
+        hm = stats["heatmap"]
+        assert tuple(hm.shape) == z["heatmap"].shape
+        assert np.max(np.abs(hm.float().numpy() - z["heatmap"].astype(np.float32))) <= gu.COLOR_HEATMAP_ATOL
     assert m._ctx.launch_count() > 0
 
 
@@ -160,3 +164,21 @@ def test_plugin_source_and_pooling_entry():
     assert abs(float(jod_p) - float(jod)) <= 1e-4
     P = O.Params()
     assert abs(float(m.do_pooling_and_jods(fast["Q_per_ch"])) - float(O.do_pooling_and_jods(fast["Q_per_ch"], P))) < 2e-5
+
+
+def test_config4_hdr_pq_4k_heatmap_one_frame():
+    """BASELINE config 4 shape: 3840x2160 HDR (PQ) at 60 fps on standard_hdr_pq with the raw heat map.
+    The oracle checks Q_per_ch and the heat map of one late frame (17 frames of history)."""
+    tst, ref = synth.make_pair_pq_u16(46, 18, 2160, 3840)
+    m = cv.cvvdp(display_name="standard_hdr_pq", heatmap="raw", device=DEV)
+    vs = cv.video_source_array(_t(tst), _t(ref), 60, display_photometry=m.display_photometry)
+    Q, hm = m.compute_q_per_ch(vs, (17, 18))
+    _, so = O.predict(tst, ref, "BCFHW", 60, "standard_hdr_pq", heatmap="raw", frame_range=(17, 18))
+    gu.assert_q_close(Q.cpu().numpy()[:, :, 17:18], so["Q_per_ch"][:, :, 17:18], "4k hdr frame 17")
+    err = np.abs(hm[0, 0, 17].float().cpu().numpy() - so["heatmap"][0, 0, 17].astype(np.float32))
+    assert err.max() <= gu.HEATMAP_ATOL
+    # whole 18-frame clip through the public API, host-resident input, heat map returned on the CPU in fp16
+    jod, stats = m.predict(tst, ref, frames_per_second=60)
+    assert stats["heatmap"].shape == (1, 1, 18, 2160, 3840) and stats["heatmap"].dtype == torch.float16
+    assert np.array_equal(stats["Q_per_ch"][:, :, 17], Q.cpu().numpy()[:, :, 17])
+    assert 0.0 < float(jod) < 10.0
