@@ -285,7 +285,18 @@ def main():
 
     # ---- end-to-end arm: pinned host clips through the public tensor API ----
     e2e = None
-    if not args.no_e2e:
+    do_e2e = not args.no_e2e
+    if do_e2e:  # never pin more than half of the host's available memory (all ranks together)
+        need = world * 2 * tst.numel() * tst.element_size()
+        try:
+            avail = int([l for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0].split()[1]) * 1024
+        except Exception:
+            avail = 1 << 62
+        flag = torch.tensor([1 if need < 0.5 * avail else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        do_e2e = bool(flag.item())
+    if do_e2e:
         tst_h = torch.empty(tst.shape, dtype=tst.dtype, pin_memory=True).copy_(tst)
         ref_h = torch.empty(ref.shape, dtype=ref.dtype, pin_memory=True).copy_(ref)
 

@@ -41,10 +41,15 @@ class Display(C.Structure):
                 ("rgb2xyz", C.c_float * 9), ("ppd", C.c_float)]
 
 
+class Yuv(C.Structure):
+    _fields_ = [("chroma", C.c_int32), ("bit_depth", C.c_int32), ("coef", C.c_float * 4)]
+
+
 class Job(C.Structure):
     _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("n_frames", C.c_int32),
                 ("fps", C.c_float), ("in_channels", C.c_int32), ("dtype", C.c_int32), ("padding", C.c_int32),
-                ("heatmap", C.c_int32), ("max_block_frames", C.c_int32), ("workspace_limit_bytes", C.c_int64)]
+                ("heatmap", C.c_int32), ("max_block_frames", C.c_int32), ("workspace_limit_bytes", C.c_int64),
+                ("yuv", Yuv)]
 
 
 class PlanInfo(C.Structure):
@@ -75,6 +80,8 @@ SYMBOLS = {
                                          C.c_void_p]),
     "cvvdp_b200_frontend": (C.c_int, [C.c_void_p, C.POINTER(Clip), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cvvdp_b200_frontend_yuv": (C.c_int, [C.c_void_p, C.POINTER(Clip), C.POINTER(Yuv), C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_launch_count": (C.c_int64, [C.c_void_p]),
     "cvvdp_b200_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "cvvdp_b200_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
@@ -87,7 +94,7 @@ class KernelStat(C.Structure):
     _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("launches", C.c_int32), ("total_ms", C.c_float),
                 ("algo_bytes", C.c_double)]
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NativeError(RuntimeError):
@@ -172,6 +179,10 @@ class Context:
     def frontend(self, src: Clip, B, cin, H, W, dtype, frame, colorspace, dst_ptr, flags_ptr, stream):
         self._check(self._lib.cvvdp_b200_frontend(self._h, C.byref(src), B, cin, H, W, dtype, frame, colorspace,
                                                   dst_ptr, flags_ptr, stream), "frontend")
+
+    def frontend_yuv(self, src: Clip, yuv: Yuv, B, H, W, dtype, frame, colorspace, dst_ptr, stream):
+        self._check(self._lib.cvvdp_b200_frontend_yuv(self._h, C.byref(src), C.byref(yuv), B, H, W, dtype, frame,
+                                                      colorspace, dst_ptr, stream), "frontend_yuv")
 
     def launch_count(self):
         return int(self._lib.cvvdp_b200_launch_count(self._h))

@@ -279,6 +279,30 @@ void to_display_dev(const cvvdp_b200_display &d, DisplayDev *o, int colorspace =
         }
 }
 
+// video_source_yuv.py:196-207: limited-range weights/offsets for luma and chroma
+void fill_yuv(const cvvdp_b200_yuv &y, int W, int H, YuvDev *o) {
+    memset(o, 0, sizeof(*o));
+    o->chroma = y.chroma;
+    if (y.chroma == 0) return;
+    o->W = W;
+    o->H = H;
+    const double sc = pow(2.0, (double)(y.bit_depth - 8));
+    o->yw = (float)(1.0 / (sc * 219.0));
+    o->yo = (float)(16.0 / 219.0);
+    o->cw = (float)(1.0 / (sc * 224.0));
+    o->co = (float)(128.0 / 224.0);
+    o->m_rv = y.coef[0];
+    o->m_gu = y.coef[1];
+    o->m_gv = y.coef[2];
+    o->m_bu = y.coef[3];
+}
+
+// elements of one planar YUV frame
+long long yuv_frame_elems(const cvvdp_b200_yuv &y, int W, int H) {
+    const long long ypix = (long long)W * H;
+    return y.chroma == 444 ? 3 * ypix : (y.chroma == 422 ? 2 * ypix : ypix * 3 / 2);
+}
+
 size_t dtype_size(int dtype) {
     switch (dtype) {
         case CVVDP_DTYPE_U8: return 1;
@@ -376,10 +400,12 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         const double bytes = (double)npix * B * 2 * ((double)(whi - wlo) * job.in_channels * dtype_size(job.dtype) + 16.0 * n);
         LaunchScope ls(ctx, st, CVVDP_K_TEMPORAL, 0, bytes);
         const int e = ctx->disp.eotf;
-        const bool use_lut = job.dtype == CVVDP_DTYPE_U8 &&
+        const bool is_yuv = job.yuv.chroma != 0;
+        fill_yuv(job.yuv, job.width, job.height, &ta.yuv);
+        const bool use_lut = !is_yuv && job.dtype == CVVDP_DTYPE_U8 &&
                              (e == CVVDP_EOTF_SRGB || e == CVVDP_EOTF_PQ || e == CVVDP_EOTF_LINEAR || e == CVVDP_EOTF_GAMMA);
         // staged (cp.async) variant: dense, 16-byte aligned planes and whole warps
-        bool staged = npix % 32 == 0 && job.in_channels <= 3;
+        bool staged = !is_yuv && npix % 32 == 0 && job.in_channels <= 3;
         static const bool no_stage = getenv("CVVDP_B200_NO_TSTAGE") != nullptr;
         if (no_stage) staged = false;
         for (int v = 0; v < 2 && staged; ++v) {
@@ -706,6 +732,17 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         return fail(ctx, CVVDP_ERR_INVALID, "Heatmaps not supported when batches are used");  // cvvdp_metric.py:311-312
     if (ctx->disp.eotf == CVVDP_EOTF_HLG && job->in_channels != 3)
         return fail(ctx, CVVDP_ERR_UNSUPPORTED, "HLG needs three colour channels");
+    if (job->yuv.chroma != 0) {
+        const cvvdp_b200_yuv &yv = job->yuv;
+        if (yv.chroma != 420 && yv.chroma != 422 && yv.chroma != 444)
+            return fail(ctx, CVVDP_ERR_UNSUPPORTED, "Unsupported chroma subsampling %d", yv.chroma);
+        if (job->in_channels != 3 || job->batch != 1) return fail(ctx, CVVDP_ERR_INVALID, "YUV input: three channels, batch of one");
+        if (yv.bit_depth < 8 || yv.bit_depth > 16 || (yv.bit_depth == 8) != (job->dtype == CVVDP_DTYPE_U8) ||
+            (yv.bit_depth > 8 && job->dtype != CVVDP_DTYPE_U16))
+            return fail(ctx, CVVDP_ERR_INVALID, "YUV input: dtype U8 for 8 bits, U16 for 9..16 bits");
+        if ((yv.chroma != 444 && (job->width & 1)) || (yv.chroma == 420 && (job->height & 1)))
+            return fail(ctx, CVVDP_ERR_INVALID, "subsampled chroma needs even luma dimensions");
+    }
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     CU_CHECK(ctx, cudaDeviceSynchronize());
     free_plan(ctx);
@@ -888,6 +925,13 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
     const long long ext_t[5] = {test->stride[0] ? job.batch : 1, job.in_channels, 0, job.height, job.width};
     const long long ext_r[5] = {ref->stride[0] ? job.batch : 1, job.in_channels, 0, job.height, job.width};
     HostLayout hl[2] = {analyse_layout(test, ext_t), analyse_layout(ref, ext_r)};
+    if (job.yuv.chroma != 0) {  // planar YUV: a frame is one dense run of stride[2] elements, batch of one
+        for (int v = 0; v < 2; ++v) {
+            hl[v] = HostLayout();
+            for (int d = 0; d < 5; ++d) hl[v].extent[d] = 1;
+            hl[v].ok = (v == 0 ? test : ref)->stride[2] >= yuv_frame_elems(job.yuv, job.width, job.height);
+        }
+    }
     if (!hl[0].ok || !hl[1].ok)
         return fail(ctx, CVVDP_ERR_UNSUPPORTED,
                     "host clips must store each frame densely (dims with a stride below the frame stride must tile it)");
@@ -1106,6 +1150,42 @@ int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int bat
     auto kfn = k_frontend;
     {
         LaunchScope ls(ctx, (cudaStream_t)stream, CVVDP_K_FRONTEND, 0, (double)npix * batch * in_channels * (dtype_size(dtype) + 4.0));
+        CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), batch), dim3(256), 0, (cudaStream_t)stream, fa);
+    }
+    CU_CHECK(ctx, cudaGetLastError());
+    return CVVDP_OK;
+}
+
+int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, const cvvdp_b200_yuv *yuv, int batch, int height,
+                            int width, int dtype, int frame, int colorspace, float *dst_dev, void *stream) {
+    if (!ctx || !src || !src->data || !dst_dev || !yuv) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    if (!ctx->have_display) return fail(ctx, CVVDP_ERR_STATE, "set_display must be called first");
+    if (yuv->chroma != 420 && yuv->chroma != 422 && yuv->chroma != 444)
+        return fail(ctx, CVVDP_ERR_UNSUPPORTED, "Unsupported chroma subsampling %d", yuv->chroma);
+    if (dtype != CVVDP_DTYPE_U8 && dtype != CVVDP_DTYPE_U16) return fail(ctx, CVVDP_ERR_INVALID, "YUV input: dtype U8 or U16");
+    if ((yuv->chroma != 444 && (width & 1)) || (yuv->chroma == 420 && (height & 1)))
+        return fail(ctx, CVVDP_ERR_INVALID, "subsampled chroma needs even luma dimensions");
+    if (frame < src->frame0 || frame >= src->frame0 + src->n_frames) return fail(ctx, CVVDP_ERR_INVALID, "frame %d outside the view", frame);
+    if (colorspace < CVVDP_CS_DKLD65 || colorspace > CVVDP_CS_LMS2006) return fail(ctx, CVVDP_ERR_INVALID, "unknown colour space id %d", colorspace);
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrontendArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.clip = to_view(src);
+    to_display_dev(ctx->disp, &fa.dd, colorspace);
+    fill_yuv(*yuv, width, height, &fa.yuv);
+    fa.dtype = dtype;
+    fa.cin = 3;
+    fa.B = batch;
+    fa.H = height;
+    fa.W = width;
+    fa.frame = frame - src->frame0;
+    fa.dst = dst_dev;
+    fa.flags = nullptr;
+    const long long npix = (long long)height * width;
+    auto kfn = k_frontend;
+    {
+        LaunchScope ls(ctx, (cudaStream_t)stream, CVVDP_K_FRONTEND, 0,
+                       (double)batch * (yuv_frame_elems(*yuv, width, height) * dtype_size(dtype) + 12.0 * npix));
         CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), batch), dim3(256), 0, (cudaStream_t)stream, fa);
     }
     CU_CHECK(ctx, cudaGetLastError());

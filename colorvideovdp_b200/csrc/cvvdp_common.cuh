@@ -193,6 +193,29 @@ __device__ __forceinline__ void mbar_emu_complete(unsigned long long *) {}
 // FMUL2, PTX fma.rn.f32x2): same IEEE results per lane, half the issue slots -- these kernels are
 // bound by instruction issue, not by the FP32 lanes.
 __device__ __forceinline__ float4 f4(float v) { return make_float4(v, v, v, v); }
+// packed pairs (one FFMA2 / FMUL2 / FADD2 each on sm_100)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__) && !defined(CVVDP_NO_F32X2)
+    return __ffma2_rn(a, b, c);
+#else
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && !defined(CVVDP_NO_F32X2)
+    return __fmul2_rn(a, b);
+#else
+    return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && !defined(CVVDP_NO_F32X2)
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
 #if defined(__CUDA_ARCH__) && !defined(CVVDP_NO_F32X2)
 __device__ __forceinline__ float4 operator+(float4 a, float4 b) {
     const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
@@ -232,6 +255,13 @@ struct ClipView {
     int ring;  // > 0: frames live in a ring of that many slots (frame f at slot f % ring); 0: linear view
 };
 __device__ __forceinline__ int frame_slot(const ClipView &cv, int f) { return cv.ring > 0 ? f % cv.ring : f - cv.frame0; }
+
+struct YuvDev {   // planar YUV description (see cvvdp_b200_yuv); chroma == 0: not YUV
+    int chroma;
+    int W, H;
+    float yw, yo, cw, co;          // limited-range unpack: Y' = clip(yw*Y - yo, 0, 1), C' = clip(cw*C - co, -.5, .5)
+    float m_rv, m_gu, m_gv, m_bu;  // YCbCr -> RGB
+};
 
 struct DisplayDev {
     int eotf;

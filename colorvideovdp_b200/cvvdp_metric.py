@@ -193,7 +193,7 @@ class cvvdp(vq_metric):
         return self.predict_video_source(test_vs)
 
     # ------------------------------------------------------------------------------------------
-    def _plan(self, B, H, W, F, fps, cin, dtype_id, photo):
+    def _plan(self, B, H, W, F, fps, cin, dtype_id, photo, yuv=None):
         """(Re)build the native plan when the job or the display changed.  photo=None: frames already
         are DKLd65 (plugin sources), the front end passes them through."""
         if self.temp_padding not in ("replicate", "symmetric"):
@@ -204,13 +204,16 @@ class cvvdp(vq_metric):
         else:
             disp = photo.native_display(self.pix_per_deg)
         hm = N.HEATMAP_RAW if self.do_heatmap else N.HEATMAP_NONE
-        key = (B, H, W, F, float(fps), cin, dtype_id, self.temp_padding, hm, bytes(disp), self.gpu_mem)
+        key = (B, H, W, F, float(fps), cin, dtype_id, self.temp_padding, hm, bytes(disp), self.gpu_mem,
+               bytes(yuv) if yuv is not None else None)
         if key != self._plan_key:
             self._ctx.set_display(disp)
             job = N.Job(batch=B, height=H, width=W, n_frames=F, fps=float(fps), in_channels=cin, dtype=dtype_id,
                         padding=N.PAD_REPLICATE if self.temp_padding == "replicate" else N.PAD_SYMMETRIC,
                         heatmap=hm, max_block_frames=0,
                         workspace_limit_bytes=int(self.gpu_mem * 1e9) if self.gpu_mem else 0)
+            if yuv is not None:
+                job.yuv = yuv
             self._info = self._ctx.plan(job)
             self._plan_key = key
         return self._info
@@ -249,7 +252,39 @@ class cvvdp(vq_metric):
         fast = type(vid_source) is video_source_array and type(vid_source.dm_photometry) is vvdp_display_photo_eotf
         if fast:
             return self._run_arrays(vid_source, B, H, W, F, fps, f0, f1)
+        from .video_source_yuv import video_source_yuv_file
+        if type(vid_source) is video_source_yuv_file and type(vid_source.dm_photometry) is vvdp_display_photo_eotf:
+            tr, rr = vid_source.test_vidr, vid_source.reference_vidr
+            same = all(getattr(tr, k) == getattr(rr, k) for k in ("width", "height", "chroma_ss", "bit_depth", "color_space"))
+            if same and F <= min(tr.frames, rr.frames) - vid_source.offset:
+                return self._run_yuv(vid_source, H, W, F, fps, f0, f1)
         return self._run_plugin(vid_source, B, H, W, F, fps, f0, f1)
+
+    def _run_yuv(self, vs, H, W, F, fps, f0, f1):
+        """Raw planar YUV files: the memory-mapped frames go straight into the fused temporal kernel, which
+        unpacks, upsamples the chroma and applies the YCbCr matrix on the fly (video_source_yuv.py:146-233)."""
+        tr, rr = vs.test_vidr, vs.reference_vidr
+        info = self._plan(1, H, W, F, fps, 3, tr.native_dtype(), vs.dm_photometry, tr.native_yuv())
+        fl = info.filter_len
+        wlo, whi = self._needed_frames(f0, f1, fl, F)
+        tt = tr.frames_tensor(vs.offset + wlo, whi - wlo)
+        rt = rr.frames_tensor(vs.offset + wlo, whi - wlo)
+        if self.device.type == "cuda":
+            tt, rt = tt.pin_memory(), rt.pin_memory()
+
+        def clip_of(t, reader):
+            c = N.Clip()
+            c.data = t.data_ptr()
+            c.stride[0], c.stride[2] = 0, reader.frame_pixels
+            c.frame0, c.n_frames = wlo, whi - wlo
+            return c
+
+        pin = self.device.type == "cuda"
+        Qh = torch.zeros((1, info.n_channels, F, info.n_bands), dtype=torch.float32, pin_memory=pin)
+        hmh = torch.zeros((1, 1, F, H, W), dtype=torch.float16, pin_memory=pin) if self.do_heatmap else None
+        self._ctx.process_host(clip_of(tt, tr), clip_of(rt, rr), f0, f1, Qh.data_ptr(),
+                               hmh.data_ptr() if hmh is not None else None)
+        return Qh, hmh
 
     def _alloc_outputs(self, B, C, F, L, H, W):
         Q = torch.zeros((B, C, F, L), dtype=torch.float32, device=self.device)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CVVDP_B200_ABI_VERSION 1
+#define CVVDP_B200_ABI_VERSION 2
 #define CVVDP_MAX_BANDS 16
 #define CVVDP_MAX_FILTER_LEN 129
 #define CVVDP_CSF_LUT_N 32
@@ -80,6 +80,19 @@ typedef struct {
     float ppd;               /* pixels per visual degree */
 } cvvdp_b200_display;
 
+/* Planar YUV input (raw .yuv frames / ffmpeg rawvideo), replaces YUVReader._fixed2float_upscale +
+ * get_frame_rgb_tensor (video_source_yuv.py:153-233) and video_reader_yuv_pytorch.unpack
+ * (video_source_file.py:261-324): limited-range unpack, bilinear chroma upsampling
+ * (F.interpolate(scale_factor=2, mode='bilinear')), YCbCr->RGB matrix, clip to 0..1 -- fused into the
+ * front end.  A frame is Y[h*w] U[ch*cw] V[ch*cw] (8-bit, or 16-bit little endian for bit_depth > 8);
+ * the clip view's frame stride (stride[2], in elements) is the frame size, stride[0] the batch stride,
+ * the other strides are ignored.  chroma == 0 means "not YUV" (RGB / grey planes as described by the clip). */
+typedef struct {
+    int32_t chroma;          /* 0, 420, 422 or 444 */
+    int32_t bit_depth;       /* 8..16 */
+    float coef[4];           /* R = Y + coef[0] Cr; G = Y + coef[1] Cb + coef[2] Cr; B = Y + coef[3] Cb */
+} cvvdp_b200_yuv;
+
 /* One prediction job (what cvvdp.predict_video_source derives from the video source, cvvdp_metric.py:304-355). */
 typedef struct {
     int32_t batch;           /* B */
@@ -92,6 +105,7 @@ typedef struct {
     int32_t heatmap;         /* CVVDP_HEATMAP_* */
     int32_t max_block_frames;/* frames per pass (0 = choose from the workspace budget) */
     int64_t workspace_limit_bytes; /* 0 = default */
+    cvvdp_b200_yuv yuv;      /* yuv.chroma != 0: the clips hold planar YUV frames (dtype U8 or U16, in_channels 3) */
 } cvvdp_b200_job;
 
 typedef struct {
@@ -163,6 +177,10 @@ int cvvdp_b200_pool_device(cvvdp_b200_ctx *ctx, const float *q_per_ch_dev, int B
 int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int batch, int in_channels, int height,
                         int width, int dtype, int frame, int colorspace, float *dst_dev, int32_t *flags_dev,
                         void *stream);
+/* Same for a planar YUV frame; with the context's display set to CVVDP_EOTF_NONE and colorspace
+ * CVVDP_CS_RGB_LINEAR the result is the display-encoded RGB of YUVReader.get_frame_rgb_tensor. */
+int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, const cvvdp_b200_yuv *yuv, int batch,
+                            int height, int width, int dtype, int frame, int colorspace, float *dst_dev, void *stream);
 
 /* Per-kernel timing for bench.py's roofline: when enabled, every launch is bracketed by CUDA events on
  * its stream.  profile_read synchronises the device, aggregates by (kind, pyramid level) and resets.

@@ -177,3 +177,42 @@ def test_host_streaming_chunks_match_resident_path(mock_device):
     _, s1 = m.predict(fchw_t, fchw_r, dim_order="FCHW", frames_per_second=30)
     _, s2 = m.predict(tst, ref, frames_per_second=30)
     assert np.array_equal(s1["Q_per_ch"], s2["Q_per_ch"])
+
+
+@pytest.mark.parametrize("name", gu.yuv_case_names())
+def test_yuv_files_on_mock_device(name, tmp_path, mock_device):
+    """video_source_yuv_file: fused YUV front end (fast path), the single-frame plugin surface and the
+    generic plugin path must all match the reference-generated fixture."""
+    tf, rf, z, meta = gu.write_yuv_case(name, str(tmp_path))
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"])
+    vs = cv.video_source_yuv_file(tf, rf, display_photometry=meta["display"])
+    jod, stats = m.predict_video_source(vs)
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+    F = z["Q_per_ch"].shape[2]
+    rgb = vs.test_vidr.get_frame_rgb_tensor(F - 1, torch.device("cpu"))
+    assert tuple(rgb.shape) == z["rgb_last_test_frame"].shape
+    assert np.max(np.abs(rgb.numpy() - z["rgb_last_test_frame"])) <= 2e-6
+
+    class Wrapped(cv.video_source):  # forces the generic plugin path (frames pulled one by one in DKLd65)
+        def get_video_size(self):
+            return vs.get_video_size()
+
+        def get_frames_per_second(self):
+            return vs.get_frames_per_second()
+
+        def get_test_frame(self, f, device, colorspace):
+            return vs.get_test_frame(f, device, colorspace)
+
+        def get_reference_frame(self, f, device, colorspace):
+            return vs.get_reference_frame(f, device, colorspace)
+
+    _, plug = m.predict_video_source(Wrapped())
+    gu.assert_q_close(plug["Q_per_ch"], z["Q_per_ch"], name + " (plugin path)")
+
+
+def test_yuv_filename_metadata():
+    p = cv.decode_video_props("/x/clip_1280x720_10b_444_2020_59.94fps.yuv")
+    assert (p["width"], p["height"], p["bit_depth"], p["chroma_ss"], p["color_space"], p["fps"]) == (1280, 720, 10, "444", "2020", 59.94)
+    assert cv.decode_video_props("a_640x480p30_hdr.yuv")["fps"] == 30
+    assert cv.create_yuv_fname("b", p) == "b_1280x720_10b_444_2020_59.94fps.yuv"

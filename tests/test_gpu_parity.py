@@ -182,3 +182,33 @@ def test_config4_hdr_pq_4k_heatmap_one_frame():
     assert stats["heatmap"].shape == (1, 1, 18, 2160, 3840) and stats["heatmap"].dtype == torch.float16
     assert np.array_equal(stats["Q_per_ch"][:, :, 17], Q.cpu().numpy()[:, :, 17])
     assert 0.0 < float(jod) < 10.0
+
+
+@pytest.mark.parametrize("name", gu.yuv_case_names())
+def test_yuv_files(name, tmp_path):
+    """Raw planar YUV ingestion fused into the temporal front end, against the reference fixture."""
+    tf, rf, z, meta = gu.write_yuv_case(name, str(tmp_path))
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"], device=DEV)
+    vs = cv.video_source_yuv_file(tf, rf, display_photometry=meta["display"])
+    jod, stats = m.predict_video_source(vs)
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+    rgb = vs.test_vidr.get_frame_rgb_tensor(z["Q_per_ch"].shape[2] - 1, DEV)
+    assert np.max(np.abs(rgb.cpu().numpy() - z["rgb_last_test_frame"])) <= 2e-6
+
+
+def test_yuv_1080p_matches_oracle_and_rgb_path(tmp_path):
+    """1080p 4:2:0 8-bit clip: fused YUV path == (oracle RGB conversion -> fp32 RGB path)."""
+    from golden.make_golden_yuv_synth import synth_yuv  # shared synthetic YUV generator
+    F, H, W = 10, 1080, 1920
+    t, r = synth_yuv(71, F, H, W, "420", 8)
+    props = {"width": W, "height": H, "fps": 30, "bit_depth": 8, "color_space": "709", "chroma_ss": "420"}
+    tf, rf = str(tmp_path / cv.create_yuv_fname("t", props)), str(tmp_path / cv.create_yuv_fname("r", props))
+    t.tofile(tf), r.tofile(rf)
+    m = cv.cvvdp(display_name="standard_fhd", device=DEV)
+    jod, stats = m.predict_video_source(cv.video_source_yuv_file(tf, rf, display_photometry="standard_fhd"))
+    T, _ = O.read_yuv_rgb(tf)
+    R, _ = O.read_yuv_rgb(rf)
+    jod2, stats2 = m.predict(torch.from_numpy(T).to(DEV), torch.from_numpy(R).to(DEV), frames_per_second=30)
+    gu.assert_q_close(stats["Q_per_ch"], stats2["Q_per_ch"], "yuv vs rgb path")
+    assert abs(float(jod) - float(jod2)) <= 1e-4

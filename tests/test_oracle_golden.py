@@ -99,3 +99,14 @@ def test_oracle_vs_live_reference_random_shapes():
         jod, stats = O.predict(tst, ref, "BCFHW", fps, disp, pad)
         gu.assert_q_close(stats["Q_per_ch"], s["Q_per_ch"], f"{F}x{H}x{W}")
         assert abs(float(jod) - float(q)) <= gu.JOD_TOL
+
+
+@pytest.mark.parametrize("name", gu.yuv_case_names())
+def test_oracle_yuv_ingestion(name, tmp_path):
+    """Raw planar YUV files: unpack + chroma upsampling + matrix, then the whole path."""
+    tf, rf, z, meta = gu.write_yuv_case(name, str(tmp_path))
+    rgb, fps = O.read_yuv_rgb(tf)
+    assert np.max(np.abs(rgb[0, :, -1].transpose(1, 2, 0) - z["rgb_last_test_frame"])) <= 2e-6
+    jod, stats = O.predict_yuv(tf, rf, meta["display"], meta["padding"])
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
