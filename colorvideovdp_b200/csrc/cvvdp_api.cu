@@ -414,9 +414,19 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             if (cvw.s[4] != 1 || cvw.s[3] != job.width) staged = false;
             if (((uintptr_t)cvw.data) % 16 || (cvw.s[0] * es) % 16 || (cvw.s[1] * es) % 16 || (cvw.s[2] * es) % 16) staged = false;
         }
+        // packed two-pixels-per-thread variant: additionally whole 64-pixel warp segments
+        static const bool no_x2 = getenv("CVVDP_B200_NO_TX2") != nullptr;
+        const bool packed = staged && !no_x2 && npix % 64 == 0;
+        dim3 grid_x2((unsigned)((npix / 64 + CVVDP_TX2_THREADS / 32 - 1) / (CVVDP_TX2_THREADS / 32)), (unsigned)(B * 2));
 #define CVVDP_TEMPORAL_CASE(FLV)                                                              \
     case FLV: {                                                                               \
-        if (staged && use_lut) {                                                              \
+        if (packed && use_lut) {                                                              \
+            auto kfn = k_temporal_x2<FLV, true>;                                              \
+            CVVDP_LAUNCH(kfn, grid_x2, dim3(CVVDP_TX2_THREADS), 0, st, ta);                   \
+        } else if (packed) {                                                                  \
+            auto kfn = k_temporal_x2<FLV, false>;                                             \
+            CVVDP_LAUNCH(kfn, grid_x2, dim3(CVVDP_TX2_THREADS), 0, st, ta);                   \
+        } else if (staged && use_lut) {                                                       \
             auto kfn = k_temporal_stg<FLV, true>;                                             \
             CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
         } else if (staged) {                                                                  \
@@ -431,15 +441,19 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         }                                                                                     \
     } break;
         switch (info.filter_len) {
+#ifndef CVVDP_DEV_FAST  // development builds keep only 30 and 60 fps specialisations (the rest takes the generic kernel)
             CVVDP_TEMPORAL_CASE(1)
             CVVDP_TEMPORAL_CASE(3)
             CVVDP_TEMPORAL_CASE(5)
             CVVDP_TEMPORAL_CASE(7)
-            CVVDP_TEMPORAL_CASE(9)
             CVVDP_TEMPORAL_CASE(11)
             CVVDP_TEMPORAL_CASE(13)
             CVVDP_TEMPORAL_CASE(15)
+#endif
+#ifndef CVVDP_DEV_NO_TEMPORAL  // SASS-inspection builds of the other kernels
+            CVVDP_TEMPORAL_CASE(9)
             CVVDP_TEMPORAL_CASE(17)
+#endif
             default: {  // long filters (> 64 fps): generic shared-memory ring
                 auto kfn = k_temporal;
                 CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
@@ -521,11 +535,26 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             ba.tm_coarse = ctx->lv[i + 1].tm_as_coarse;
         }
         dim3 grid(lv.tiles_x, lv.tiles_y, pairs);
-        auto kfn = k_band2;
         LaunchScope ls(ctx, st, CVVDP_K_BAND, i,
                        (double)pairs * 2 * 16.0 * ((double)ba.h * ba.w + (double)ba.hc * ba.wc) +
                            (do_hm ? (double)pairs * 4.0 * ba.h * ba.w : 0.0));
-        CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Band2Smem), st, ba);
+        const int variant = (ba.do_blur ? 4 : 0) | (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
+#define CVVDP_BAND_CASE(V)                                                                         \
+    case V: {                                                                                      \
+        auto kfn = k_band2<((V) & 4) != 0, ((V) & 2) != 0, ((V) & 1) != 0>;                        \
+        CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Band2Smem), st, ba);                \
+    } break;
+        switch (variant) {
+            CVVDP_BAND_CASE(0)
+            CVVDP_BAND_CASE(1)
+            CVVDP_BAND_CASE(2)
+            CVVDP_BAND_CASE(3)
+            CVVDP_BAND_CASE(4)
+            CVVDP_BAND_CASE(5)
+            CVVDP_BAND_CASE(6)
+            CVVDP_BAND_CASE(7)
+        }
+#undef CVVDP_BAND_CASE
     }
     {
         BasebandArgs bb;
@@ -678,8 +707,12 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
         cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming);
     }
-    auto kb = k_band2;
-    cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
+    {
+        void (*kb[8])(const BandArgs) = {k_band2<false, false, false>, k_band2<false, false, true>, k_band2<false, true, false>,
+                                         k_band2<false, true, true>,   k_band2<true, false, false>, k_band2<true, false, true>,
+                                         k_band2<true, true, false>,   k_band2<true, true, true>};
+        for (auto k : kb) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
+    }
     auto kr2 = k_reduce2;
     cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem));
     auto kt = k_temporal;

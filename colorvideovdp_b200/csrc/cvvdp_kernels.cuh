@@ -534,6 +534,148 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_stg(const T
     cp_async_wait_all();
 }
 
+// Packed variant of the staged kernel: a thread owns TWO pixels of the warp's 64-pixel segment (lane l:
+// pixels l and l+32, so both 128-bit stores of a warp cover 512 contiguous bytes) and keeps them as the
+// two halves of fp32x2 registers.  The FIR then costs one FFMA2 per (tap, channel) for both pixels --
+// the tap is a uniform-register broadcast operand -- and every staging / addressing instruction is
+// shared by the pair: ~1/3 of the warp instructions of k_temporal_stg per pixel.  The per-lane
+// arithmetic (EOTF table or eotf_forward, matrix order, tap order) is the one of the other variants.
+// Needs what k_temporal_stg needs, with H*W % 64 == 0.
+#define CVVDP_TX2_THREADS 128
+#define CVVDP_TX2_DEPTH 4
+#define CVVDP_TX2_SLOT (3 * 64 * 4)  // bytes of one stage slot: 3 channels x 64 pixels x up to 4 bytes
+template <int FL, bool USE_LUT>
+__global__ void __launch_bounds__(CVVDP_TX2_THREADS, 3) k_temporal_x2(const __grid_constant__ TemporalArgs a) {
+    __shared__ float s_lut[256];
+    __shared__ __align__(16) unsigned char s_stage[(CVVDP_TX2_THREADS / 32) * CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (USE_LUT) {
+        for (int i = tid; i < 256; i += CVVDP_TX2_THREADS) {
+            float v[1] = {(float)i / 255.0f};
+            eotf_forward(v, 1, a.dd);
+            s_lut[i] = v[0];
+        }
+        __syncthreads();
+    }
+    const long long npix = (long long)a.H * a.W;
+    const long long wp = ((long long)blockIdx.x * (CVVDP_TX2_THREADS / 32) + warp) * 64;  // first pixel of the warp
+    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
+    if (wp >= npix) return;  // whole 64-pixel segments only (npix % 64 == 0)
+    const ClipView &cv = a.clip[v];
+    const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
+    const int row_bytes = 64 * esz;   // one (channel, frame) segment of this warp
+    const int cpc = row_bytes / 16;   // 16-byte pieces per channel segment: 4, 8 or 16
+    const int npieces = a.cin * cpc;  // <= 48: lanes copy one piece, lanes < npieces-32 a second one
+    unsigned char *wst = s_stage + warp * (CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT);
+    const long long fstride = cv.s[2] * esz;
+    const unsigned char *wsrc = (const unsigned char *)cv.data + (b * cv.s[0] + wp) * esz;
+    const int pc0 = lane / cpc, pc1 = (lane + 32) / cpc;
+    const unsigned char *psrc0 = wsrc + (long long)pc0 * cv.s[1] * esz + (lane - pc0 * cpc) * 16;
+    const unsigned char *psrc1 = wsrc + (long long)pc1 * cv.s[1] * esz + (lane + 32 - pc1 * cpc) * 16;
+    const int pdst0 = lane * 16, pdst1 = (lane + 32) * 16;  // channel segments are contiguous in a slot
+    const int n = a.f1 - a.f0;
+    const int NI = (FL - 1) + n;
+    float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + wp + lane;
+    const long long ostep = 2 * npix;
+    constexpr int RP = FL + 1;
+    float2 r0[RP], r1[RP], r2[RP];
+#pragma unroll
+    for (int i = 0; i < RP; ++i) r0[i] = r1[i] = r2[i] = make_float2(0.f, 0.f);
+
+    // Stage bookkeeping: iteration i (frame f0-(FL-1)+i, padded before frame 0) lands in stage slot i % DEPTH.
+    // The copies run DEPTH-1 iterations ahead.  Warm-up iterations resolve the temporal padding (integer
+    // divisions); from iteration FL-1 on the clip slot just advances, so the steady-state loop carries no
+    // padding logic.  (FL-1 warm-up fetches each issue one copy: the warm-up issues cover iterations
+    // < FL-1 + DEPTH-1, hence the `i < FL - 1` test below and a plain increment afterwards.)
+    const int slots = cv.ring > 0 ? cv.ring : 0x7fffffff;
+    int pf_it = 0, pf_slot = frame_slot(cv, a.f0), pf_off = 0, rd_off = 0;
+    auto copy_frame = [&](int slot) {
+        unsigned char *dst = wst + pf_off;
+        if (lane < npieces) cp_async16(dst + pdst0, psrc0 + (long long)slot * fstride);
+        if (lane + 32 < npieces) cp_async16(dst + pdst1, psrc1 + (long long)slot * fstride);
+    };
+    auto advance = [&]() {
+        pf_off = pf_off + CVVDP_TX2_SLOT == CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT ? 0 : pf_off + CVVDP_TX2_SLOT;
+        ++pf_it;
+        cp_async_commit();
+    };
+    auto issue_warm = [&]() {  // any iteration
+        if (pf_it < NI) {
+            if (pf_it < FL - 1) {
+                copy_frame(frame_slot(cv, temporal_source_frame(a, a.f0 - (FL - 1) + pf_it)));
+            } else {
+                copy_frame(pf_slot);
+                pf_slot = pf_slot + 1 == slots ? 0 : pf_slot + 1;
+            }
+        }
+        advance();
+    };
+    auto issue_steady = [&]() {  // iterations >= FL-1 only
+        if (pf_it < NI) {
+            copy_frame(pf_slot);
+            pf_slot = pf_slot + 1 == slots ? 0 : pf_slot + 1;
+        }
+        advance();
+    };
+    // wait for the oldest outstanding iteration, convert this lane's two pixels to DKL
+    auto fetch = [&](float2 &d0, float2 &d1, float2 &d2) {
+        cp_async_wait_n<CVVDP_TX2_DEPTH - 1>();
+        __syncwarp();
+        const unsigned char *q = wst + rd_off;
+        rd_off = rd_off + CVVDP_TX2_SLOT == CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT ? 0 : rd_off + CVVDP_TX2_SLOT;
+        unsigned ba[3], bb[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const unsigned char *qc = q + (a.cin == 3 ? c : 0) * row_bytes;
+            if (esz == 1) {
+                ba[c] = qc[lane];
+                bb[c] = qc[lane + 32];
+            } else if (esz == 2) {
+                ba[c] = ((const unsigned short *)qc)[lane];
+                bb[c] = ((const unsigned short *)qc)[lane + 32];
+            } else {
+                ba[c] = ((const unsigned *)qc)[lane];
+                bb[c] = ((const unsigned *)qc)[lane + 32];
+            }
+        }
+        __syncwarp();  // every lane has read the slot before it is refilled
+        bits_to_dkl<USE_LUT>(a, s_lut, ba, d0.x, d1.x, d2.x);
+        bits_to_dkl<USE_LUT>(a, s_lut, bb, d0.y, d1.y, d2.y);
+    };
+#pragma unroll
+    for (int i = 0; i < CVVDP_TX2_DEPTH - 1; ++i) issue_warm();
+#pragma unroll
+    for (int s = 0; s < FL - 1; ++s) {
+        issue_warm();
+        fetch(r0[s], r1[s], r2[s]);
+    }
+    // here pf_it = FL-1 + DEPTH-1 >= FL-1: only steady issues from now on
+    for (int tb = a.f0; tb < a.f1; tb += RP) {
+#pragma unroll
+        for (int j = 0; j < RP; ++j) {
+            const int t = tb + j;
+            if (t < a.f1) {  // uniform
+                const int s = (FL - 1 + j) % RP;
+                issue_steady();
+                fetch(r0[s], r1[s], r2[s]);
+                float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+#pragma unroll
+                for (int k = 0; k < FL; ++k) {
+                    const int sl = (s + RP - (FL - 1) + k) % RP;
+                    o0 = fma2(bc2(a.taps[0][k]), r0[sl], o0);
+                    o1 = fma2(bc2(a.taps[1][k]), r1[sl], o1);
+                    o2 = fma2(bc2(a.taps[2][k]), r2[sl], o2);
+                    o3 = fma2(bc2(a.taps[3][k]), r0[sl], o3);
+                }
+                outp[0] = make_float4(o0.x, o1.x, o2.x, o3.x);
+                outp[32] = make_float4(o0.y, o1.y, o2.y, o3.y);
+                outp += ostep;
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
 // =================================================================================================
 // Gaussian pyramid reduce  (lpyr_dec.py:186-211): zero-padded 5-tap stride-2 passes (rows, then
 // columns) with the reference's edge fix-ups, including the parity quirk at line 206 (the ROW count
@@ -756,10 +898,12 @@ struct BandArgs {
     int do_blur;
     float mul;             // get_band: 1 for band 0, 2 for middle bands (lpyr_dec.py:60-66)
     float lut_a, lut_b;    // LUT index = clamp(log2(L_bkg) * lut_a + lut_b, 0, 31)
-    float kern[2 * CVVDP_BHALO + 1];
+    // packed-operand constants: 16-byte aligned so that pairs load straight into aligned uniform-register pairs
+    alignas(16) float X[16];  // 2^xcm_weights [source][masked]
+    alignas(16) float q[4];
+    alignas(16) float kern[2 * CVVDP_BHALO + 1];
     float mc;              // 10^mask_c
-    float q[4], p;
-    float X[16];           // 2^xcm_weights [source][masked]
+    float p;
     float dmax;            // 10^d_max
     float eps;
     float beta;
@@ -1085,12 +1229,18 @@ __device__ __forceinline__ void band2_stage(const BandArgs &a, Band2Smem &sm, co
     cp_async_commit();
 }
 
+// Template flags: BLUR = phase-uncertainty Gaussian on (off only for levels with h <= 6 or w <= 6, Q7),
+// HM = write the per-band heat-map plane, BETA2 = spatial pooling exponent is exactly 2 (shipped value).
+// The per-pixel bodies of phases A and C are straight-line code (no per-pixel branches): rows and
+// columns outside the segment are computed on whatever the stage holds and discarded by a select, so
+// the compiler can interleave the MUFU chains of a thread's four pixels.
+template <bool BLUR, bool HM, bool BETA2>
 __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_constant__ BandArgs a) {
     CVVDP_DYN_SMEM(smem_raw);
     Band2Smem &sm = *reinterpret_cast<Band2Smem *>(smem_raw);
     const int tid = threadIdx.x;
     const int pair = blockIdx.z;
-    const int hal = a.do_blur ? CVVDP_BHALO : 0;
+    constexpr int hal = BLUR ? CVVDP_BHALO : 0;
     const int x0 = blockIdx.x * CVVDP_B2_SW, ex0 = x0 - hal;  // even
     const int ys = blockIdx.y * a.seg_rows, ye = min(ys + a.seg_rows, a.h);
     const int y_begin = max(ys - hal, 0);                     // even
@@ -1112,7 +1262,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
 #pragma unroll
     for (int c = 0; c < 4; ++c) eps_q[c] = f_pow(a.eps, a.q[c]);
     const float eps_p = f_pow(a.eps, a.p);
-    const float eps_b = (a.beta == 2.0f) ? 0.f : f_pow(a.eps, a.beta);
+    const float eps_b = BETA2 ? 0.f : f_pow(a.eps, a.beta);
     float4 acc = f4(0.f);
     // loop-invariant thread roles
     const int qy = tid / (CVVDP_B2_EW / 2), qx = tid - qy * (CVVDP_B2_EW / 2);  // phase A: one 2x2 quad
@@ -1163,16 +1313,21 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                     e[v][2] = fma4(0.1f, vo[2], fma4(0.8f, vo[1], 0.1f * vo[0]));
                     e[v][3] = fma4(0.5f, vo[2], 0.5f * vo[1]);
                 }
+                // pixels beyond the image / segment are evaluated on the stage's fill values and never read back
+                // (phase B reflects at the borders, phase C selects); their df slot belongs to rows long consumed
+                float4 mm[4], df[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
-                    const int py = a0 + ry, px = ex0 + rx;
-                    if (py >= a_end || px < 0 || px >= a.w) continue;
-                    float4 mm, df;
-                    band_pixel(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm, df);
-                    sm.mm[ry][rx] = mm;
-                    const int ix = px - x0;
-                    if (ix >= 0 && ix < CVVDP_B2_SW) sm.df[py & (CVVDP_B2_DFR - 1)][ix] = df;
+                    band_pixel(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm[k], df[k]);
+                }
+                const int ix = ex0 + 2 * qx - x0;  // even; the pair (ix, ix+1) is inside or outside the strip together
+                const bool in_strip = ix >= 0 && ix < CVVDP_B2_SW;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
+                    sm.mm[ry][rx] = mm[k];
+                    if (in_strip) sm.df[(a0 + ry) & (CVVDP_B2_DFR - 1)][ix + (k & 1)] = df[k];
                 }
             }
         }
@@ -1180,7 +1335,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
         // ---- prefetch the next step's stage while phases B and C run ----
         if (a0 + CVVDP_B2_RB < a_end) band2_stage(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B2_RB, a_end, ex0, tid, pair);
         // ---- phase B: horizontal pass of the phase-uncertainty Gaussian for the new rows ----
-        if (have_a && a.do_blur && tid < CVVDP_B2_RB * (CVVDP_B2_SW / 4)) {
+        if (BLUR && have_a && tid < CVVDP_B2_RB * (CVVDP_B2_SW / 4)) {
             const int gy = a0 + b_r, gxb = x0 + b_xg * 4;
             if (gy < a_end && gxb < a.w) {
                 float4 win[2 * CVVDP_BHALO + 4];
@@ -1212,7 +1367,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
             const int cyb = a0 - hal + c_rg * 4;  // 4 consecutive rows per thread
             if (gx < a.w && cyb + 3 >= ys && cyb < ye) {
                 float4 win[2 * CVVDP_BHALO + 4];
-                if (a.do_blur) {
+                if (BLUR) {
                     const bool y_edge = (cyb - CVVDP_BHALO < 0) || (cyb + 3 + CVVDP_BHALO >= a.h);
                     if (y_edge) {
 #pragma unroll
@@ -1227,34 +1382,40 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                             win[j] = sm.hb[(cyb + j - CVVDP_BHALO) & (CVVDP_B2_HBR - 1)][c_ix];
                     }
                 }
+                float4 D[4];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) {
+                for (int o = 0; o < 4; ++o) {  // straight-line: rows outside [ys, ye) are discarded below
                     const int gy = cyb + o;
-                    if (gy < ys || gy >= ye) continue;
                     float4 m;
-                    if (a.do_blur) {
+                    if (BLUR) {
                         m = f4(0.f);
 #pragma unroll
                         for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) m = fma4(a.kern[k], win[o + k], m);
                     } else {
-                        m = sm.mm[gy - a0][gx - ex0];
+                        m = sm.mm[(gy - a0) & (CVVDP_B2_RB - 1)][gx - ex0];
                     }
-                    const float4 D = band_mask(a, m, sm.df[gy & (CVVDP_B2_DFR - 1)][c_ix], eps_q, eps_p);
-                    if (a.beta == 2.0f) {
-                        acc.x = fmaf(D.x, D.x + 2.f * a.eps, acc.x);
-                        acc.y = fmaf(D.y, D.y + 2.f * a.eps, acc.y);
-                        acc.z = fmaf(D.z, D.z + 2.f * a.eps, acc.z);
-                        acc.w = fmaf(D.w, D.w + 2.f * a.eps, acc.w);
+                    D[o] = band_mask(a, m, sm.df[gy & (CVVDP_B2_DFR - 1)][c_ix], eps_q, eps_p);
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int gy = cyb + o;
+                    const bool live = gy >= ys && gy < ye;
+                    float4 t;
+                    if (BETA2) {  // (D+eps)^2 - eps^2 == D (D + 2 eps), exact at D = 0
+                        const float e2 = 2.f * a.eps;
+                        t = make_float4(D[o].x * (D[o].x + e2), D[o].y * (D[o].y + e2), D[o].z * (D[o].z + e2), D[o].w * (D[o].w + e2));
                     } else {
-                        acc.x += f_pow(D.x + a.eps, a.beta) - eps_b;
-                        acc.y += f_pow(D.y + a.eps, a.beta) - eps_b;
-                        acc.z += f_pow(D.z + a.eps, a.beta) - eps_b;
-                        acc.w += f_pow(D.w + a.eps, a.beta) - eps_b;
+                        t = make_float4(f_pow(D[o].x + a.eps, a.beta) - eps_b, f_pow(D[o].y + a.eps, a.beta) - eps_b,
+                                        f_pow(D[o].z + a.eps, a.beta) - eps_b, f_pow(D[o].w + a.eps, a.beta) - eps_b);
                     }
-                    if (a.hm) {
+                    acc.x += live ? t.x : 0.f;
+                    acc.y += live ? t.y : 0.f;
+                    acc.z += live ? t.z : 0.f;
+                    acc.w += live ? t.w : 0.f;
+                    if (HM && live) {
                         const float eb = f_pow(a.eps, a.hm_beta);
-                        float s = (f_pow(D.x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D.y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
-                                  (f_pow(D.z * a.hm_w[2] + a.eps, a.hm_beta) - eb) + (f_pow(D.w * a.hm_w[3] + a.eps, a.hm_beta) - eb);
+                        float s = (f_pow(D[o].x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
+                                  (f_pow(D[o].z * a.hm_w[2] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].w * a.hm_w[3] + a.eps, a.hm_beta) - eb);
                         const float ib = 1.f / a.hm_beta;
                         a.hm[(long long)pair * npix + (long long)gy * a.w + gx] = (f_pow(s + a.eps, ib) - f_pow(a.eps, ib)) * a.hm_scale;
                     }
