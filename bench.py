@@ -340,10 +340,14 @@ def main():
     if dom_name:
         k = kernels[dom_name]
         achieved = k["bytes"] / 1e9 / (k["ms"] / 1e3)
+        # DRAM bytes of one launch of this kernel from the committed `ncu --set full` capture of this same
+        # command (profiles/ncu_traffic.json), rescaled if this run's launch covers a different frame count
         traffic = None
         tfile = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.isfile(tfile):
-            traffic = json.load(open(tfile)).get(dom_name)
+            ent = json.load(open(tfile)).get(dom_name)
+            if ent:
+                traffic = round(ent["dram_bytes_per_launch"] * (k["bytes"] / k["launches"]) / ent["algo_bytes_per_launch"], 0)
         roof = {"kernel": dom_name, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "avg_launch_ms": round(k["ms"] / k["launches"], 4),

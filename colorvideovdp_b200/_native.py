@@ -83,6 +83,7 @@ SYMBOLS = {
     "cvvdp_b200_frontend_yuv": (C.c_int, [C.c_void_p, C.POINTER(Clip), C.POINTER(Yuv), C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_launch_count": (C.c_int64, [C.c_void_p]),
+    "cvvdp_b200_band_strip_width": (C.c_int, [C.c_void_p, C.c_int]),
     "cvvdp_b200_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "cvvdp_b200_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
 }
@@ -186,6 +187,9 @@ class Context:
 
     def launch_count(self):
         return int(self._lib.cvvdp_b200_launch_count(self._h))
+
+    def band_is_wide(self, level):
+        return int(self._lib.cvvdp_b200_band_strip_width(self._h, int(level))) == 116
 
     def profile_enable(self, on=True):
         self._check(self._lib.cvvdp_b200_profile_enable(self._h, 1 if on else 0), "profile_enable")

@@ -26,6 +26,7 @@ struct LevelBuf {
     float4 *lut = nullptr;      // [32]
     int tiles_x = 0, tiles_y = 0;  // band kernel grid: column strips x row segments
     int seg_rows = 0;
+    bool wide = false;             // band kernel: k_band3 (116-column strips) instead of k_band2 (52)
     int do_blur = 0;
     TensorMap3D tm;  // fp32 view [planes][h][4w] of g; box depends on the role (see make_tensor_map)
     TensorMap3D tm_as_coarse;
@@ -417,14 +418,21 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         // packed two-pixels-per-thread variant: additionally whole 64-pixel warp segments
         static const bool no_x2 = getenv("CVVDP_B200_NO_TX2") != nullptr;
         const bool packed = staged && !no_x2 && npix % 64 == 0;
+        // A/B switch: measured slower than the 4-warp CTAs (15.1 vs 14.4 ms per 120 4K frames on the same box), off by default
+        static const bool want_lockstep = getenv("CVVDP_B200_LOCKSTEP") != nullptr;
+        const bool lockstep = want_lockstep && npix % (64 * 12) == 0;
+        dim3 grid_x12((unsigned)(npix / (64 * 12)), (unsigned)(B * 2));
         dim3 grid_x2((unsigned)((npix / 64 + CVVDP_TX2_THREADS / 32 - 1) / (CVVDP_TX2_THREADS / 32)), (unsigned)(B * 2));
 #define CVVDP_TEMPORAL_CASE(FLV)                                                              \
     case FLV: {                                                                               \
-        if (packed && use_lut) {                                                              \
-            auto kfn = k_temporal_x2<FLV, true>;                                              \
+        if (packed && use_lut && lockstep) {                                                  \
+            auto kfn = k_temporal_x2<FLV, true, 12>;                                          \
+            CVVDP_LAUNCH(kfn, grid_x12, dim3(12 * 32), 0, st, ta);                            \
+        } else if (packed && use_lut) {                                                       \
+            auto kfn = k_temporal_x2<FLV, true, 4>;                                           \
             CVVDP_LAUNCH(kfn, grid_x2, dim3(CVVDP_TX2_THREADS), 0, st, ta);                   \
         } else if (packed) {                                                                  \
-            auto kfn = k_temporal_x2<FLV, false>;                                             \
+            auto kfn = k_temporal_x2<FLV, false, 4>;                                          \
             CVVDP_LAUNCH(kfn, grid_x2, dim3(CVVDP_TX2_THREADS), 0, st, ta);                   \
         } else if (staged && use_lut) {                                                       \
             auto kfn = k_temporal_stg<FLV, true>;                                             \
@@ -538,6 +546,13 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         LaunchScope ls(ctx, st, CVVDP_K_BAND, i,
                        (double)pairs * 2 * 16.0 * ((double)ba.h * ba.w + (double)ba.hc * ba.wc) +
                            (do_hm ? (double)pairs * 4.0 * ba.h * ba.w : 0.0));
+        if (lv.wide) {
+            const int v3 = (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
+            void (*k3[4])(const BandArgs) = {k_band3<false, false>, k_band3<false, true>, k_band3<true, false>, k_band3<true, true>};
+            auto kfn = k3[v3];
+            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B3_THREADS), sizeof(Band3Smem), st, ba);
+            continue;
+        }
         const int variant = (ba.do_blur ? 4 : 0) | (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
 #define CVVDP_BAND_CASE(V)                                                                         \
     case V: {                                                                                      \
@@ -712,6 +727,8 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
                                          k_band2<false, true, true>,   k_band2<true, false, false>, k_band2<true, false, true>,
                                          k_band2<true, true, false>,   k_band2<true, true, true>};
         for (auto k : kb) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
+        void (*k3[4])(const BandArgs) = {k_band3<false, false>, k_band3<false, true>, k_band3<true, false>, k_band3<true, true>};
+        for (auto k : k3) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band3Smem));
     }
     auto kr2 = k_reduce2;
     cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem));
@@ -823,8 +840,13 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         LevelBuf &lv = ctx->lv[i];
         lv.h = info.band_height[i];
         lv.w = info.band_width[i];
-        {   // strips of 52 columns; split the rows into segments only when there are too few CTAs
-            lv.tiles_x = (lv.w + CVVDP_B2_SW - 1) / CVVDP_B2_SW;
+        lv.do_blur = (ctx->blur_pad > 0 && lv.h > ctx->blur_pad && lv.w > ctx->blur_pad) ? 1 : 0;  // cvvdp_metric.py:965
+        {   // strips of 116 columns (levels at least two such strips wide) or 52 columns; the rows are split
+            // into segments only when there are too few CTAs
+            static const bool no_wide = getenv("CVVDP_B200_NO_WIDE") != nullptr;  // A/B switch
+            lv.wide = !no_wide && lv.do_blur && lv.w >= 2 * CVVDP_B3_SW && lv.h >= 32;
+            const int sw = lv.wide ? CVVDP_B3_SW : CVVDP_B2_SW;
+            lv.tiles_x = (lv.w + sw - 1) / sw;
             // the split depends on the level geometry only, never on the batch or block size, so that
             // the summation order (hence every bit of Q_per_ch) is independent of how frames are
             // partitioned into blocks, shards or ranks
@@ -832,7 +854,6 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
             lv.seg_rows = (((lv.h + nseg - 1) / nseg) + 7) / 8 * 8;
             lv.tiles_y = (lv.h + lv.seg_rows - 1) / lv.seg_rows;
         }
-        lv.do_blur = (ctx->blur_pad > 0 && lv.h > ctx->blur_pad && lv.w > ctx->blur_pad) ? 1 : 0;  // cvvdp_metric.py:965
         const size_t npix = (size_t)lv.h * lv.w;
         off_g[i] = off;
         off += align_up(B * nb * 2 * npix * sizeof(float4), 256);
@@ -1226,6 +1247,11 @@ int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, con
 }
 
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int cvvdp_b200_band_strip_width(const cvvdp_b200_ctx *ctx, int level) {
+    if (!ctx || !ctx->planned || level < 0 || level + 1 >= (int)ctx->lv.size()) return 0;
+    return ctx->lv[level].wide ? CVVDP_B3_SW : CVVDP_B2_SW;
+}
 
 int cvvdp_b200_profile_enable(cvvdp_b200_ctx *ctx, int enable) {
     if (!ctx) return CVVDP_ERR_INVALID;

@@ -188,6 +188,25 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const TensorMap3D *m
 __device__ __forceinline__ void mbar_emu_complete(unsigned long long *) {}
 #endif
 
+// ---- 1-D bulk copies (cp.async.bulk, the TMA engine without a tensor map): 16-byte aligned source,
+// destination and size; completion is signalled on an mbarrier like the tensor copies -------------------
+#ifdef CVVDP_EMU
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *) {
+    memcpy(smem_dst, gmem_src, bytes);
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *) {}
+#else
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+#endif
+
 // ---- float4 arithmetic ------------------------------------------------------------------------
 // On sm_100 the four lanes of a pixel are processed as two packed fp32x2 operations (FFMA2 / FADD2 /
 // FMUL2, PTX fma.rn.f32x2): same IEEE results per lane, half the issue slots -- these kernels are

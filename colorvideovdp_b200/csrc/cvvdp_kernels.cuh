@@ -544,13 +544,14 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_stg(const T
 #define CVVDP_TX2_THREADS 128
 #define CVVDP_TX2_DEPTH 4
 #define CVVDP_TX2_SLOT (3 * 64 * 4)  // bytes of one stage slot: 3 channels x 64 pixels x up to 4 bytes
-template <int FL, bool USE_LUT>
-__global__ void __launch_bounds__(CVVDP_TX2_THREADS, 3) k_temporal_x2(const __grid_constant__ TemporalArgs a) {
+template <int FL, bool USE_LUT, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, NWARPS == 4 ? 3 : 1) k_temporal_x2(const __grid_constant__ TemporalArgs a) {
+    constexpr bool CTA_SYNC = NWARPS != 4;  // lockstep variant: one 12-warp CTA per SM
     __shared__ float s_lut[256];
-    __shared__ __align__(16) unsigned char s_stage[(CVVDP_TX2_THREADS / 32) * CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT];
+    __shared__ __align__(16) unsigned char s_stage[NWARPS * CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (USE_LUT) {
-        for (int i = tid; i < 256; i += CVVDP_TX2_THREADS) {
+        for (int i = tid; i < 256; i += NWARPS * 32) {
             float v[1] = {(float)i / 255.0f};
             eotf_forward(v, 1, a.dd);
             s_lut[i] = v[0];
@@ -558,9 +559,9 @@ __global__ void __launch_bounds__(CVVDP_TX2_THREADS, 3) k_temporal_x2(const __gr
         __syncthreads();
     }
     const long long npix = (long long)a.H * a.W;
-    const long long wp = ((long long)blockIdx.x * (CVVDP_TX2_THREADS / 32) + warp) * 64;  // first pixel of the warp
+    const long long wp = ((long long)blockIdx.x * NWARPS + warp) * 64;  // first pixel of the warp
     const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
-    if (wp >= npix) return;  // whole 64-pixel segments only (npix % 64 == 0)
+    if (wp >= npix) return;  // whole 64-pixel segments only (npix % 64 == 0); CTA_SYNC: npix % (64 NWARPS) == 0, no partial CTA
     const ClipView &cv = a.clip[v];
     const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
     const int row_bytes = 64 * esz;   // one (channel, frame) segment of this warp
@@ -638,7 +639,12 @@ __global__ void __launch_bounds__(CVVDP_TX2_THREADS, 3) k_temporal_x2(const __gr
                 bb[c] = ((const unsigned *)qc)[lane + 32];
             }
         }
-        __syncwarp();  // every lane has read the slot before it is refilled
+        // every lane has read the slot before it is refilled.  In the 12-warp variant a CTA-wide barrier
+        // replaces __syncwarp: it keeps all warps of the SM at the same place of the fully unrolled (~60 KB)
+        // time loop, so the three warps of a scheduler share one instruction stream through its 6 KB L0
+        // instruction cache (ncu on the 4-warp variant: 2.4 stall cycles per issue waiting for instructions)
+        if (CTA_SYNC) __syncthreads();
+        else __syncwarp();
         bits_to_dkl<USE_LUT>(a, s_lut, ba, d0.x, d1.x, d2.x);
         bits_to_dkl<USE_LUT>(a, s_lut, bb, d0.y, d1.y, d2.y);
     };
@@ -1441,6 +1447,304 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < CVVDP_B2_THREADS / 32; ++w) s += sm.red[w][tid];
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
+        a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
+    }
+}
+
+// =================================================================================================
+// Fused band kernel, wide strips (levels at least two strips wide, blur on).  Same arithmetic and the
+// same three phases per step as k_band2, re-proportioned for FP32-pipe efficiency and occupancy:
+//   * a CTA of 256 threads owns 116 columns (128 with the +-6 halo): the redundant halo columns of
+//     phase A drop from 23 % to 10 %, phases B and C keep 232 of 256 threads busy (81 % -> 91 %);
+//   * 110 KB of shared memory per CTA -> 2 CTAs = 16 warps per SM (k_band2: 12): the mutual-masking
+//     rows overwrite the test rows of the stage in place (each thread consumes exactly the four pixels
+//     it then overwrites), the ring of horizontally blurred rows holds exactly the 20 live rows;
+//   * the stage is filled by 1-D bulk copies (cp.async.bulk, one row each, issued by 28 lanes and
+//     counted on one mbarrier): rows land with a padded stride (129 float4), so the row-per-lane
+//     accesses of phase B stay free of bank conflicts, which a tensor-map box (dense rows, 128-byte
+//     aligned) cannot give.  Nothing outside the image is copied; those entries are never consumed.
+// =================================================================================================
+#define CVVDP_B3_SW 116
+#define CVVDP_B3_EW 128
+#define CVVDP_B3_RB 8
+#define CVVDP_B3_THREADS 256
+#define CVVDP_B3_HBR 20
+#define CVVDP_B3_DFR 16
+#define CVVDP_B3_CR (CVVDP_B3_RB / 2 + 2)  // 6 coarse rows per step
+#define CVVDP_B3_CC (CVVDP_B3_EW / 2 + 2)  // 66 coarse columns
+#define CVVDP_B3_FS (CVVDP_B3_EW + 1)      // padded row stride of the fine / mm rows
+#define CVVDP_B3_NCOPY (2 * CVVDP_B3_RB + 2 * CVVDP_B3_CR)  // bulk copies (= mbarrier arrivals) per step
+
+struct Band3Smem {
+    float4 lut[CVVDP_CSF_LUT_N];
+    float4 crs[2][CVVDP_B3_CR][CVVDP_B3_CC];
+    float4 fine[2][CVVDP_B3_RB][CVVDP_B3_FS];  // [0] = test rows, overwritten by min(|T'|,|R'|) in phase A
+    float4 hb[CVVDP_B3_HBR][CVVDP_B3_SW + 1];
+    float4 df[CVVDP_B3_DFR][CVVDP_B3_SW];
+    float red[CVVDP_B3_THREADS / 32][4];
+    unsigned long long bar;
+};
+
+// Copy `c` of the stage of rows [a0, a0+8): c < 8: test row c; c < 16: reference row c-8; else the
+// coarse rows under them (test, then reference).  Every copy arrives once on the barrier.
+__device__ __forceinline__ void band3_copy(const BandArgs &a, Band3Smem &sm, const float4 *fine_t, const float4 *crs_g,
+                                           long long npix, long long ncpix, int a0, int a_end, int ex0, int c) {
+    void *dst = nullptr;
+    const float4 *src = nullptr;
+    int n = 0;
+    if (c < 2 * CVVDP_B3_RB) {
+        const int v = c / CVVDP_B3_RB, r = c - v * CVVDP_B3_RB, gy = a0 + r;
+        const int gx0 = max(ex0, 0), gx1 = min(ex0 + CVVDP_B3_EW, a.w);
+        if (gy < a_end && gx1 > gx0) {
+            n = gx1 - gx0;
+            dst = &sm.fine[v][r][gx0 - ex0];
+            src = fine_t + v * npix + (long long)gy * a.w + gx0;
+        }
+    } else {
+        const int cc = c - 2 * CVVDP_B3_RB, v = cc / CVVDP_B3_CR, r = cc - v * CVVDP_B3_CR;
+        const int cy = a0 / 2 - 1 + r, cx0 = ex0 / 2 - 1;
+        const int gx0 = max(cx0, 0), gx1 = min(cx0 + CVVDP_B3_CC, a.wc);
+        if (cy >= 0 && cy < a.hc && gx1 > gx0) {
+            n = gx1 - gx0;
+            dst = &sm.crs[v][r][gx0 - cx0];
+            src = crs_g + v * ncpix + (long long)cy * a.wc + gx0;
+        }
+    }
+    if (n > 0) {
+        mbar_expect_tx(&sm.bar, 16u * n);
+        bulk_copy_g2s(dst, src, 16u * n, &sm.bar);
+    } else {
+        mbar_arrive(&sm.bar);
+    }
+}
+// Issue copies [c0, c1) of a stage: one lane each on the device, one thread in the mock-device build
+// (whose copies are synchronous; the phase is completed after the last group).
+__device__ __forceinline__ void band3_issue(const BandArgs &a, Band3Smem &sm, const float4 *fine_t, const float4 *crs_g,
+                                            long long npix, long long ncpix, int a0, int a_end, int ex0, int tid, int c0, int c1,
+                                            bool last) {
+#ifdef CVVDP_EMU
+    if (tid == 0) {
+        for (int c = c0; c < c1; ++c) band3_copy(a, sm, fine_t, crs_g, npix, ncpix, a0, a_end, ex0, c);
+        if (last) mbar_emu_complete(&sm.bar);
+    }
+#else
+    (void)last;
+    if (tid < c1 - c0) {
+        fence_proxy_async();  // the destination was last touched through the generic proxy
+        band3_copy(a, sm, fine_t, crs_g, npix, ncpix, a0, a_end, ex0, c0 + tid);
+    }
+#endif
+}
+
+template <bool HM, bool BETA2>
+__global__ void __launch_bounds__(CVVDP_B3_THREADS, 2) k_band3(const __grid_constant__ BandArgs a) {
+    CVVDP_DYN_SMEM(smem_raw);
+    Band3Smem &sm = *reinterpret_cast<Band3Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.z;
+    constexpr int hal = CVVDP_BHALO;
+    const int x0 = blockIdx.x * CVVDP_B3_SW, ex0 = x0 - hal;  // even
+    const int ys = blockIdx.y * a.seg_rows, ye = min(ys + a.seg_rows, a.h);
+    const int y_begin = max(ys - hal, 0);  // even
+    const int a_end = min(ye + hal, a.h);
+    const long long npix = (long long)a.h * a.w, ncpix = (long long)a.hc * a.wc;
+    const float4 *fine_t = a.fine + (long long)pair * 2 * npix;
+    const float4 *crs_g = a.coarse + (long long)pair * 2 * ncpix;
+    const bool x_edge = (ex0 < 0) || (x0 + CVVDP_B3_SW + hal > a.w);
+    const int cx0 = ex0 / 2 - 1;
+
+    if (tid == 0) mbar_init(&sm.bar, CVVDP_B3_NCOPY);
+    if (tid < CVVDP_CSF_LUT_N) sm.lut[tid] = a.lut[tid];
+    __syncthreads();
+    unsigned phase = 0;
+    // copies 0..7 (test rows) are issued apart from the rest: their destination doubles as mm
+    band3_issue(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, CVVDP_B3_RB, CVVDP_B3_NCOPY, false);
+    band3_issue(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, 0, CVVDP_B3_RB, true);
+    float eps_q[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) eps_q[c] = f_pow(a.eps, a.q[c]);
+    const float eps_p = f_pow(a.eps, a.p);
+    const float eps_b = BETA2 ? 0.f : f_pow(a.eps, a.beta);
+    float4 acc = f4(0.f);
+    const int qy = tid / (CVVDP_B3_EW / 2), qx = tid - qy * (CVVDP_B3_EW / 2);  // phase A: one 2x2 quad
+    const int b_r = tid % CVVDP_B3_RB, b_xg = tid / CVVDP_B3_RB;               // phase B: row, group of 4 columns
+    const int c_ix = tid % CVVDP_B3_SW, c_rg = tid / CVVDP_B3_SW;              // phase C: column, group of 4 rows
+    const int a_gx = ex0 + 2 * qx;
+    const bool a_cols = a_gx + 1 >= 0 && a_gx < a.w;
+    float4(*mm)[CVVDP_B3_FS] = sm.fine[0];
+    int ring0 = 0;  // hb slot of row a0 = (a0 - y_begin) mod 20
+
+    for (int a0 = y_begin; a0 - hal < ye; a0 += CVVDP_B3_RB) {
+        const bool have_a = a0 < a_end;
+        if (have_a) {
+            mbar_wait(&sm.bar, phase);
+            phase ^= 1u;
+            // the reference pads the coarse level by replication (lpyr_dec.py:136-141): fill the entries
+            // outside the coarse image from the nearest valid row / column
+            const int cy0 = a0 / 2 - 1;
+            if (cy0 < 0 || cy0 + CVVDP_B3_CR > a.hc || cx0 < 0 || cx0 + CVVDP_B3_CC > a.wc) {
+                for (int i = tid; i < 2 * CVVDP_B3_CR * CVVDP_B3_CC; i += CVVDP_B3_THREADS) {
+                    const int v = i / (CVVDP_B3_CR * CVVDP_B3_CC), rem = i - v * (CVVDP_B3_CR * CVVDP_B3_CC);
+                    const int r = rem / CVVDP_B3_CC, c = rem - r * CVVDP_B3_CC;
+                    const int rr = min(max(cy0 + r, 0), a.hc - 1) - cy0, cc = min(max(cx0 + c, 0), a.wc - 1) - cx0;
+                    if ((rr != r || cc != c) && rr >= 0 && rr < CVVDP_B3_CR && cc >= 0 && cc < CVVDP_B3_CC)
+                        sm.crs[v][r][c] = sm.crs[v][rr][cc];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase A: one 2x2 quad per thread: expand, contrast, CSF -> mm (in place of the test rows), df ----
+        if (have_a) {
+            const int gy = a0 + 2 * qy;
+            if (gy < a_end && a_cols) {
+                float4 e[2][4];
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    float4 ve[3], vo[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 c0 = sm.crs[v][qy][qx + c], c1 = sm.crs[v][qy + 1][qx + c], c2 = sm.crs[v][qy + 2][qx + c];
+                        ve[c] = fma4(0.1f, c2, fma4(0.8f, c1, 0.1f * c0));
+                        vo[c] = fma4(0.5f, c2, 0.5f * c1);
+                    }
+                    e[v][0] = fma4(0.1f, ve[2], fma4(0.8f, ve[1], 0.1f * ve[0]));
+                    e[v][1] = fma4(0.5f, ve[2], 0.5f * ve[1]);
+                    e[v][2] = fma4(0.1f, vo[2], fma4(0.8f, vo[1], 0.1f * vo[0]));
+                    e[v][3] = fma4(0.5f, vo[2], 0.5f * vo[1]);
+                }
+                float4 mmv[4], dfv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
+                    band_pixel(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mmv[k], dfv[k]);
+                }
+                const int ix = ex0 + 2 * qx - x0;
+                const bool in_strip = ix >= 0 && ix < CVVDP_B3_SW;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
+                    mm[ry][rx] = mmv[k];
+                    if (in_strip) sm.df[(a0 + ry) & (CVVDP_B3_DFR - 1)][ix + (k & 1)] = dfv[k];
+                }
+            }
+        }
+        __syncthreads();
+        const bool more = a0 + CVVDP_B3_RB < a_end;
+        // the reference rows and the coarse rows are free: prefetch them for the next step
+        if (more) band3_issue(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B3_RB, a_end, ex0, tid, CVVDP_B3_RB, CVVDP_B3_NCOPY, false);
+        // ---- phase B: horizontal pass of the phase-uncertainty Gaussian for the new rows ----
+        if (have_a && tid < CVVDP_B3_RB * (CVVDP_B3_SW / 4)) {
+            const int gy = a0 + b_r, gxb = x0 + b_xg * 4;
+            if (gy < a_end && gxb < a.w) {
+                float4 win[2 * CVVDP_BHALO + 4];
+                if (x_edge) {
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                        int lx = reflect_idx(gxb + j - CVVDP_BHALO, a.w) - ex0;
+                        lx = min(max(lx, 0), CVVDP_B3_EW - 1);  // only for outputs beyond the image (discarded)
+                        win[j] = mm[b_r][lx];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) win[j] = mm[b_r][b_xg * 4 + j];
+                }
+                int slot = ring0 + b_r;
+                slot -= slot >= CVVDP_B3_HBR ? CVVDP_B3_HBR : 0;
+                float4 *dst = &sm.hb[slot][b_xg * 4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    float4 sacc = f4(0.f);
+#pragma unroll
+                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) sacc = fma4(a.kern[k], win[o + k], sacc);
+                    dst[o] = sacc;
+                }
+            }
+        }
+        __syncthreads();
+        // mm is consumed: prefetch the test rows of the next step into its place
+        if (more) band3_issue(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B3_RB, a_end, ex0, tid, 0, CVVDP_B3_RB, true);
+        // ---- phase C: vertical pass, masking, clamp, pooling for the rows whose window is complete ----
+        if (tid < 2 * CVVDP_B3_SW) {
+            const int gx = x0 + c_ix;
+            const int cyb = a0 - hal + c_rg * 4;  // 4 consecutive rows per thread
+            if (gx < a.w && cyb + 3 >= ys && cyb < ye) {
+                float4 win[2 * CVVDP_BHALO + 4];
+                const bool y_edge = (cyb - CVVDP_BHALO < 0) || (cyb + 3 + CVVDP_BHALO >= a.h);
+                if (y_edge) {
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                        int yy = reflect_idx(cyb + j - CVVDP_BHALO, a.h);
+                        yy = min(max(yy, y_begin), a.h - 1);
+                        win[j] = sm.hb[(yy - y_begin) % CVVDP_B3_HBR][c_ix];
+                    }
+                } else {
+                    // row cyb-6 = a0-12+4*c_rg sits 8+4*c_rg slots after the slot of row a0 (mod 20)
+                    int s0 = ring0 + 8 + 4 * c_rg;
+                    s0 -= s0 >= CVVDP_B3_HBR ? CVVDP_B3_HBR : 0;
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                        int sl = s0 + j;
+                        sl -= sl >= CVVDP_B3_HBR ? CVVDP_B3_HBR : 0;
+                        win[j] = sm.hb[sl][c_ix];
+                    }
+                }
+                float4 D[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int gy = cyb + o;
+                    float4 m = f4(0.f);
+#pragma unroll
+                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) m = fma4(a.kern[k], win[o + k], m);
+                    D[o] = band_mask(a, m, sm.df[gy & (CVVDP_B3_DFR - 1)][c_ix], eps_q, eps_p);
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int gy = cyb + o;
+                    const bool live = gy >= ys && gy < ye;
+                    float4 t;
+                    if (BETA2) {
+                        const float e2 = 2.f * a.eps;
+                        t = make_float4(D[o].x * (D[o].x + e2), D[o].y * (D[o].y + e2), D[o].z * (D[o].z + e2), D[o].w * (D[o].w + e2));
+                    } else {
+                        t = make_float4(f_pow(D[o].x + a.eps, a.beta) - eps_b, f_pow(D[o].y + a.eps, a.beta) - eps_b,
+                                        f_pow(D[o].z + a.eps, a.beta) - eps_b, f_pow(D[o].w + a.eps, a.beta) - eps_b);
+                    }
+                    acc.x += live ? t.x : 0.f;
+                    acc.y += live ? t.y : 0.f;
+                    acc.z += live ? t.z : 0.f;
+                    acc.w += live ? t.w : 0.f;
+                    if (HM && live) {
+                        const float eb = f_pow(a.eps, a.hm_beta);
+                        float s = (f_pow(D[o].x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
+                                  (f_pow(D[o].z * a.hm_w[2] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].w * a.hm_w[3] + a.eps, a.hm_beta) - eb);
+                        const float ib = 1.f / a.hm_beta;
+                        a.hm[(long long)pair * npix + (long long)gy * a.w + gx] = (f_pow(s + a.eps, ib) - f_pow(a.eps, ib)) * a.hm_scale;
+                    }
+                }
+            }
+        }
+        ring0 += CVVDP_B3_RB;
+        ring0 -= ring0 >= CVVDP_B3_HBR ? CVVDP_B3_HBR : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if ((tid & 31) == 0) {
+        sm.red[tid >> 5][0] = acc.x;
+        sm.red[tid >> 5][1] = acc.y;
+        sm.red[tid >> 5][2] = acc.z;
+        sm.red[tid >> 5][3] = acc.w;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < CVVDP_B3_THREADS / 32; ++w) s += sm.red[w][tid];
         const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
         a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
     }

@@ -200,6 +200,10 @@ int cvvdp_b200_profile_read(cvvdp_b200_ctx *ctx, cvvdp_b200_kernel_stat *out, in
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx);
 
+/* Column-strip width of the band kernel chosen for pyramid level `level` of the current plan (116: wide-strip
+ * kernel, 52: narrow-strip kernel, 0: baseband or no plan).  Introspection for tests and profiling only. */
+int cvvdp_b200_band_strip_width(const cvvdp_b200_ctx *ctx, int level);
+
 #ifdef __cplusplus
 }
 #endif

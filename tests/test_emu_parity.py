@@ -41,6 +41,23 @@ def test_identical_pair_is_exactly_10(mock_device):
     assert np.all(stats["Q_per_ch"] == 0)
 
 
+@pytest.mark.parametrize("shape,fps,heatmap", [((1, 150, 360), 0, None), ((1, 131, 250), 0, "raw"), ((5, 64, 236), 30, None)])
+def test_wide_strip_band_kernel_and_packed_temporal_kernel(shape, fps, heatmap, mock_device):
+    """Levels at least 232 pixels wide take the 116-column strip kernel (k_band3: several row segments,
+    a ragged last strip, the 20-row ring wrapping, the heat-map variant); clips whose planes are whole
+    64-pixel warp segments take the packed two-pixel temporal kernel.  Checked against the oracle."""
+    F, H, W = shape
+    tst, ref = synth.make_pair_u8(11, F, H, W)
+    m = cv.cvvdp(display_name="standard_fhd", heatmap=heatmap)
+    jod, stats = m.predict(tst, ref, frames_per_second=fps)
+    assert m._ctx.band_is_wide(0), "level 0 should use the wide-strip kernel"
+    jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd", heatmap=heatmap)
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], str(shape))
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
+    if heatmap:
+        assert np.max(np.abs(stats["heatmap"].float().numpy() - stats_o["heatmap"].astype(np.float32))) <= gu.HEATMAP_ATOL
+
+
 def test_frame_blocks_and_ranges_are_partition_independent(mock_device):
     """Blocking (gpu_mem limit -> 1..n frames per pass) and frame ranges must not change any value."""
     tst, ref = synth.make_pair_u8(4, 9, 36, 48)

@@ -46,8 +46,11 @@ def launches(src, dst):
             continue
         ms = float(val.replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1e-6)
         short = re.sub(r"\(.*", "", name)
-        if not short.startswith("cvvdp::"):
+        ours = short.startswith("cvvdp::") or re.match(r"(void )?k_[a-z0-9_]+", short)
+        if not ours:
             short = "other: " + short[:60]
+        else:
+            short = "cvvdp::" + re.sub(r"^(void )?(cvvdp::)?", "", short)
         a = agg.setdefault(short, [0, 0.0])
         a[0] += 1
         a[1] += ms
