@@ -214,11 +214,12 @@ int temporal_filters(const cvvdp_b200_params &P, double fps, cvvdp_b200_plan_inf
                 R[k] = exp(-(d * d) / (double)P.sigma_tf[3]);
             }
         }
-        for (int t = 0; t < N; ++t) {
+        for (int t = 0; t <= N / 2; ++t) {  // x[t] == x[N-t]: evaluate one half, mirror it (exactly symmetric taps)
             double x = R[0];
             for (int k = 1; k < No; ++k) x += 2.0 * R[k] * cos(2.0 * pi * k * t / (double)N);
             x /= (double)N;
             info->filters[c][(t + N / 2) % N] = (float)x;  // fftshift
+            info->filters[c][(N - t + N / 2) % N] = (float)x;
         }
     }
     return N;
@@ -423,9 +424,27 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         const bool lockstep = want_lockstep && npix % (64 * 12) == 0;
         dim3 grid_x12((unsigned)(npix / (64 * 12)), (unsigned)(B * 2));
         dim3 grid_x2((unsigned)((npix / 64 + CVVDP_TX2_THREADS / 32 - 1) / (CVVDP_TX2_THREADS / 32)), (unsigned)(B * 2));
+        // two-stage variant (rolled front end, unrolled FIR only): needs its dynamic shared memory
+        static const bool no_2s = getenv("CVVDP_B200_NO_T2S") != nullptr;  // A/B switch
+        const int t_esz = use_lut ? 1 : (int)dtype_size(job.dtype);
+        const size_t smem_2s = t2s_smem_bytes(info.filter_len, t_esz);
+        bool taps_symmetric = true;  // exact: the two-stage kernel adds mirrored frames before multiplying
+        for (int c = 0; c < 4; ++c)
+            for (int k = 0; k < info.filter_len / 2; ++k)
+                if (ta.taps[c][k] != ta.taps[c][info.filter_len - 1 - k]) taps_symmetric = false;
+        const bool two_stage = packed && !no_2s && info.filter_len >= 3 && taps_symmetric;
+        dim3 grid_2s((unsigned)((npix / 64 + CVVDP_T2S_THREADS / 32 - 1) / (CVVDP_T2S_THREADS / 32)), (unsigned)(B * 2));
 #define CVVDP_TEMPORAL_CASE(FLV)                                                              \
     case FLV: {                                                                               \
-        if (packed && use_lut && lockstep) {                                                  \
+        if (two_stage && use_lut) {                                                           \
+            auto kfn = k_temporal_2s<FLV, true>;                                              \
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2s); \
+            CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);             \
+        } else if (two_stage) {                                                               \
+            auto kfn = k_temporal_2s<FLV, false>;                                             \
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2s); \
+            CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);             \
+        } else if (packed && use_lut && lockstep) {                                           \
             auto kfn = k_temporal_x2<FLV, true, 12>;                                          \
             CVVDP_LAUNCH(kfn, grid_x12, dim3(12 * 32), 0, st, ta);                            \
         } else if (packed && use_lut) {                                                       \
@@ -823,10 +842,10 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         per_frame += align_up(B * tiles * 4 * sizeof(float), 256);
         if (do_hm) per_frame += align_up(npix * sizeof(float), 256);
     }
-    size_t limit = job->workspace_limit_bytes > 0 ? (size_t)job->workspace_limit_bytes : (size_t)40 << 30;
+    size_t limit = job->workspace_limit_bytes > 0 ? (size_t)job->workspace_limit_bytes : (size_t)64 << 30;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) limit = std::min(limit, free_b / 2);
-    int nb = (int)std::min<size_t>(std::max<size_t>(limit / std::max<size_t>(per_frame, 1), 1), 64);
+    int nb = (int)std::min<size_t>(std::max<size_t>(limit / std::max<size_t>(per_frame, 1), 1), 128);
     if (job->max_block_frames > 0) nb = std::min(nb, job->max_block_frames);
     nb = std::min(nb, job->n_frames);
     if ((long long)B * nb * 2 > 65535) nb = std::max(1, (int)(65535 / (B * 2)));
@@ -843,8 +862,11 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.do_blur = (ctx->blur_pad > 0 && lv.h > ctx->blur_pad && lv.w > ctx->blur_pad) ? 1 : 0;  // cvvdp_metric.py:965
         {   // strips of 116 columns (levels at least two such strips wide) or 52 columns; the rows are split
             // into segments only when there are too few CTAs
-            static const bool no_wide = getenv("CVVDP_B200_NO_WIDE") != nullptr;  // A/B switch
-            lv.wide = !no_wide && lv.do_blur && lv.w >= 2 * CVVDP_B3_SW && lv.h >= 32;
+            // k_band3 is opt-in: on B200 it measured 4 % slower than k_band2 at 4K (18.9 vs 18.2 ms per 120 frames
+            // on the same box; ncu: 3x the barrier stalls with 8-warp CTAs, +9 instructions per pixel of ring
+            // arithmetic) -- see DESIGN.md section 5.  Read at plan time.
+            const bool want_wide = getenv("CVVDP_B200_WIDE") != nullptr;
+            lv.wide = want_wide && lv.do_blur && lv.w >= 2 * CVVDP_B3_SW && lv.h >= 32;
             const int sw = lv.wide ? CVVDP_B3_SW : CVVDP_B2_SW;
             lv.tiles_x = (lv.w + sw - 1) / sw;
             // the split depends on the level geometry only, never on the batch or block size, so that

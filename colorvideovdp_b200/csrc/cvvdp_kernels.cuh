@@ -682,6 +682,215 @@ __global__ void __launch_bounds__(NWARPS * 32, NWARPS == 4 ? 3 : 1) k_temporal_x
     cp_async_wait_all();
 }
 
+// Two-stage variant of the packed kernel.  The fully unrolled time loop of k_temporal_x2 is ~60 KB of
+// straight-line code, twice the SM's 32 KB L1.5 instruction cache: ncu shows it waiting for instructions
+// 2.4 cycles per issue.  Here only the FIR is unrolled.  Time advances in chunks of G = (FL+1)/2 frames:
+//   stage 1 (a rolled loop, one copy of the code): raw values of the chunk (already in shared memory,
+//            copied with cp.async during the previous chunk) -> EOTF -> DKL -> a per-thread slab of
+//            shared memory (each thread reads back only what it wrote: no synchronisation);
+//   stage 2 (unrolled over one ring period = two chunks): 3 LDS.64 bring a frame into its static ring
+//            slot, 4*FL FFMA2, two 128-bit stores.
+// The unrolled part shrinks to ~25 KB, the front end (including the generic per-pixel EOTF switch of
+// the non-table variant) exists once, and the warps of a CTA never synchronise with each other.
+// Same requirements and the same per-lane arithmetic as k_temporal_x2.
+// One byte from shared memory straight into a 32-bit register (the compiler otherwise packs pairs of
+// 8-bit loads into 16-bit halves and unpacks them again).
+__device__ __forceinline__ unsigned lds_u8(const unsigned char *p) {
+#ifdef __CUDA_ARCH__
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+}
+// Two pixels (a, b) -> DKL, as the halves of fp32x2 values.  Per lane the same operations in the same
+// order as bits_to_dkl (v1*M1, then fma with v0*M0, then fma with v2*M2), two lanes per instruction.
+template <bool USE_LUT>
+__device__ __forceinline__ void bits_to_dkl2(const TemporalArgs &a, const float *lut, const unsigned ba[3], const unsigned bb[3],
+                                             float2 &d0, float2 &d1, float2 &d2) {
+    float va[3], vb[3];
+    if (USE_LUT) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            va[i] = lut[ba[i]];
+            vb[i] = lut[bb[i]];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            switch (a.dtype) {
+                case CVVDP_DTYPE_U8: va[i] = (float)ba[i] / 255.0f; vb[i] = (float)bb[i] / 255.0f; break;
+                case CVVDP_DTYPE_U16: va[i] = (float)ba[i] * (1.0f / 65535.0f); vb[i] = (float)bb[i] * (1.0f / 65535.0f); break;
+                case CVVDP_DTYPE_F16: va[i] = half_bits_to_float((unsigned short)ba[i]); vb[i] = half_bits_to_float((unsigned short)bb[i]); break;
+                default: va[i] = bits_as_float(ba[i]); vb[i] = bits_as_float(bb[i]);
+            }
+        }
+        eotf_forward(va, a.cin, a.dd);
+        eotf_forward(vb, a.cin, a.dd);
+    }
+    if (a.cin == 3) {
+        const float2 v0 = make_float2(va[0], vb[0]), v1 = make_float2(va[1], vb[1]), v2 = make_float2(va[2], vb[2]);
+        d0 = fma2(v2, bc2(a.dd.M[2]), fma2(v0, bc2(a.dd.M[0]), mul2(v1, bc2(a.dd.M[1]))));
+        d1 = fma2(v2, bc2(a.dd.M[5]), fma2(v0, bc2(a.dd.M[3]), mul2(v1, bc2(a.dd.M[4]))));
+        d2 = fma2(v2, bc2(a.dd.M[8]), fma2(v0, bc2(a.dd.M[6]), mul2(v1, bc2(a.dd.M[7]))));
+    } else {
+        d0 = d1 = d2 = make_float2(va[0], vb[0]);
+    }
+}
+
+#define CVVDP_T2S_THREADS 128
+template <int FL>
+struct T2SGeom {
+    static constexpr int RP = FL + 1;   // ring period (even)
+    static constexpr int G = RP / 2;    // frames per chunk
+};
+// dynamic shared memory: [warps][G][3][64*esz] raw bytes, then [G][3][threads] float2
+__host__ __device__ inline size_t t2s_smem_bytes(int fl, int esz) {
+    const int G = (fl + 1) / 2;
+    return (size_t)(CVVDP_T2S_THREADS / 32) * G * 3 * 64 * esz + (size_t)G * 3 * CVVDP_T2S_THREADS * 8;
+}
+template <int FL, bool USE_LUT>
+__global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __grid_constant__ TemporalArgs a) {
+    constexpr int RP = T2SGeom<FL>::RP, G = T2SGeom<FL>::G;
+    __shared__ float s_lut[256];
+    CVVDP_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (USE_LUT) {
+        for (int i = tid; i < 256; i += CVVDP_T2S_THREADS) {
+            float v[1] = {(float)i / 255.0f};
+            eotf_forward(v, 1, a.dd);
+            s_lut[i] = v[0];
+        }
+        __syncthreads();
+    }
+    const long long npix = (long long)a.H * a.W;
+    const long long wp = ((long long)blockIdx.x * (CVVDP_T2S_THREADS / 32) + warp) * 64;  // first pixel of the warp
+    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
+    if (wp >= npix) return;  // whole 64-pixel segments only (npix % 64 == 0); no block-level barrier below
+    const ClipView &cv = a.clip[v];
+    const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
+    const int row_bytes = 64 * esz;          // one (channel, frame) segment of this warp
+    const int frame_bytes = 3 * row_bytes;   // slot of one frame in the raw stage (cin == 1 uses the first third)
+    const int cpc = row_bytes / 16;          // 16-byte pieces per channel segment
+    const int ppf = a.cin * cpc;             // pieces per frame
+    unsigned char *raw = smem_raw + (size_t)warp * G * frame_bytes;
+    float2 *dkl = reinterpret_cast<float2 *>(smem_raw + (size_t)(CVVDP_T2S_THREADS / 32) * G * frame_bytes) + tid;
+    const long long fstride = cv.s[2] * esz, cstride = cv.s[1] * esz;
+    const unsigned char *wsrc = (const unsigned char *)cv.data + (b * cv.s[0] + wp) * esz;
+    const int n = a.f1 - a.f0;
+    const int NI = (FL - 1) + n;  // iterations: FL-1 warm-up frames (temporal padding before frame 0), then the block
+    float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + wp + lane;
+    const long long ostep = 2 * npix;
+    float2 r0[RP], r1[RP], r2[RP];
+#pragma unroll
+    for (int i = 0; i < RP; ++i) r0[i] = r1[i] = r2[i] = make_float2(0.f, 0.f);
+
+    // cp.async copies of chunk `c` (iterations c*G .. c*G+G-1) into the raw stage; issued as soon as the
+    // previous chunk is converted, so they land while the FIR of that chunk runs.  Piece p = lane + 32 r of
+    // a chunk is (frame g, channel, 16-byte part); (g, rem) advance incrementally from round to round.
+    const int q32 = 32 / ppf, r32 = 32 - q32 * ppf;  // 32 = q32 * ppf + r32
+    const int g_first = lane / ppf, rem_first = lane - g_first * ppf;
+    const int cpc_shift = esz == 1 ? 2 : (esz == 2 ? 3 : 4);
+    auto issue_chunk = [&](int c) {
+        int g = g_first, rem = rem_first;
+        const int it0 = c * G;
+        while (g < G) {
+            const int it = it0 + g;
+            if (it < NI) {
+                const int t = a.f0 - (FL - 1) + it;
+                const int slot = frame_slot(cv, t >= 0 ? t : temporal_source_frame(a, t));
+                const int ch = rem >> cpc_shift, part = rem & (cpc - 1);
+                cp_async16(raw + g * frame_bytes + ch * row_bytes + part * 16, wsrc + (long long)slot * fstride + ch * cstride + part * 16);
+            }
+            g += q32;
+            rem += r32;
+            if (rem >= ppf) {
+                rem -= ppf;
+                ++g;
+            }
+        }
+        cp_async_commit();
+    };
+    // stage 1: raw -> DKL for the G frames of the chunk in the raw stage (rolled; three frames in flight)
+    auto convert_chunk = [&]() {
+#pragma unroll 3
+        for (int g = 0; g < G; ++g) {
+            const unsigned char *q = raw + g * frame_bytes;
+            unsigned ba[3], bb[3];
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const unsigned char *qc = q + (a.cin == 3 ? ch : 0) * row_bytes;
+                if (esz == 1) {
+                    ba[ch] = lds_u8(qc + lane);
+                    bb[ch] = lds_u8(qc + lane + 32);
+                } else if (esz == 2) {
+                    ba[ch] = ((const unsigned short *)qc)[lane];
+                    bb[ch] = ((const unsigned short *)qc)[lane + 32];
+                } else {
+                    ba[ch] = ((const unsigned *)qc)[lane];
+                    bb[ch] = ((const unsigned *)qc)[lane + 32];
+                }
+            }
+            float2 d0, d1, d2;
+            bits_to_dkl2<USE_LUT>(a, s_lut, ba, bb, d0, d1, d2);
+            dkl[(g * 3 + 0) * CVVDP_T2S_THREADS] = d0;
+            dkl[(g * 3 + 1) * CVVDP_T2S_THREADS] = d1;
+            dkl[(g * 3 + 2) * CVVDP_T2S_THREADS] = d2;
+        }
+    };
+    issue_chunk(0);
+    int it = 0;
+    for (int c = 0; it < NI; c += 2) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {  // the two chunks of one ring period
+            cp_async_wait_all();
+            __syncwarp();          // the chunk's raw values (copied by all lanes) are visible
+            convert_chunk();
+            __syncwarp();          // every lane is done with the raw stage before it is refilled
+            issue_chunk(c + h + 1);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int s = h * G + g;  // static ring slot: it % RP
+                if (it < NI) {            // uniform
+                    r0[s] = dkl[(g * 3 + 0) * CVVDP_T2S_THREADS];
+                    r1[s] = dkl[(g * 3 + 1) * CVVDP_T2S_THREADS];
+                    r2[s] = dkl[(g * 3 + 2) * CVVDP_T2S_THREADS];
+                    if (it >= FL - 1) {   // uniform
+                        // the filters are exactly symmetric (the host checks, else k_temporal_x2 runs): frames at
+                        // mirrored taps are added first, which also lets A-sust and A-trans share the sums
+                        // (splitting each sum into two chains for more ILP was tried: +29 instructions per pixel of
+                        // rematerialised addresses under register pressure, 13 % slower)
+                        float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+#pragma unroll
+                        for (int k = 0; k < FL / 2; ++k) {  // tap k <-> frame t-(FL-1)+k <-> slot (s-(FL-1)+k) mod RP
+                            const int sa = (s + RP - (FL - 1) + k) % RP, sb = (s + RP - k) % RP;
+                            const float2 p0 = add2(r0[sa], r0[sb]), p1 = add2(r1[sa], r1[sb]), p2 = add2(r2[sa], r2[sb]);
+                            o0 = fma2(bc2(a.taps[0][k]), p0, o0);
+                            o1 = fma2(bc2(a.taps[1][k]), p1, o1);
+                            o2 = fma2(bc2(a.taps[2][k]), p2, o2);
+                            o3 = fma2(bc2(a.taps[3][k]), p0, o3);
+                        }
+                        {
+                            constexpr int k = FL / 2;
+                            const int sl = (s + RP - (FL - 1) + k) % RP;
+                            o0 = fma2(bc2(a.taps[0][k]), r0[sl], o0);
+                            o1 = fma2(bc2(a.taps[1][k]), r1[sl], o1);
+                            o2 = fma2(bc2(a.taps[2][k]), r2[sl], o2);
+                            o3 = fma2(bc2(a.taps[3][k]), r0[sl], o3);
+                        }
+                        outp[0] = make_float4(o0.x, o1.x, o2.x, o3.x);
+                        outp[32] = make_float4(o0.y, o1.y, o2.y, o3.y);
+                        outp += ostep;
+                    }
+                }
+                ++it;
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
 // =================================================================================================
 // Gaussian pyramid reduce  (lpyr_dec.py:186-211): zero-padded 5-tap stride-2 passes (rows, then
 // columns) with the reference's edge fix-ups, including the parity quirk at line 206 (the ROW count

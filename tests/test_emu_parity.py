@@ -42,15 +42,21 @@ def test_identical_pair_is_exactly_10(mock_device):
 
 
 @pytest.mark.parametrize("shape,fps,heatmap", [((1, 150, 360), 0, None), ((1, 131, 250), 0, "raw"), ((5, 64, 236), 30, None)])
-def test_wide_strip_band_kernel_and_packed_temporal_kernel(shape, fps, heatmap, mock_device):
-    """Levels at least 232 pixels wide take the 116-column strip kernel (k_band3: several row segments,
-    a ragged last strip, the 20-row ring wrapping, the heat-map variant); clips whose planes are whole
-    64-pixel warp segments take the packed two-pixel temporal kernel.  Checked against the oracle."""
+@pytest.mark.parametrize("wide", [False, True])
+def test_band_kernel_variants_and_packed_temporal_kernel(shape, fps, heatmap, wide, mock_device, monkeypatch):
+    """Both band kernels on levels at least 232 pixels wide: the default 52-column strip kernel and the
+    opt-in 116-column one (CVVDP_B200_WIDE: several row segments, a ragged last strip, the 20-row ring
+    wrapping, the heat-map variant); clips whose planes are whole 64-pixel warp segments take the packed
+    two-stage temporal kernel.  Checked against the oracle."""
     F, H, W = shape
     tst, ref = synth.make_pair_u8(11, F, H, W)
+    if wide:
+        monkeypatch.setenv("CVVDP_B200_WIDE", "1")
+    else:
+        monkeypatch.delenv("CVVDP_B200_WIDE", raising=False)
     m = cv.cvvdp(display_name="standard_fhd", heatmap=heatmap)
     jod, stats = m.predict(tst, ref, frames_per_second=fps)
-    assert m._ctx.band_is_wide(0), "level 0 should use the wide-strip kernel"
+    assert m._ctx.band_is_wide(0) == wide
     jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd", heatmap=heatmap)
     gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], str(shape))
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
