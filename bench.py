@@ -297,12 +297,27 @@ def main():
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         do_e2e = bool(flag.item())
     if do_e2e:
-        tst_h = torch.empty(tst.shape, dtype=tst.dtype, pin_memory=True).copy_(tst)
-        ref_h = torch.empty(ref.shape, dtype=ref.dtype, pin_memory=True).copy_(ref)
+        # Host-side data placement of the sharded job.  Short shards (history window >= 1.5x the shard, i.e. 4 or
+        # more ranks at 60 fps): every rank's host memory holds only the frames it owns and the fl-1 history frames
+        # come from their owners over NVLink (NCCL send/recv) -- each byte crosses PCIe once.  Long shards: the
+        # history is small next to the shard, so the rank uploads its whole window through the streaming C-ABI
+        # path, which overlaps the upload with compute (measured at N=2: 160 ms streamed vs 171 ms exchanged).
+        exchange = world > 1 and (whi - wlo) >= 1.5 * (hi - lo)
+        if exchange:
+            own_t, own_r = tst[:, :, lo - wlo:hi - wlo], ref[:, :, lo - wlo:hi - wlo]
+            tst_h = torch.empty(own_t.shape, dtype=tst.dtype, pin_memory=True).copy_(own_t)
+            ref_h = torch.empty(own_r.shape, dtype=ref.dtype, pin_memory=True).copy_(own_r)
 
-        def step_host():
-            jod_h, Qd = D.predict_frame_sharded(metric, tst_h, ref_h, wlo, F, fps)
-            return jod_h.cpu()  # D2H of the result
+            def step_host():
+                jod_h, Qd = D.predict_frame_sharded_exchange(metric, tst_h, ref_h, F, fps)
+                return jod_h.cpu()  # D2H of the result
+        else:
+            tst_h = torch.empty(tst.shape, dtype=tst.dtype, pin_memory=True).copy_(tst)
+            ref_h = torch.empty(ref.shape, dtype=ref.dtype, pin_memory=True).copy_(ref)
+
+            def step_host():
+                jod_h, Qd = D.predict_frame_sharded(metric, tst_h, ref_h, wlo, F, fps)
+                return jod_h.cpu()  # D2H of the result
 
         ms_e2e, jod_h = timed(step_host, max(2, min(args.steps, 3)), 1)
         assert torch.equal(jod_h, jod.cpu()), "host and device arms disagree"
@@ -311,7 +326,10 @@ def main():
         e2e = {"value": round(pix_per_step / 1e6 / (ms_e2e / 1e3), 2), "unit": "Mpix/s",
                "ms_per_step": round(ms_e2e, 3),
                "h2d_bytes_per_step": int(n * (tst_h.numel() * tst_h.element_size() + ref_h.numel() * ref_h.element_size())),
-               "d2h_bytes_per_step": int(q_bytes + 4 * n)}
+               "d2h_bytes_per_step": int(q_bytes + 4 * n),
+               "input": ("every rank's pinned host memory holds the frames it owns (uploaded once); the fl-1 history "
+                         "frames of a shard arrive from their owners by NCCL send/recv over NVLink") if exchange else
+                        "pinned host clips streamed through cvvdp_b200_process_host (upload overlapped with compute)"}
         del tst_h, ref_h
 
     if rank != 0:

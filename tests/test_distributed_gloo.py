@@ -8,6 +8,9 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from emu_util import mock_device  # noqa: E402,F401
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.abspath(os.path.join(HERE, ".."))
 
@@ -32,7 +35,11 @@ def _worker(rank, world, port, out_dir):
     wlo, whi = D.needed_window(m, F, fps, lo, hi)
     tw, rw = torch.from_numpy(tb[:, :, wlo:whi].copy()), torch.from_numpy(ref[:, :, wlo:whi].copy())
     jod, Q = D.predict_frame_sharded(m, tw, rw, wlo, F, fps)
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), jod=jod.numpy(), Q=Q.numpy(), shard=np.asarray([lo, hi, wlo, whi]))
+    # same shard, but every rank holds only its own frames: history frames come from their owners
+    to, ro = torch.from_numpy(tb[:, :, lo:hi].copy()), torch.from_numpy(ref[:, :, lo:hi].copy())
+    jod_x, Q_x = D.predict_frame_sharded_exchange(m, to, ro, F, fps)
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), jod=jod.numpy(), Q=Q.numpy(), shard=np.asarray([lo, hi, wlo, whi]),
+             jod_x=jod_x.numpy(), Q_x=Q_x.numpy())
     if rank == 0:
         j_full, s_full = m.predict(tb, ref, frames_per_second=fps)
         np.savez(os.path.join(out_dir, "full.npz"), jod=j_full.numpy(), Q=s_full["Q_per_ch"])
@@ -48,6 +55,28 @@ def test_frame_sharding_world2_gloo(tmp_path):
     assert np.array_equal(r0["Q"], r1["Q"]) and np.array_equal(r0["jod"], r1["jod"])
     assert np.array_equal(r0["Q"], full["Q"])  # sharded == single process, bit for bit
     assert np.array_equal(r0["jod"], full["jod"])
+    # halo exchange instead of double upload: identical bits again
+    assert np.array_equal(r0["Q_x"], full["Q"]) and np.array_equal(r1["Q_x"], full["Q"])
+    assert np.array_equal(r0["jod_x"], full["jod"]) and np.array_equal(r1["jod_x"], full["jod"])
+
+
+def test_exchange_plan_covers_every_window(mock_device):
+    """Every frame a rank needs and does not own is delivered exactly once, by its owner."""
+    import colorvideovdp_b200 as cv
+    from colorvideovdp_b200 import distributed as D
+    for padding in ("replicate", "symmetric"):
+        m = cv.cvvdp(display_name="standard_fhd", temp_padding=padding)
+        for F, fps, world in ((120, 60, 8), (9, 30, 2), (20, 60, 4), (7, 24, 3)):
+            shards, windows, transfers = D.exchange_plan(m, F, fps, world)
+            for r, ((lo, hi), (wlo, whi)) in enumerate(zip(shards, windows)):
+                have = set(range(lo, hi))
+                for src, dst, flo, fhi in transfers:
+                    if dst == r:
+                        assert shards[src][0] <= flo and fhi <= shards[src][1]
+                        got = set(range(flo, fhi))
+                        assert not (got & have)
+                        have |= got
+                assert have == set(range(wlo, whi)), (padding, F, fps, world, r)
 
 
 def test_frame_shard_partition():
