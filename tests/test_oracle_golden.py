@@ -110,3 +110,12 @@ def test_oracle_yuv_ingestion(name, tmp_path):
     jod, stats = O.predict_yuv(tf, rf, meta["display"], meta["padding"])
     gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
     assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+
+
+@pytest.mark.parametrize("name", gu.feature_case_names())
+def test_oracle_features_match_reference(name):
+    """per-band patch statistics of |T|S, |R|S, D (cvvdp_ml_metric.py:78-106, 302-352) against
+    tensors produced by the reference's own cvvdp_ml_base.extract_features."""
+    z, meta = gu.load_case(name)
+    _, stats = O.predict(z["test"], z["ref"], meta["dim_order"], meta["fps"], meta["display"], meta["padding"], features=True)
+    gu.assert_features_close(stats["features"], z, name)
