@@ -49,7 +49,7 @@ class Job(C.Structure):
     _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("n_frames", C.c_int32),
                 ("fps", C.c_float), ("in_channels", C.c_int32), ("dtype", C.c_int32), ("padding", C.c_int32),
                 ("heatmap", C.c_int32), ("max_block_frames", C.c_int32), ("workspace_limit_bytes", C.c_int64),
-                ("yuv", Yuv)]
+                ("yuv", Yuv), ("features", C.c_int32)]
 
 
 class PlanInfo(C.Structure):
@@ -84,6 +84,9 @@ SYMBOLS = {
                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_launch_count": (C.c_int64, [C.c_void_p]),
     "cvvdp_b200_band_strip_width": (C.c_int, [C.c_void_p, C.c_int]),
+    "cvvdp_b200_feature_layout": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
+    "cvvdp_b200_set_feature_output": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cvvdp_b200_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "cvvdp_b200_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
 }
@@ -95,7 +98,7 @@ class KernelStat(C.Structure):
     _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("launches", C.c_int32), ("total_ms", C.c_float),
                 ("algo_bytes", C.c_double)]
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class NativeError(RuntimeError):
@@ -187,6 +190,16 @@ class Context:
 
     def launch_count(self):
         return int(self._lib.cvvdp_b200_launch_count(self._h))
+
+    def feature_layout(self, band):
+        """(ph, pw, feature_size, float offset) of the feature tensor of `band` (band == n_bands: total floats)."""
+        ph, pw, fs, off = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        self._check(self._lib.cvvdp_b200_feature_layout(self._h, int(band), C.byref(ph), C.byref(pw), C.byref(fs),
+                                                        C.byref(off)), "feature_layout")
+        return ph.value, pw.value, fs.value, off.value
+
+    def set_feature_output(self, ptr):
+        self._check(self._lib.cvvdp_b200_set_feature_output(self._h, ptr), "set_feature_output")
 
     def band_is_wide(self, level):
         return int(self._lib.cvvdp_b200_band_strip_width(self._h, int(level))) == 116

@@ -23,6 +23,9 @@ struct LevelBuf {
     float4 *g = nullptr;        // [B*nb*2][h*w]
     float *partials = nullptr;  // [B*nb][tiles][4]
     float *hm = nullptr;        // [nb][h*w] (heat map only)
+    float4 *feat = nullptr;     // [3][B*nb][h*w] (feature mode only): |T|S, |R|S, D
+    int ph = 0, pw = 0;         // feature patches of this band
+    long long feat_off = 0;     // float offset of this band's tensor in the caller's feature buffer
     float4 *lut = nullptr;      // [32]
     int tiles_x = 0, tiles_y = 0;  // band kernel grid: column strips x row segments
     int seg_rows = 0;
@@ -59,6 +62,9 @@ struct cvvdp_b200_ctx {
     int num_sms = 148;
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;
     Staging stage[2];
+    float *feat_out = nullptr;    // caller's device buffer for the feature tensors (feature mode)
+    int feature_size = 0;         // ceil(ppd)
+    long long feat_total = 0;     // floats in the feature buffer
     float *q_dev = nullptr;       // for process_host / pool
     size_t q_dev_bytes = 0;
     void *hm_dev = nullptr;
@@ -365,6 +371,7 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
     const int n = f1 - f0, L = info.n_bands, B = job.batch;
     const int pairs = B * n;
     const bool do_hm = job.heatmap == CVVDP_HEATMAP_RAW;
+    const bool do_feat = job.features != 0 && ctx->feat_out != nullptr;
     const float eps = 1e-5f;
 
     // ---- temporal stage ----
@@ -531,6 +538,12 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ba.lut = lv.lut;
         ba.partials = lv.partials;
         ba.hm = do_hm ? lv.hm : nullptr;
+        ba.feat = do_feat ? lv.feat : nullptr;
+        ba.feat_plane = (long long)pairs * lv.h * lv.w;
+        {
+            const float gain[4] = {1.f, 1.45f, 1.f, 1.f};  // the CSF rows carry the masking gain (plan), the features do not
+            for (int c = 0; c < 4; ++c) ba.inv_gain[c] = 1.f / gain[c];
+        }
         ba.h = lv.h;
         ba.w = lv.w;
         ba.hc = ctx->lv[i + 1].h;
@@ -565,6 +578,16 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         LaunchScope ls(ctx, st, CVVDP_K_BAND, i,
                        (double)pairs * 2 * 16.0 * ((double)ba.h * ba.w + (double)ba.hc * ba.wc) +
                            (do_hm ? (double)pairs * 4.0 * ba.h * ba.w : 0.0));
+        if (do_feat) {  // feature mode: the narrow-strip kernel with the three extra planes
+            const int vf = (ba.do_blur ? 4 : 0) | (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
+            void (*kf[8])(const BandArgs) = {k_band2<false, false, false, true>, k_band2<false, false, true, true>,
+                                             k_band2<false, true, false, true>,  k_band2<false, true, true, true>,
+                                             k_band2<true, false, false, true>,  k_band2<true, false, true, true>,
+                                             k_band2<true, true, false, true>,   k_band2<true, true, true, true>};
+            auto kfn = kf[vf];
+            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Band2Smem), st, ba);
+            continue;
+        }
         if (lv.wide) {
             const int v3 = (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
             void (*k3[4])(const BandArgs) = {k_band3<false, false>, k_band3<false, true>, k_band3<true, false>, k_band3<true, true>};
@@ -598,6 +621,7 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         bb.lut = lv.lut;
         bb.partials = lv.partials;
         bb.hm = do_hm ? lv.hm : nullptr;
+        bb.feat = do_feat ? lv.feat : nullptr;
         bb.npix = lv.h * lv.w;
         const float x0 = log10f(ctx->lut.L_bkg[0]), x1 = log10f(ctx->lut.L_bkg[CVVDP_CSF_LUT_N - 1]);
         const double sc = (double)(CVVDP_CSF_LUT_N - 1) / ((double)x1 - (double)x0);
@@ -635,6 +659,28 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         for (int i = 0; i < L; ++i) pbytes += (double)pairs * fa.ntiles[i] * 16.0;
         LaunchScope ls(ctx, st, CVVDP_K_FINALIZE, 0, pbytes);
         CVVDP_LAUNCH(kfn, dim3((warps * 32 + 127) / 128), dim3(128), 0, st, fa);
+    }
+    // ---- feature pooling (cvvdp_ml_metric.py:78-106) ----
+    if (do_feat) {
+        for (int i = 0; i < L; ++i) {
+            const LevelBuf &lv = ctx->lv[i];
+            FeaturePoolArgs fp;
+            fp.feat = lv.feat;
+            fp.feat_plane = (long long)pairs * lv.h * lv.w;
+            fp.out = ctx->feat_out + lv.feat_off;
+            fp.h = lv.h;
+            fp.w = lv.w;
+            fp.ps = ctx->feature_size;
+            fp.ph = lv.ph;
+            fp.pw = lv.pw;
+            fp.C = info.n_channels;
+            fp.n = n;
+            fp.f_off = f0;
+            fp.F_total = job.n_frames;
+            auto kfn = k_feature_pool;
+            LaunchScope ls(ctx, st, CVVDP_K_FEATURES, i, (double)pairs * 3 * 16.0 * lv.h * lv.w);
+            CVVDP_LAUNCH(kfn, dim3(lv.pw, lv.ph, pairs), dim3(128), 0, st, fp);
+        }
     }
     // ---- heat map ----
     if (do_hm) {
@@ -841,6 +887,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
                                                 (info.band_height[i] / 16 + 1);  // upper bound
         per_frame += align_up(B * tiles * 4 * sizeof(float), 256);
         if (do_hm) per_frame += align_up(npix * sizeof(float), 256);
+        if (job->features) per_frame += align_up(3 * B * npix * sizeof(float4), 256);
     }
     size_t limit = job->workspace_limit_bytes > 0 ? (size_t)job->workspace_limit_bytes : (size_t)64 << 30;
     size_t free_b = 0, total_b = 0;
@@ -854,7 +901,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     // arena layout
     ctx->lv.resize(L);
     size_t off = 0;
-    std::vector<size_t> off_g(L), off_p(L), off_h(L), off_l(L);
+    std::vector<size_t> off_g(L), off_p(L), off_h(L), off_l(L), off_f(L);
     for (int i = 0; i < L; ++i) {
         LevelBuf &lv = ctx->lv[i];
         lv.h = info.band_height[i];
@@ -866,7 +913,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
             // on the same box; ncu: 3x the barrier stalls with 8-warp CTAs, +9 instructions per pixel of ring
             // arithmetic) -- see DESIGN.md section 5.  Read at plan time.
             const bool want_wide = getenv("CVVDP_B200_WIDE") != nullptr;
-            lv.wide = want_wide && lv.do_blur && lv.w >= 2 * CVVDP_B3_SW && lv.h >= 32;
+            lv.wide = want_wide && !job->features && lv.do_blur && lv.w >= 2 * CVVDP_B3_SW && lv.h >= 32;
             const int sw = lv.wide ? CVVDP_B3_SW : CVVDP_B2_SW;
             lv.tiles_x = (lv.w + sw - 1) / sw;
             // the split depends on the level geometry only, never on the batch or block size, so that
@@ -884,8 +931,24 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         off += align_up(B * nb * tiles * 4 * sizeof(float), 256);
         off_h[i] = off;
         if (do_hm) off += align_up((size_t)nb * npix * sizeof(float), 256);
+        off_f[i] = off;
+        if (job->features) off += align_up(3 * B * nb * npix * sizeof(float4), 256);
         off_l[i] = off;
         off += align_up(CVVDP_CSF_LUT_N * sizeof(float4), 256);
+    }
+    {   // feature tensors: [B][F][ph][pw][C][6] per band, band after band (cvvdp_ml_metric.py:349-352)
+        ctx->feature_size = (int)ceil((double)ctx->disp.ppd);
+        long long foff = 0;
+        for (int i = 0; i < L; ++i) {
+            LevelBuf &lv = ctx->lv[i];
+            const int ps = std::max(ctx->feature_size, 1);
+            lv.ph = (lv.h + ps - 1) / ps;
+            lv.pw = (lv.w + ps - 1) / ps;
+            lv.feat_off = foff;
+            foff += (long long)B * job->n_frames * lv.ph * lv.pw * info.n_channels * 6;
+        }
+        ctx->feat_total = foff;
+        ctx->feat_out = nullptr;  // a new plan invalidates the registered buffer
     }
     ctx->arena_bytes = off;
     info.workspace_bytes = (int64_t)off;
@@ -906,6 +969,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.g = (float4 *)(base + off_g[i]);
         lv.partials = (float *)(base + off_p[i]);
         lv.hm = do_hm ? (float *)(base + off_h[i]) : nullptr;
+        lv.feat = job->features ? (float4 *)(base + off_f[i]) : nullptr;
         lv.lut = (float4 *)(base + off_l[i]);
         lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_EW, CVVDP_B2_RB) &&
                    make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_CC, CVVDP_B2_CR) &&
@@ -1269,6 +1333,32 @@ int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, con
 }
 
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int cvvdp_b200_feature_layout(const cvvdp_b200_ctx *ctx, int band, int32_t *ph, int32_t *pw, int32_t *feature_size,
+                              int64_t *float_offset) {
+    if (!ctx || !ctx->planned) return CVVDP_ERR_STATE;
+    const int L = (int)ctx->lv.size();
+    if (band < 0 || band > L) return CVVDP_ERR_INVALID;
+    if (feature_size) *feature_size = ctx->feature_size;
+    if (band == L) {
+        if (ph) *ph = 0;
+        if (pw) *pw = 0;
+        if (float_offset) *float_offset = ctx->feat_total;
+        return CVVDP_OK;
+    }
+    if (ph) *ph = ctx->lv[band].ph;
+    if (pw) *pw = ctx->lv[band].pw;
+    if (float_offset) *float_offset = ctx->lv[band].feat_off;
+    return CVVDP_OK;
+}
+
+int cvvdp_b200_set_feature_output(cvvdp_b200_ctx *ctx, float *features_dev) {
+    if (!ctx || !ctx->planned) return CVVDP_ERR_STATE;
+    if (features_dev && !ctx->job.features)
+        return fail(ctx, CVVDP_ERR_STATE, "the current plan was made without job.features");
+    ctx->feat_out = features_dev;
+    return CVVDP_OK;
+}
 
 int cvvdp_b200_band_strip_width(const cvvdp_b200_ctx *ctx, int level) {
     if (!ctx || !ctx->planned || level < 0 || level + 1 >= (int)ctx->lv.size()) return 0;

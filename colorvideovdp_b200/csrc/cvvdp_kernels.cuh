@@ -1109,6 +1109,9 @@ struct BandArgs {
     const float4 *lut;     // [32] per-level CSF rows of the 4 channels, pre-scaled: row*log2(10)+log2(sens*gain)
     float *partials;       // [pairs][tiles][4]
     float *hm;             // [pairs][h*w] per-band heat-map plane or null
+    float4 *feat;          // feature mode: [3][pairs][h*w] planes |T|S, |R|S, D, or null
+    long long feat_plane;  // float4 elements between two of those three plane sets (pairs * h * w)
+    float inv_gain[4];     // 1 / masking gain: the CSF rows carry the gain, the features do not (cvvdp_ml_metric.py:352)
     int h, w, hc, wc;
     int do_blur;
     float mul;             // get_band: 1 for band 0, 2 for middle bands (lpyr_dec.py:60-66)
@@ -1146,8 +1149,9 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' p
 }
 
 // Contrast / CSF / mutual-masking inputs of one pixel (phase 1).
+template <bool FEAT = false>
 __device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lut, float4 gt, float4 gr, float4 et,
-                                           float4 er, float4 &mm, float4 &df) {
+                                           float4 er, float4 &mm, float4 &df, float4 *feat_t = nullptr, float4 *feat_r = nullptr) {
     const float4 lt = gt - et, lr = gr - er;  // Laplacian (lpyr_dec.py:387)
     const float Lt = fmaxf(et.x, 0.01f), Lr = fmaxf(er.x, 0.01f);  // l.394
     const float it = a.mul * f_rcp(Lt), ir = a.mul * f_rcp(Lr);
@@ -1171,6 +1175,10 @@ __device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lu
                      fminf(fabsf(T23.x), fabsf(R23.x)), fminf(fabsf(T23.y), fabsf(R23.y)));
     const float2 d01 = add2(T01, make_float2(-R01.x, -R01.y)), d23 = add2(T23, make_float2(-R23.x, -R23.y));
     df = make_float4(fabsf(d01.x), fabsf(d01.y), fabsf(d23.x), fabsf(d23.y));
+    if (FEAT) {  // |T_f| S and |R_f| S without the masking gain
+        *feat_t = make_float4(fabsf(T01.x) * a.inv_gain[0], fabsf(T01.y) * a.inv_gain[1], fabsf(T23.x) * a.inv_gain[2], fabsf(T23.y) * a.inv_gain[3]);
+        *feat_r = make_float4(fabsf(R01.x) * a.inv_gain[0], fabsf(R01.y) * a.inv_gain[1], fabsf(R23.x) * a.inv_gain[2], fabsf(R23.y) * a.inv_gain[3]);
+    }
 }
 
 __device__ __forceinline__ float spow_fast(float x, float p, float eps, float eps_p) {
@@ -1449,7 +1457,9 @@ __device__ __forceinline__ void band2_stage(const BandArgs &a, Band2Smem &sm, co
 // The per-pixel bodies of phases A and C are straight-line code (no per-pixel branches): rows and
 // columns outside the segment are computed on whatever the stage holds and discarded by a select, so
 // the compiler can interleave the MUFU chains of a thread's four pixels.
-template <bool BLUR, bool HM, bool BETA2>
+// FEAT = feature mode: additionally write |T|S, |R|S (phase A) and D (phase C) of every pixel of the segment's
+// interior to three planes that k_feature_pool turns into the per-patch statistics of the ML heads.
+template <bool BLUR, bool HM, bool BETA2, bool FEAT = false>
 __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_constant__ BandArgs a) {
     CVVDP_DYN_SMEM(smem_raw);
     Band2Smem &sm = *reinterpret_cast<Band2Smem *>(smem_raw);
@@ -1530,11 +1540,11 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                 }
                 // pixels beyond the image / segment are evaluated on the stage's fill values and never read back
                 // (phase B reflects at the borders, phase C selects); their df slot belongs to rows long consumed
-                float4 mm[4], df[4];
+                float4 mm[4], df[4], ft[4], fr[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
-                    band_pixel(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm[k], df[k]);
+                    band_pixel<FEAT>(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm[k], df[k], &ft[k], &fr[k]);
                 }
                 const int ix = ex0 + 2 * qx - x0;  // even; the pair (ix, ix+1) is inside or outside the strip together
                 const bool in_strip = ix >= 0 && ix < CVVDP_B2_SW;
@@ -1543,6 +1553,14 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                     const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
                     sm.mm[ry][rx] = mm[k];
                     if (in_strip) sm.df[(a0 + ry) & (CVVDP_B2_DFR - 1)][ix + (k & 1)] = df[k];
+                    if (FEAT) {  // every pixel belongs to the interior of exactly one (strip, segment)
+                        const int py = a0 + ry, px = ex0 + rx;
+                        if (in_strip && py >= ys && py < ye && px < a.w) {
+                            float4 *dst = a.feat + (long long)pair * npix + (long long)py * a.w + px;
+                            dst[0] = ft[k];
+                            dst[a.feat_plane] = fr[k];
+                        }
+                    }
                 }
             }
         }
@@ -1627,6 +1645,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                     acc.y += live ? t.y : 0.f;
                     acc.z += live ? t.z : 0.f;
                     acc.w += live ? t.w : 0.f;
+                    if (FEAT && live) a.feat[2 * a.feat_plane + (long long)pair * npix + (long long)gy * a.w + gx] = D[o];
                     if (HM && live) {
                         const float eb = f_pow(a.eps, a.hm_beta);
                         float s = (f_pow(D[o].x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
@@ -1969,6 +1988,7 @@ struct BasebandArgs {
     const float4 *lut;     // [32] rows, pre-scaled: row*log2(10)+log2(sens)
     float *partials;       // [pairs][1][4]
     float *hm;             // [pairs][npix] or null
+    float4 *feat;          // feature mode: [3][pairs][npix] planes |T|S, |R|S, D, or null
     int npix;
     float lut_a, lut_b;
     float eps, beta;
@@ -2024,6 +2044,18 @@ __global__ void __launch_bounds__(256) k_baseband(const BasebandArgs a) {
             for (int c = 0; c < 4; ++c) s += powf(D[c] * a.hm_w[c] + a.eps, a.hm_beta) - eb;
             const float ib = 1.f / a.hm_beta;
             a.hm[(long long)pair * a.npix + i] = powf(s + a.eps, ib) - powf(a.eps, ib);
+        }
+        if (a.feat) {  // cvvdp_ml_metric.py:352 on the baseband: |T_f| S, |R_f| S, D
+            const long long plane = (long long)gridDim.x * a.npix, off = (long long)pair * a.npix + i;
+            float ft[4], fr[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                ft[c] = fabsf(fminf(tv[c] / Lt, 1000.f)) * S[c];
+                fr[c] = fabsf(fminf(rv[c] / Lr, 1000.f)) * S[c];
+            }
+            a.feat[off] = make_float4(ft[0], ft[1], ft[2], ft[3]);
+            a.feat[plane + off] = make_float4(fr[0], fr[1], fr[2], fr[3]);
+            a.feat[2 * plane + off] = make_float4(D[0], D[1], D[2], D[3]);
         }
     }
 #pragma unroll
@@ -2116,6 +2148,65 @@ __global__ void __launch_bounds__(256) k_pool(const PoolArgs a) {
         if (a.F == 1) Q = q_img * a.image_int;  // l.636
         else Q = spow_acc(tot / (float)a.F, 1.f / a.beta_t, a.eps);  // l.638
         a.jod[b] = met2jod_dev(Q, a.jod_a, a.jod_exp);
+    }
+}
+
+// =================================================================================================
+// Feature pooling for the ML heads (cvvdp_feature_pooling, cvvdp_ml_metric.py:78-106): mean and
+// variance of |T|S, |R|S and D over feature_size x feature_size patches of one band
+// (AvgPool2d(ceil_mode=True): a ragged border patch is averaged over the pixels it covers).
+// One CTA per (patch, item-frame); fixed-order reduction.  Output [B][F][ph][pw][C][6].
+// =================================================================================================
+struct FeaturePoolArgs {
+    const float4 *feat;   // [3][pairs][h*w]
+    long long feat_plane;
+    float *out;           // this band: [B][F_total][ph][pw][C][6]
+    int h, w, ps, ph, pw;
+    int C, n, f_off, F_total;
+};
+__global__ void __launch_bounds__(128) k_feature_pool(const FeaturePoolArgs a) {
+    __shared__ float red[4][24];
+    const int tid = threadIdx.x, pxi = blockIdx.x, pyi = blockIdx.y, pair = blockIdx.z;
+    const int x0 = pxi * a.ps, y0 = pyi * a.ps;
+    const int pwid = min(a.ps, a.w - x0), phgt = min(a.ps, a.h - y0);
+    const long long npix = (long long)a.h * a.w;
+    float s[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) s[i] = 0.f;
+    for (int i = tid; i < pwid * phgt; i += 128) {
+        const int r = i / pwid, c = i - r * pwid;
+        const long long off = (long long)pair * npix + (long long)(y0 + r) * a.w + (x0 + c);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float4 v = a.feat[k * a.feat_plane + off];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                s[k * 8 + ch] += vv[ch];
+                s[k * 8 + 4 + ch] = fmaf(vv[ch], vv[ch], s[k * 8 + 4 + ch]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < 24; ++i) red[tid >> 5][i] = s[i];
+    }
+    __syncthreads();
+    if (tid < 3 * a.C) {
+        const int k = tid / a.C, ch = tid - k * a.C;
+        const float cnt = (float)(pwid * phgt);
+        const float sum = (red[0][k * 8 + ch] + red[1][k * 8 + ch]) + (red[2][k * 8 + ch] + red[3][k * 8 + ch]);
+        const float sq = (red[0][k * 8 + 4 + ch] + red[1][k * 8 + 4 + ch]) + (red[2][k * 8 + 4 + ch] + red[3][k * 8 + 4 + ch]);
+        const float mean = sum / cnt;
+        const int b = pair / a.n, f = pair - b * a.n;
+        float *dst = a.out + (((((long long)b * a.F_total + (a.f_off + f)) * a.ph + pyi) * a.pw + pxi) * a.C + ch) * 6 + 2 * k;
+        dst[0] = mean;
+        dst[1] = sq / cnt - mean * mean;
     }
 }
 

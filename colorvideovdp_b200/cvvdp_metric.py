@@ -193,7 +193,7 @@ class cvvdp(vq_metric):
         return self.predict_video_source(test_vs)
 
     # ------------------------------------------------------------------------------------------
-    def _plan(self, B, H, W, F, fps, cin, dtype_id, photo, yuv=None):
+    def _plan(self, B, H, W, F, fps, cin, dtype_id, photo, yuv=None, features=False):
         """(Re)build the native plan when the job or the display changed.  photo=None: frames already
         are DKLd65 (plugin sources), the front end passes them through."""
         if self.temp_padding not in ("replicate", "symmetric"):
@@ -205,7 +205,7 @@ class cvvdp(vq_metric):
             disp = photo.native_display(self.pix_per_deg)
         hm = N.HEATMAP_RAW if self.do_heatmap else N.HEATMAP_NONE
         key = (B, H, W, F, float(fps), cin, dtype_id, self.temp_padding, hm, bytes(disp), self.gpu_mem,
-               bytes(yuv) if yuv is not None else None)
+               bytes(yuv) if yuv is not None else None, bool(features))
         if key != self._plan_key:
             self._ctx.set_display(disp)
             job = N.Job(batch=B, height=H, width=W, n_frames=F, fps=float(fps), in_channels=cin, dtype=dtype_id,
@@ -214,6 +214,7 @@ class cvvdp(vq_metric):
                         workspace_limit_bytes=int(self.gpu_mem * 1e9) if self.gpu_mem else 0)
             if yuv is not None:
                 job.yuv = yuv
+            job.features = 1 if features else 0
             self._info = self._ctx.plan(job)
             self._plan_key = key
         return self._info
@@ -337,6 +338,40 @@ class cvvdp(vq_metric):
             self._ctx.process_host(_clip_of(test, B, first_frame), _clip_of(ref, B, first_frame), f0, f1,
                                    Qh.data_ptr(), hmh.data_ptr() if hmh is not None else None)
         return Qh, hmh
+
+    def extract_features(self, vid_source):
+        """Per-band feature tensors for the ML heads -- cvvdp_ml_base.extract_features with
+        cvvdp_feature_pooling (pycvvdp/cvvdp_ml_metric.py:78-106, 206-298, 302-352): a list with one
+        tensor [B, F, ph, pw, C, 6] per band on the metric's device, last axis (mean_T, var_T, mean_R,
+        var_R, mean_D, var_D) of |T_f| S, |R_f| S and D over ceil(ppd) x ceil(ppd) patches, and None for
+        the heat map (the reference's ML metrics do not produce one).  The regression heads themselves
+        need downloaded weights and are not part of this package."""
+        if self.do_heatmap:
+            raise vq_exception("Currently cvvdp-ml metrics do not produce heatmaps")
+        if not (type(vid_source) is video_source_array and type(vid_source.dm_photometry) is vvdp_display_photo_eotf):
+            raise NotImplementedError("extract_features needs a video_source_array with a vvdp_display_photo_eotf display")
+        H, W, F = vid_source.get_video_size()
+        B = vid_source.get_batch_size()
+        fps = vid_source.get_frames_per_second() if F > 1 else 0
+        test, ref = vid_source.test_video, vid_source.reference_video
+        if test.dtype != ref.dtype:
+            raise RuntimeError("Test and reference must have the same dtype")
+        info = self._plan(B, H, W, F, fps, test.shape[1], _TORCH_DTYPES[test.dtype], vid_source.dm_photometry, features=True)
+        C, L = info.n_channels, info.n_bands
+        layout = [self._ctx.feature_layout(bb) for bb in range(L + 1)]
+        buf = torch.zeros((layout[L][3],), dtype=torch.float32, device=self.device)
+        test, ref = test.to(self.device), ref.to(self.device)
+        Q, _ = self._alloc_outputs(B, C, F, L, H, W)
+        self._ctx.set_feature_output(buf.data_ptr())
+        try:
+            self._ctx.process_device(_clip_of(test, B, 0), _clip_of(ref, B, 0), 0, F, Q.data_ptr(), None, self._stream())
+        finally:
+            self._ctx.set_feature_output(None)
+        feats = []
+        for bb in range(L):
+            ph, pw, _, off = layout[bb]
+            feats.append(buf[off:layout[bb + 1][3]].view(B, F, ph, pw, C, 6))
+        return feats, None
 
     def _run_plugin(self, vs, B, H, W, F, fps, f0, f1):
         """Any third-party video_source: frames are pulled through get_*_frame(..., 'DKLd65'), strictly in

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CVVDP_B200_ABI_VERSION 2
+#define CVVDP_B200_ABI_VERSION 3
 #define CVVDP_MAX_BANDS 16
 #define CVVDP_MAX_FILTER_LEN 129
 #define CVVDP_CSF_LUT_N 32
@@ -106,6 +106,7 @@ typedef struct {
     int32_t max_block_frames;/* frames per pass (0 = choose from the workspace budget) */
     int64_t workspace_limit_bytes; /* 0 = default */
     cvvdp_b200_yuv yuv;      /* yuv.chroma != 0: the clips hold planar YUV frames (dtype U8 or U16, in_channels 3) */
+    int32_t features;        /* != 0: also produce the per-band patch statistics of the ML heads (see cvvdp_b200_feature_layout) */
 } cvvdp_b200_job;
 
 typedef struct {
@@ -188,7 +189,7 @@ int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, con
  * temporal = input bytes read once + 32 B/pixel written, reduce = 32 read + 8 written per input
  * pixel-pair, band = 32 + 8 read per level pixel-pair, ... */
 enum { CVVDP_K_TEMPORAL = 0, CVVDP_K_REDUCE = 1, CVVDP_K_BAND = 2, CVVDP_K_BASEBAND = 3, CVVDP_K_FINALIZE = 4,
-       CVVDP_K_HEATMAP = 5, CVVDP_K_POOL = 6, CVVDP_K_FRONTEND = 7 };
+       CVVDP_K_HEATMAP = 5, CVVDP_K_POOL = 6, CVVDP_K_FRONTEND = 7, CVVDP_K_FEATURES = 8 };
 typedef struct {
     int32_t kind, level, launches;
     float total_ms;
@@ -199,6 +200,18 @@ int cvvdp_b200_profile_read(cvvdp_b200_ctx *ctx, cvvdp_b200_kernel_stat *out, in
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx);
+
+/* Feature mode (job.features != 0) -- replaces cvvdp_ml_base.extract_features / cvvdp_feature_pooling
+ * (pycvvdp/cvvdp_ml_metric.py:78-106, 206-298, 302-352): for every band, mean and variance of |T_f| S, |R_f| S and D
+ * over feature_size x feature_size patches (feature_size = ceil(ppd), ragged border patches averaged over the
+ * pixels they cover).  The tensor of band `band` is fp32 [B][F][ph][pw][C][6] with the last axis
+ * (mean_T, var_T, mean_R, var_R, mean_D, var_D); all bands live in ONE device buffer, band after band.
+ * cvvdp_b200_feature_layout reports ph, pw and the float offset of a band (offset of band n_bands = total
+ * floats); cvvdp_b200_set_feature_output registers the device buffer that the next process_device /
+ * process_host calls fill for the frames they evaluate (NULL detaches it). */
+int cvvdp_b200_feature_layout(const cvvdp_b200_ctx *ctx, int band, int32_t *ph, int32_t *pw, int32_t *feature_size,
+                              int64_t *float_offset);
+int cvvdp_b200_set_feature_output(cvvdp_b200_ctx *ctx, float *features_dev);
 
 /* Column-strip width of the band kernel chosen for pyramid level `level` of the current plan (116: wide-strip
  * kernel, 52: narrow-strip kernel, 0: baseband or no plan).  Introspection for tests and profiling only. */

@@ -40,7 +40,7 @@ def test_struct_sizes_match_the_header():
     assert ctypes.sizeof(N.Display) == 4 * (2 + 5 + 9 + 1)
     assert ctypes.sizeof(N.Clip) == 8 + 5 * 8 + 8
     assert ctypes.sizeof(N.Yuv) == 4 * 6
-    assert ctypes.sizeof(N.Job) == 4 * 10 + 8 + 4 * 6
+    assert ctypes.sizeof(N.Job) == 4 * 10 + 8 + 4 * 6 + 4 + 4  # ... + features + tail padding (8-byte alignment)
     assert ctypes.sizeof(N.PlanInfo) == 4 * 4 + 4 * 16 * 3 + 4 * 4 * 129 + 8
 
 

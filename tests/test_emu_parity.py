@@ -239,3 +239,19 @@ def test_yuv_filename_metadata():
     assert (p["width"], p["height"], p["bit_depth"], p["chroma_ss"], p["color_space"], p["fps"]) == (1280, 720, 10, "444", "2020", 59.94)
     assert cv.decode_video_props("a_640x480p30_hdr.yuv")["fps"] == 30
     assert cv.create_yuv_fname("b", p) == "b_1280x720_10b_444_2020_59.94fps.yuv"
+
+
+@pytest.mark.parametrize("name", gu.feature_case_names())
+def test_features_on_mock_device(name, mock_device):
+    """cvvdp.extract_features (band kernel in feature mode + k_feature_pool) against tensors
+    produced by the reference's cvvdp_ml_base.extract_features, and the ordinary prediction is unchanged
+    by switching between the two plans."""
+    z, meta = gu.load_case(name)
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"])
+    vs = cv.video_source_array(z["test"], z["ref"], meta["fps"], dim_order=meta["dim_order"], display_photometry=m.display_photometry)
+    j0, s0 = m.predict_video_source(vs)
+    feats, hm = m.extract_features(vs)
+    assert hm is None
+    gu.assert_features_close([f.numpy() for f in feats], z, name)
+    j1, s1 = m.predict_video_source(vs)
+    assert np.array_equal(s0["Q_per_ch"], s1["Q_per_ch"]) and torch.equal(torch.as_tensor(j0), torch.as_tensor(j1))

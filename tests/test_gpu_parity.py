@@ -212,3 +212,34 @@ def test_yuv_1080p_matches_oracle_and_rgb_path(tmp_path):
     jod2, stats2 = m.predict(torch.from_numpy(T).to(DEV), torch.from_numpy(R).to(DEV), frames_per_second=30)
     gu.assert_q_close(stats["Q_per_ch"], stats2["Q_per_ch"], "yuv vs rgb path")
     assert abs(float(jod) - float(jod2)) <= 1e-4
+
+
+@pytest.mark.parametrize("name", gu.feature_case_names())
+def test_features_against_reference_fixtures(name):
+    """extract_features (band kernel in feature mode + k_feature_pool) against the tensors the
+    reference's cvvdp_ml_base.extract_features produced, and an ordinary prediction after it is unchanged."""
+    z, meta = gu.load_case(name)
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"], device=DEV)
+    vs = cv.video_source_array(_t(z["test"]), _t(z["ref"]), meta["fps"], dim_order=meta["dim_order"],
+                               display_photometry=m.display_photometry)
+    j0, s0 = m.predict_video_source(vs)
+    feats, hm = m.extract_features(vs)
+    assert hm is None and all(f.device.type == "cuda" for f in feats)
+    gu.assert_features_close([f.cpu().numpy() for f in feats], z, name)
+    j1, s1 = m.predict_video_source(vs)
+    assert np.array_equal(s0["Q_per_ch"], s1["Q_per_ch"]) and torch.equal(j0, j1)
+
+
+def test_features_1080p_against_oracle():
+    """Feature mode at a BASELINE size (1080p, 38-pixel patches, ragged last patch row) against the oracle."""
+    tst, ref = synth.make_pair_u8(41, 2, 1080, 1920)
+    m = cv.cvvdp(display_name="standard_fhd", device=DEV)
+    vs = cv.video_source_array(_t(tst), _t(ref), 30, dim_order="BCFHW", display_photometry=m.display_photometry)
+    feats, _ = m.extract_features(vs)
+    _, so = O.predict(tst, ref, "BCFHW", 30, "standard_fhd", features=True)
+    z = {f"features_b{bb}": f for bb, f in enumerate(so["features"])}
+
+    class Z(dict):
+        files = list(z)
+
+    gu.assert_features_close([f.cpu().numpy() for f in feats], Z(z), "1080p")
