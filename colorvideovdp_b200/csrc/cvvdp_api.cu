@@ -792,6 +792,11 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
                                          k_band2<false, true, true>,   k_band2<true, false, false>, k_band2<true, false, true>,
                                          k_band2<true, true, false>,   k_band2<true, true, true>};
         for (auto k : kb) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
+        void (*kf[8])(const BandArgs) = {k_band2<false, false, false, true>, k_band2<false, false, true, true>,
+                                         k_band2<false, true, false, true>,  k_band2<false, true, true, true>,
+                                         k_band2<true, false, false, true>,  k_band2<true, false, true, true>,
+                                         k_band2<true, true, false, true>,   k_band2<true, true, true, true>};
+        for (auto k : kf) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
         void (*k3[4])(const BandArgs) = {k_band3<false, false>, k_band3<false, true>, k_band3<true, false>, k_band3<true, true>};
         for (auto k : k3) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band3Smem));
     }

@@ -86,3 +86,36 @@ def test_frame_shard_partition():
             parts = [frame_shard(F, r, world) for r in range(world)]
             assert parts[0][0] == 0 and parts[-1][1] == F
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+
+
+def _worker_exchange4(rank, world, port, out_dir):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import colorvideovdp_b200 as cv
+    from colorvideovdp_b200 import cvvdp_metric, distributed as D
+    import emu_util
+    import synth
+    cvvdp_metric._set_mock_library_for_tests(emu_util.emu_library())
+    F, fps = 20, 60  # fl = 17: every shard of 5 frames needs history from up to four earlier ranks
+    tst, ref = synth.make_pair_u8(52, F, 24, 32)
+    m = cv.cvvdp(display_name="standard_fhd")
+    lo, hi = D.frame_shard(F, rank, world)
+    jod, Q = D.predict_frame_sharded_exchange(m, torch.from_numpy(tst[:, :, lo:hi].copy()), torch.from_numpy(ref[:, :, lo:hi].copy()), F, fps)
+    np.savez(os.path.join(out_dir, f"x{rank}.npz"), jod=jod.numpy(), Q=Q.numpy())
+    if rank == 0:
+        j_full, s_full = m.predict(tst, ref, frames_per_second=fps)
+        np.savez(os.path.join(out_dir, "xfull.npz"), jod=j_full.numpy(), Q=s_full["Q_per_ch"])
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_world4_gloo(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_exchange4, args=(4, port, str(tmp_path)), nprocs=4, join=True)
+    full = np.load(tmp_path / "xfull.npz")
+    for r in range(4):
+        z = np.load(tmp_path / f"x{r}.npz")
+        assert np.array_equal(z["Q"], full["Q"]) and np.array_equal(z["jod"], full["jod"])
