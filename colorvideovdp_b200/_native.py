@@ -84,6 +84,7 @@ SYMBOLS = {
                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_launch_count": (C.c_int64, [C.c_void_p]),
     "cvvdp_b200_band_strip_width": (C.c_int, [C.c_void_p, C.c_int]),
+    "cvvdp_b200_temporal_filters": (C.c_int, [C.c_void_p, C.c_float, C.POINTER(C.c_float)]),
     "cvvdp_b200_feature_layout": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
     "cvvdp_b200_set_feature_output": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -190,6 +191,14 @@ class Context:
 
     def launch_count(self):
         return int(self._lib.cvvdp_b200_launch_count(self._h))
+
+    def temporal_filters(self, fps):
+        """[4][n] taps (A-sust, RG, YV, A-trans) at `fps`, as a list of lists."""
+        buf = (C.c_float * (4 * MAX_FILTER_LEN))()
+        n = self._lib.cvvdp_b200_temporal_filters(self._h, float(fps), buf)
+        if n < 0:
+            raise NativeError(f"temporal_filters: error {n}")
+        return [[buf[c * MAX_FILTER_LEN + k] for k in range(n)] for c in range(4)]
 
     def feature_layout(self, band):
         """(ph, pw, feature_size, float offset) of the feature tensor of `band` (band == n_bands: total floats)."""

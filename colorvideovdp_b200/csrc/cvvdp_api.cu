@@ -1339,6 +1339,16 @@ int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, con
 
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int cvvdp_b200_temporal_filters(const cvvdp_b200_ctx *ctx, float fps, float *filters) {
+    if (!ctx || !filters || !(fps > 0.f)) return CVVDP_ERR_INVALID;
+    cvvdp_b200_plan_info tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    const int n = temporal_filters(ctx->P, (double)fps, &tmp);
+    if (n < 0) return CVVDP_ERR_UNSUPPORTED;
+    memcpy(filters, tmp.filters, sizeof(tmp.filters));
+    return n;
+}
+
 int cvvdp_b200_feature_layout(const cvvdp_b200_ctx *ctx, int band, int32_t *ph, int32_t *pw, int32_t *feature_size,
                               int64_t *float_offset) {
     if (!ctx || !ctx->planned) return CVVDP_ERR_STATE;

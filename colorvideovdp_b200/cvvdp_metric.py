@@ -339,6 +339,12 @@ class cvvdp(vq_metric):
                                    Qh.data_ptr(), hmh.data_ptr() if hmh is not None else None)
         return Qh, hmh
 
+    def get_temporal_filters(self, frames_per_s):
+        """cvvdp_metric.py:1057-1092: (list of the four filters [N] on the metric's device, omega_bands [0, 5]).
+        The taps come from the native planner, i.e. they are the ones the temporal kernel applies."""
+        F = [torch.tensor(row, dtype=torch.float32, device=self.device) for row in self._ctx.temporal_filters(frames_per_s)]
+        return F, torch.as_tensor([0.0, 5.0], device=self.device)
+
     def extract_features(self, vid_source):
         """Per-band feature tensors for the ML heads -- cvvdp_ml_base.extract_features with
         cvvdp_feature_pooling (pycvvdp/cvvdp_ml_metric.py:78-106, 206-298, 302-352): a list with one

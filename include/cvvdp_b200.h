@@ -201,6 +201,11 @@ int cvvdp_b200_profile_read(cvvdp_b200_ctx *ctx, cvvdp_b200_kernel_stat *out, in
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx);
 
+/* Temporal filters of the four channels at `fps` -- replaces cvvdp.get_temporal_filters (pycvvdp/cvvdp_metric.py:1057-1092):
+ * writes F[c][0..n-1], c = A-sust, RG, YV, A-trans, to `filters` (4 rows of CVVDP_MAX_FILTER_LEN floats) and returns n
+ * (odd), or a negative error code.  These are exactly the taps the temporal kernel uses. */
+int cvvdp_b200_temporal_filters(const cvvdp_b200_ctx *ctx, float fps, float *filters);
+
 /* Feature mode (job.features != 0) -- replaces cvvdp_ml_base.extract_features / cvvdp_feature_pooling
  * (pycvvdp/cvvdp_ml_metric.py:78-106, 206-298, 302-352): for every band, mean and variance of |T_f| S, |R_f| S and D
  * over feature_size x feature_size patches (feature_size = ceil(ppd), ragged border patches averaged over the

@@ -56,7 +56,20 @@ def save(name, test, ref, dim_order, fps, display, padding="replicate"):
     print(name, [tuple(f.shape) for f in feats])
 
 
+def save_temporal_filters():
+    """cvvdp.get_temporal_filters (cvvdp_metric.py:1057-1092) at common frame rates."""
+    m = pycvvdp.cvvdp(display_name="standard_4k", device=torch.device("cpu"), quiet=True)
+    arrays = {}
+    for fps in (15, 24, 25, 30, 50, 59.94, 60, 120):
+        F, omega = m.get_temporal_filters(fps)
+        arrays[f"fps_{fps}"] = np.stack([f.numpy() for f in F]).astype(np.float32)
+    arrays["omega_bands"] = omega.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "known_answer_temporal_filters.npz"), **arrays)
+    print("temporal filters:", {k: v.shape for k, v in arrays.items()})
+
+
 if __name__ == "__main__":
+    save_temporal_filters()
     t, r = synth.make_pair_u8(21, 1, 135, 240)   # image: ragged patches (38-pixel patches on 135x240), row-parity quirk levels
     save("feat_img_u8_135x240_fhd", t, r, "BCFHW", 0, "standard_fhd")
     t, r = synth.make_pair_u8(22, 6, 64, 100)    # video, 30 fps

@@ -255,3 +255,19 @@ def test_features_on_mock_device(name, mock_device):
     gu.assert_features_close([f.numpy() for f in feats], z, name)
     j1, s1 = m.predict_video_source(vs)
     assert np.array_equal(s0["Q_per_ch"], s1["Q_per_ch"]) and torch.equal(torch.as_tensor(j0), torch.as_tensor(j1))
+
+
+def test_get_temporal_filters_matches_reference(mock_device):
+    """cvvdp.get_temporal_filters against the reference's irfft-based filters (cvvdp_metric.py:1057-1092)."""
+    import os
+    z = np.load(os.path.join(gu.GOLDEN_DIR, "known_answer_temporal_filters.npz"))
+    m = cv.cvvdp(display_name="standard_4k")
+    for key in z.files:
+        if not key.startswith("fps_"):
+            continue
+        F, omega = m.get_temporal_filters(float(key[4:]))
+        got = np.stack([f.numpy() for f in F])
+        assert got.shape == z[key].shape
+        assert np.max(np.abs(got - z[key])) <= 2e-6, key
+        assert np.array_equal(got, got[:, ::-1])  # exactly symmetric
+        assert np.array_equal(omega.numpy(), z["omega_bands"])

@@ -119,3 +119,14 @@ def test_oracle_features_match_reference(name):
     z, meta = gu.load_case(name)
     _, stats = O.predict(z["test"], z["ref"], meta["dim_order"], meta["fps"], meta["display"], meta["padding"], features=True)
     gu.assert_features_close(stats["features"], z, name)
+
+
+def test_oracle_temporal_filters_match_reference():
+    """Direct inverse real DFT of the oracle against the reference's irfft + fftshift (cvvdp_metric.py:1057-1092)."""
+    import os
+    z = np.load(os.path.join(gu.GOLDEN_DIR, "known_answer_temporal_filters.npz"))
+    P = O.Params()
+    for key in z.files:
+        if key.startswith("fps_"):
+            got = np.stack(O.temporal_filters(float(key[4:]), P))
+            assert got.shape == z[key].shape and np.max(np.abs(got - z[key])) <= 2e-6, key
