@@ -271,3 +271,16 @@ def test_get_temporal_filters_matches_reference(mock_device):
         assert np.max(np.abs(got - z[key])) <= 2e-6, key
         assert np.array_equal(got, got[:, ::-1])  # exactly symmetric
         assert np.array_equal(omega.numpy(), z["omega_bands"])
+
+
+@pytest.mark.parametrize("fps", [8, 15, 24, 30, 40, 48, 50, 60, 120])
+def test_every_temporal_specialisation_against_oracle(fps, mock_device):
+    """Filter lengths 3..17 take the two-stage kernel specialised for that length (chunk sizes 2..9, clips
+    shorter and longer than the filter, symmetric padding); 31 taps (120 fps) take the generic kernel."""
+    F = 7 if fps < 60 else 21
+    tst, ref = synth.make_pair_u8(60 + fps, F, 16, 64)  # 1024 pixels: whole 64-pixel warp segments
+    m = cv.cvvdp(display_name="standard_fhd", temp_padding="symmetric")
+    jod, stats = m.predict(tst, ref, frames_per_second=fps)
+    jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd", "symmetric")
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"{fps} fps")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
