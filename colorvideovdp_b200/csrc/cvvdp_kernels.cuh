@@ -191,9 +191,14 @@ __global__ void __launch_bounds__(256) k_frontend(const FrontendArgs a) {
 
 // =================================================================================================
 // Temporal stage: front end fused with the causal FIR  (cvvdp_metric.py:453-561)
-// One thread owns one pixel of one video and marches over the frames of the block with a ring of the
-// last `fl` DKL triples in shared memory, so every input frame is read and EOTF-ed exactly once per
-// block (+ fl-1 history frames at the start of the block).
+// Every input frame is read and EOTF-ed exactly once per block (+ fl-1 history frames at the start of
+// the block).  Five generations of the kernel live here; the host picks the fastest one whose
+// requirements hold (cvvdp_api.cu, run_block):
+//   k_temporal_2s  two pixels per thread (fp32x2), rolled front end + unrolled symmetric FIR   [default]
+//   k_temporal_x2  two pixels per thread, fully unrolled time loop (asymmetric taps)
+//   k_temporal_stg one pixel per thread, cp.async-staged raw values (planes not whole 64-pixel segments)
+//   k_temporal_reg one pixel per thread, direct loads (strided / permuted views, planar YUV)
+//   k_temporal     generic shared-memory ring (more than 17 taps, i.e. above 64 fps)
 // =================================================================================================
 struct TemporalArgs {
     ClipView clip[2];
@@ -1089,19 +1094,10 @@ __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2
 //   (csf.py:28-51) -> mult-mutual masking with the 13x13 phase-uncertainty Gaussian, cross-channel
 //   pooling and soft clamp (cvvdp_metric.py:817-856, 963-971, 753-764, 945-950) -> spatial
 //   p-norm partial sums (cvvdp_metric.py:722, 1032-1048) [-> per-band heat-map plane, 724-734].
-// A CTA owns a 32x32 tile; the mutual-masking term needs a +-6 halo (reflect at image borders), so
-// contrast/CSF are evaluated on the 44x44 extended tile held in shared memory.
+// The per-pixel helpers below are shared by the strip-marching kernels k_band2 / k_band3 (the first
+// version of this file had a 32x32-tile kernel on top of them; it was 2.7x slower and is gone).
 // =================================================================================================
-#define CVVDP_BTX 32
-#define CVVDP_BTY 32
 #define CVVDP_BHALO 6
-#define CVVDP_BEW (CVVDP_BTX + 2 * CVVDP_BHALO)  // 44
-#define CVVDP_BEH (CVVDP_BTY + 2 * CVVDP_BHALO)  // 44
-#define CVVDP_BCW (CVVDP_BEW / 2 + 2)            // 24 coarse columns
-#define CVVDP_BCH (CVVDP_BEH / 2 + 2)
-#define CVVDP_MM_STRIDE (CVVDP_BEW + 1)          // 45: conflict-free row-wise 128-bit access
-#define CVVDP_HB_STRIDE (CVVDP_BTX + 1)          // 33
-#define CVVDP_BAND_THREADS 256
 
 struct BandArgs {
     const float4 *fine;    // level i   [pairs*2][h*w]
@@ -1131,15 +1127,6 @@ struct BandArgs {
     int use_tma;           // k_band2: stage the rows with TMA (else cp.async)
     TensorMap3D tm_fine;   // fp32 view [planes][h][4w] of level i,   box {256, 8, 2}
     TensorMap3D tm_coarse; // fp32 view [planes][hc][4wc] of level i+1, box {136, 6, 2}
-};
-
-struct BandSmem {
-    float4 lut[CVVDP_CSF_LUT_N];
-    float4 crs[2][CVVDP_BCH][CVVDP_BCW];
-    float4 mm[CVVDP_BEH][CVVDP_MM_STRIDE];
-    float4 df[CVVDP_BTY][CVVDP_BTX];
-    float4 hb[CVVDP_BEH][CVVDP_HB_STRIDE];
-    float red[CVVDP_BAND_THREADS / 32][4];
 };
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' padding
@@ -1215,181 +1202,17 @@ __device__ __forceinline__ float4 band_mask(const BandArgs &a, float4 m, float4 
     return make_float4(D01.x, D01.y, D23.x, D23.y);
 }
 
-__global__ void __launch_bounds__(CVVDP_BAND_THREADS) k_band(const BandArgs a) {
-    CVVDP_DYN_SMEM(smem_raw);
-    BandSmem &sm = *reinterpret_cast<BandSmem *>(smem_raw);
-    const int tid = threadIdx.x;
-    const int pair = blockIdx.z;
-    const int x0 = blockIdx.x * CVVDP_BTX, y0 = blockIdx.y * CVVDP_BTY;
-    const int hal = a.do_blur ? CVVDP_BHALO : 0;
-    const int ex0 = x0 - hal, ey0 = y0 - hal;        // origin of the extended tile (even)
-    const int cx0 = ex0 / 2 - 1, cy0 = ey0 / 2 - 1;  // origin of the coarse tile (ex0, ey0 are even)
-    const long long npix = (long long)a.h * a.w, ncpix = (long long)a.hc * a.wc;
-    const float4 *fine_t = a.fine + (long long)pair * 2 * npix, *fine_r = fine_t + npix;
-    const float4 *crs_t = a.coarse + (long long)pair * 2 * ncpix;
-
-    // ---- phase 0: CSF rows + coarse tile (replicate-clamped, lpyr_dec.py:136-141) ----
-    if (tid < CVVDP_CSF_LUT_N) sm.lut[tid] = a.lut[tid];
-    for (int i = tid; i < 2 * CVVDP_BCH * CVVDP_BCW; i += CVVDP_BAND_THREADS) {
-        const int v = i / (CVVDP_BCH * CVVDP_BCW), rem = i - v * (CVVDP_BCH * CVVDP_BCW);
-        const int r = rem / CVVDP_BCW, c = rem - r * CVVDP_BCW;
-        const int cy = min(max(cy0 + r, 0), a.hc - 1), cx = min(max(cx0 + c, 0), a.wc - 1);
-        sm.crs[v][r][c] = crs_t[v * ncpix + (long long)cy * a.wc + cx];
-    }
-    __syncthreads();
-
-    // ---- phase 1: 2x2 quads of the extended tile: expand, contrast, CSF, |T'-R'| and min(|T'|,|R'|) ----
-    const int eh = CVVDP_BTY + 2 * hal, ew = CVVDP_BTX + 2 * hal;
-    const int qh = eh / 2, qw = ew / 2;
-    for (int qi = tid; qi < qh * qw; qi += CVVDP_BAND_THREADS) {
-        const int qy = qi / qw, qx = qi - qy * qw;
-        const int gy = ey0 + 2 * qy, gx = ex0 + 2 * qx;  // top-left fine pixel of the quad (even, even)
-        if (gy + 1 < 0 || gy >= a.h || gx + 1 < 0 || gx >= a.w) continue;
-        // expanded coarse values of the quad for test (v=0) and reference (v=1): rows then columns
-        float4 e[2][4];
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            float4 ve[3], vo[3];  // vertical pass for the three coarse columns: even row, odd row
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float4 c0 = sm.crs[v][qy][qx + c], c1 = sm.crs[v][qy + 1][qx + c], c2 = sm.crs[v][qy + 2][qx + c];
-                ve[c] = fma4(0.1f, c2, fma4(0.8f, c1, 0.1f * c0));
-                vo[c] = fma4(0.5f, c2, 0.5f * c1);
-            }
-            e[v][0] = fma4(0.1f, ve[2], fma4(0.8f, ve[1], 0.1f * ve[0]));  // (even row, even col)
-            e[v][1] = fma4(0.5f, ve[2], 0.5f * ve[1]);                     // (even row, odd col)
-            e[v][2] = fma4(0.1f, vo[2], fma4(0.8f, vo[1], 0.1f * vo[0]));  // (odd row, even col)
-            e[v][3] = fma4(0.5f, vo[2], 0.5f * vo[1]);                     // (odd row, odd col)
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int py = gy + (k >> 1), px = gx + (k & 1);
-            if (py < 0 || py >= a.h || px < 0 || px >= a.w) continue;
-            const long long off = (long long)py * a.w + px;
-            float4 mm, df;
-            band_pixel(a, sm.lut, fine_t[off], fine_r[off], e[0][k], e[1][k], mm, df);
-            const int ly = py - ey0, lx = px - ex0;
-            sm.mm[ly][lx] = mm;
-            const int iy = py - y0, ix = px - x0;
-            if (iy >= 0 && iy < CVVDP_BTY && ix >= 0 && ix < CVVDP_BTX) sm.df[iy][ix] = df;
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 2: horizontal pass of the phase-uncertainty Gaussian (reflect padding) ----
-    if (a.do_blur) {
-        for (int it = tid; it < CVVDP_BEH * (CVVDP_BTX / 4); it += CVVDP_BAND_THREADS) {
-            const int r = it % CVVDP_BEH, xg = it / CVVDP_BEH;
-            const int gy = ey0 + r;
-            if (gy < 0 || gy >= a.h) continue;
-            const int gxb = x0 + xg * 4;
-            if (gxb >= a.w) continue;
-            float4 win[2 * CVVDP_BHALO + 4];
-#pragma unroll
-            for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
-                int lx = reflect_idx(gxb + j - CVVDP_BHALO, a.w) - ex0;
-                lx = min(max(lx, 0), CVVDP_BEW - 1);  // only hit by outputs beyond the image (discarded)
-                win[j] = sm.mm[r][lx];
-            }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                float4 acc = f4(0.f);
-#pragma unroll
-                for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) acc = fma4(a.kern[k], win[o + k], acc);
-                sm.hb[r][xg * 4 + o] = acc;
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- phase 3/4: vertical pass, masking, clamp, pooling ----
-    float eps_q[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) eps_q[c] = f_pow(a.eps, a.q[c]);
-    const float eps_p = f_pow(a.eps, a.p);
-    const float eps_b = (a.beta == 2.0f) ? 0.f : f_pow(a.eps, a.beta);
-    float4 acc = f4(0.f);
-    {
-        const int ix = tid % CVVDP_BTX, yg = tid / CVVDP_BTX;  // 4 consecutive rows per thread
-        const int gx = x0 + ix;
-        const int gyb = y0 + yg * 4;
-        if (gx < a.w && gyb < a.h) {
-            float4 win[2 * CVVDP_BHALO + 4];
-            if (a.do_blur) {
-#pragma unroll
-                for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
-                    int ly = reflect_idx(gyb + j - CVVDP_BHALO, a.h) - ey0;
-                    ly = min(max(ly, 0), CVVDP_BEH - 1);
-                    win[j] = sm.hb[ly][ix];
-                }
-            }
-#pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                const int gy = gyb + o;
-                if (gy >= a.h) break;
-                float4 m;
-                if (a.do_blur) {
-                    m = f4(0.f);
-#pragma unroll
-                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) m = fma4(a.kern[k], win[o + k], m);
-                } else {
-                    m = sm.mm[yg * 4 + o][ix];
-                }
-                const float4 D = band_mask(a, m, sm.df[yg * 4 + o][ix], eps_q, eps_p);
-                if (a.beta == 2.0f) {  // (D+eps)^2 - eps^2 == D (D + 2 eps), exact at D = 0
-                    acc.x = fmaf(D.x, D.x + 2.f * a.eps, acc.x);
-                    acc.y = fmaf(D.y, D.y + 2.f * a.eps, acc.y);
-                    acc.z = fmaf(D.z, D.z + 2.f * a.eps, acc.z);
-                    acc.w = fmaf(D.w, D.w + 2.f * a.eps, acc.w);
-                } else {
-                    acc.x += f_pow(D.x + a.eps, a.beta) - eps_b;
-                    acc.y += f_pow(D.y + a.eps, a.beta) - eps_b;
-                    acc.z += f_pow(D.z + a.eps, a.beta) - eps_b;
-                    acc.w += f_pow(D.w + a.eps, a.beta) - eps_b;
-                }
-                if (a.hm) {  // cvvdp_metric.py:724-734: p-norm over the channels, then set_lband's 1/band_mul
-                    const float eb = f_pow(a.eps, a.hm_beta);
-                    float s = (f_pow(D.x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D.y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
-                              (f_pow(D.z * a.hm_w[2] + a.eps, a.hm_beta) - eb) + (f_pow(D.w * a.hm_w[3] + a.eps, a.hm_beta) - eb);
-                    const float ib = 1.f / a.hm_beta;
-                    a.hm[(long long)pair * npix + (long long)gy * a.w + gx] = (f_pow(s + a.eps, ib) - f_pow(a.eps, ib)) * a.hm_scale;
-                }
-            }
-        }
-    }
-    // ---- phase 5: deterministic block reduction of the four channel sums ----
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if ((tid & 31) == 0) {
-        sm.red[tid >> 5][0] = acc.x;
-        sm.red[tid >> 5][1] = acc.y;
-        sm.red[tid >> 5][2] = acc.z;
-        sm.red[tid >> 5][3] = acc.w;
-    }
-    __syncthreads();
-    if (tid < 4) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < CVVDP_BAND_THREADS / 32; ++w) s += sm.red[w][tid];
-        const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
-        a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
-    }
-}
-
 // =================================================================================================
-// Fused band kernel, strip-marching version.  Same arithmetic as k_band; different decomposition:
-// a CTA owns a vertical strip of 52 columns (64 with the +-6 halo) of one (item, frame) and marches
-// down a segment of rows, 8 rows per step, keeping rolling windows in shared memory:
-//   mm  : min(|T'|,|R'|) of the 8 rows of this step (64 columns)
-//   hb  : ring of the last 32 rows of the horizontally blurred mm (52 columns)
-//   df  : ring of the last 16 rows of |T'-R'| waiting for their blurred mask
-// so the 13x13 Gaussian costs 13+13 taps, the vertical halo is paid once per segment instead of once
-// per 32-row tile, and a CTA needs 56 KB of shared memory (4 CTAs/SM) instead of 89 KB.
+// Fused band kernel, strip-marching version (the default band kernel).
+// A CTA of 128 threads owns a vertical strip of 52 columns (64 with the +-6 halo of the 13x13 Gaussian)
+// of one (item, frame) and marches down a segment of rows, 8 rows per step, keeping rolling windows in
+// shared memory:
+//   fine, crs : the 8 fine rows of this step and the 6 coarse rows under them (TMA stage, one step ahead)
+//   mm        : min(|T'|,|R'|) of the 8 rows of this step (64 columns)
+//   hb        : ring of the last 32 rows of the horizontally blurred mm (52 columns)
+//   df        : ring of the last 16 rows of |T'-R'| waiting for their blurred mask
+// so the 13x13 Gaussian costs 13+13 taps and the vertical halo is paid once per segment.  72 KB of shared
+// memory and 112 registers: 3 CTAs (12 warps) per SM.
 // Step k: rows A = [a0, a0+8) get contrast/CSF/mm/df (2x2 quads, one per thread) and their horizontal
 // blur; rows C = [a0-6, a0+2) -- whose 13-row window is now complete -- get the vertical blur,
 // masking, clamp and pooling.
