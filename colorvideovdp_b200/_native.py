@@ -84,6 +84,7 @@ SYMBOLS = {
                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_launch_count": (C.c_int64, [C.c_void_p]),
     "cvvdp_b200_band_strip_width": (C.c_int, [C.c_void_p, C.c_int]),
+    "cvvdp_b200_band_kernel_id": (C.c_int, [C.c_void_p, C.c_int]),
     "cvvdp_b200_temporal_filters": (C.c_int, [C.c_void_p, C.c_float, C.POINTER(C.c_float)]),
     "cvvdp_b200_feature_layout": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
@@ -209,6 +210,9 @@ class Context:
 
     def set_feature_output(self, ptr):
         self._check(self._lib.cvvdp_b200_set_feature_output(self._h, ptr), "set_feature_output")
+
+    def band_kernel_id(self, level):
+        return int(self._lib.cvvdp_b200_band_kernel_id(self._h, int(level)))
 
     def band_is_wide(self, level):
         return int(self._lib.cvvdp_b200_band_strip_width(self._h, int(level))) == 116

@@ -29,11 +29,12 @@ struct LevelBuf {
     float4 *lut = nullptr;      // [32]
     int tiles_x = 0, tiles_y = 0;  // band kernel grid: column strips x row segments
     int seg_rows = 0;
-    bool wide = false;             // band kernel: k_band3 (116-column strips) instead of k_band2 (52)
+    int band3 = 0;                 // band kernel: 0 = k_band2 (default); 128 / 64 = k_band3<EW> (opt-in variants)
     int do_blur = 0;
     TensorMap3D tm;  // fp32 view [planes][h][4w] of g; box depends on the role (see make_tensor_map)
     TensorMap3D tm_as_coarse;
     TensorMap3D tm_reduce_in;  // box {63 px, 19 rows, 1 plane}
+    TensorMap3D tm_reduce_in16;  // box {63 px, 35 rows, 1 plane} (TY = 16 variant)
     bool tm_ok = false;
 };
 
@@ -507,18 +508,25 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         LaunchScope ls(ctx, st, CVVDP_K_REDUCE, i, (double)pairs * 2 * 16.0 * ((double)ra.h * ra.w + (double)ra.hc * ra.wc));
         static const bool no_tma_reduce = getenv("CVVDP_B200_NO_TMA") != nullptr;
         if (ctx->lv[i].tm_ok && !no_tma_reduce) {  // persistent, TMA-staged, double-buffered
+            const bool ty16 = getenv("CVVDP_B200_REDUCE_TY16") != nullptr && ra.hc >= 64;  // A/B switch (unmeasured)
+            const int ty = ty16 ? 16 : 8;
             Reduce2Args r2;
-            r2.tm_in = ctx->lv[i].tm_reduce_in;
+            r2.tm_in = ty16 ? ctx->lv[i].tm_reduce_in16 : ctx->lv[i].tm_reduce_in;
             r2.out = ra.out;
             r2.h = ra.h;
             r2.w = ra.w;
             r2.hc = ra.hc;
             r2.wc = ra.wc;
             r2.planes = pairs * 2;
-            const long long tiles = (long long)((ra.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX) * ((ra.hc + CVVDP_R2_TY - 1) / CVVDP_R2_TY) * r2.planes;
-            const int grid2 = (int)std::min<long long>(tiles, (long long)ctx->num_sms * 4);
-            auto kfn = k_reduce2;
-            CVVDP_LAUNCH(kfn, dim3(grid2), dim3(256), sizeof(Reduce2Smem), st, r2);
+            const long long tiles = (long long)((ra.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX) * ((ra.hc + ty - 1) / ty) * r2.planes;
+            const int grid2 = (int)std::min<long long>(tiles, (long long)ctx->num_sms * (ty16 ? 2 : 4));
+            if (ty16) {
+                auto kfn = k_reduce2<16>;
+                CVVDP_LAUNCH(kfn, dim3(grid2), dim3(256), sizeof(Reduce2Smem<16>), st, r2);
+            } else {
+                auto kfn = k_reduce2<8>;
+                CVVDP_LAUNCH(kfn, dim3(grid2), dim3(256), sizeof(Reduce2Smem<8>), st, r2);
+            }
         } else {
             dim3 grid((ra.wc + CVVDP_RTX - 1) / CVVDP_RTX, (ra.hc + CVVDP_RTY - 1) / CVVDP_RTY, pairs * 2);
             auto kfn = k_reduce;
@@ -588,11 +596,19 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Band2Smem), st, ba);
             continue;
         }
-        if (lv.wide) {
+        if (lv.band3) {
             const int v3 = (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
-            void (*k3[4])(const BandArgs) = {k_band3<false, false>, k_band3<false, true>, k_band3<true, false>, k_band3<true, true>};
-            auto kfn = k3[v3];
-            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B3_THREADS), sizeof(Band3Smem), st, ba);
+            if (lv.band3 == 128) {
+                void (*k3[4])(const BandArgs) = {k_band3<128, false, false>, k_band3<128, false, true>, k_band3<128, true, false>,
+                                                 k_band3<128, true, true>};
+                auto kfn = k3[v3];
+                CVVDP_LAUNCH(kfn, grid, dim3(B3Geom<128>::THREADS), sizeof(Band3Smem<128>), st, ba);
+            } else {
+                void (*k3[4])(const BandArgs) = {k_band3<64, false, false>, k_band3<64, false, true>, k_band3<64, true, false>,
+                                                 k_band3<64, true, true>};
+                auto kfn = k3[v3];
+                CVVDP_LAUNCH(kfn, grid, dim3(B3Geom<64>::THREADS), sizeof(Band3Smem<64>), st, ba);
+            }
             continue;
         }
         const int variant = (ba.do_blur ? 4 : 0) | (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
@@ -797,11 +813,17 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
                                          k_band2<true, false, false, true>,  k_band2<true, false, true, true>,
                                          k_band2<true, true, false, true>,   k_band2<true, true, true, true>};
         for (auto k : kf) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
-        void (*k3[4])(const BandArgs) = {k_band3<false, false>, k_band3<false, true>, k_band3<true, false>, k_band3<true, true>};
-        for (auto k : k3) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band3Smem));
+        void (*k3w[4])(const BandArgs) = {k_band3<128, false, false>, k_band3<128, false, true>, k_band3<128, true, false>,
+                                          k_band3<128, true, true>};
+        for (auto k : k3w) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band3Smem<128>));
+        void (*k3n[4])(const BandArgs) = {k_band3<64, false, false>, k_band3<64, false, true>, k_band3<64, true, false>,
+                                          k_band3<64, true, true>};
+        for (auto k : k3n) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band3Smem<64>));
     }
-    auto kr2 = k_reduce2;
-    cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem));
+    auto kr2 = k_reduce2<8>;
+    cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem<8>));
+    auto kr16 = k_reduce2<16>;
+    cudaFuncSetAttribute(kr16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem<16>));
     auto kt = k_temporal;
     cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          std::min(ctx->max_smem_optin, 227 * 1024));
@@ -918,8 +940,14 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
             // on the same box; ncu: 3x the barrier stalls with 8-warp CTAs, +9 instructions per pixel of ring
             // arithmetic) -- see DESIGN.md section 5.  Read at plan time.
             const bool want_wide = getenv("CVVDP_B200_WIDE") != nullptr;
-            lv.wide = want_wide && !job->features && lv.do_blur && lv.w >= 2 * CVVDP_B3_SW && lv.h >= 32;
-            const int sw = lv.wide ? CVVDP_B3_SW : CVVDP_B2_SW;
+            // CVVDP_B200_BAND3_NARROW: k_band3 at k_band2's strip width (4 CTAs/SM), not yet measured
+            const bool want_narrow3 = getenv("CVVDP_B200_BAND3_NARROW") != nullptr;
+            lv.band3 = 0;
+            if (!job->features && lv.do_blur && lv.h >= 32) {
+                if (want_wide && lv.w >= 2 * B3Geom<128>::SW) lv.band3 = 128;
+                else if (want_narrow3 && lv.w >= 2 * B3Geom<64>::SW) lv.band3 = 64;
+            }
+            const int sw = lv.band3 == 128 ? B3Geom<128>::SW : CVVDP_B2_SW;
             lv.tiles_x = (lv.w + sw - 1) / sw;
             // the split depends on the level geometry only, never on the batch or block size, so that
             // the summation order (hence every bit of Q_per_ch) is independent of how frames are
@@ -978,7 +1006,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.lut = (float4 *)(base + off_l[i]);
         lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_EW, CVVDP_B2_RB) &&
                    make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_CC, CVVDP_B2_CR) &&
-                   make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, CVVDP_R2_IH, 1);
+                   make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<8>::IH, 1) &&
+                   make_tensor_map(&lv.tm_reduce_in16, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<16>::IH, 1);
         float rows[4][CVVDP_CSF_LUT_N];
         for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
         float packed[CVVDP_CSF_LUT_N][4];
@@ -1377,7 +1406,12 @@ int cvvdp_b200_set_feature_output(cvvdp_b200_ctx *ctx, float *features_dev) {
 
 int cvvdp_b200_band_strip_width(const cvvdp_b200_ctx *ctx, int level) {
     if (!ctx || !ctx->planned || level < 0 || level + 1 >= (int)ctx->lv.size()) return 0;
-    return ctx->lv[level].wide ? CVVDP_B3_SW : CVVDP_B2_SW;
+    return ctx->lv[level].band3 == 128 ? B3Geom<128>::SW : CVVDP_B2_SW;
+}
+
+int cvvdp_b200_band_kernel_id(const cvvdp_b200_ctx *ctx, int level) {
+    if (!ctx || !ctx->planned || level < 0 || level + 1 >= (int)ctx->lv.size()) return 0;
+    return ctx->lv[level].band3 == 128 ? 3 : (ctx->lv[level].band3 == 64 ? 4 : 2);
 }
 
 int cvvdp_b200_profile_enable(cvvdp_b200_ctx *ctx, int enable) {

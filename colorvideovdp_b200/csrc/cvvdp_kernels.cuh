@@ -981,31 +981,35 @@ __global__ void __launch_bounds__(256) k_reduce(const ReduceArgs a) {
     }
 }
 
-// Persistent TMA version of the reduce: each CTA loops over output tiles of 30x8 pixels; the 63x19
+// Persistent TMA version of the reduce: each CTA loops over output tiles of 30 x TY pixels; the 63 x (2 TY + 3)
 // input box of the NEXT tile is fetched by one cp.async.bulk.tensor while the current one is filtered
 // (two shared-memory buffers, one mbarrier each).  TMA's zero fill outside the image is exactly the
 // zero padding of the reference's strided conv2d; the edge fix-ups are the same as in k_reduce.
+// TY = 8 is the default; TY = 16 (63x35 input box, surplus halo traffic 1.25x -> 1.15x of the algorithmic bytes
+// when the L2 keeps none of it) is an opt-in A/B variant (CVVDP_B200_REDUCE_TY16), not yet measured.
 #define CVVDP_R2_TX 30
-#define CVVDP_R2_TY 8
 #define CVVDP_R2_IW (2 * CVVDP_R2_TX + 3)  // 63 pixels = 252 floats (TMA box limit 256)
-#define CVVDP_R2_IH (2 * CVVDP_R2_TY + 3)  // 19
-#define CVVDP_R2_BUF 1200                  // float4 per buffer: 19*63 = 1197 rounded to a 128-byte multiple
 struct Reduce2Args {
-    TensorMap3D tm_in;  // fp32 view [planes][h][4w], box {252, 19, 1}
+    TensorMap3D tm_in;  // fp32 view [planes][h][4w], box {252, 2 TY + 3, 1}
     float4 *out;
     int h, w, hc, wc, planes;
 };
+template <int TY>
 struct Reduce2Smem {
-    float4 in[2][CVVDP_R2_BUF];
-    float4 ya[CVVDP_R2_TY][CVVDP_R2_IW + 1];
+    static constexpr int IH = 2 * TY + 3;                                    // 19 / 35 input rows
+    static constexpr int BUF = (IH * CVVDP_R2_IW * 16 + 127) / 128 * 128 / 16;  // float4 per buffer, 128-byte multiple
+    float4 in[2][BUF];
+    float4 ya[TY][CVVDP_R2_IW + 1];
     unsigned long long bar[2];
 };
+template <int TY>
 __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2Args a) {
     CVVDP_DYN_SMEM(smem_raw);
-    Reduce2Smem &sm = *reinterpret_cast<Reduce2Smem *>(smem_raw);
+    Reduce2Smem<TY> &sm = *reinterpret_cast<Reduce2Smem<TY> *>(smem_raw);
+    constexpr int IH = Reduce2Smem<TY>::IH;
     const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f;
     const int tid = threadIdx.x;
-    const int ntx = (a.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX, nty = (a.hc + CVVDP_R2_TY - 1) / CVVDP_R2_TY;
+    const int ntx = (a.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX, nty = (a.hc + TY - 1) / TY;
     const long long total = (long long)ntx * nty * a.planes;
     const bool rows_odd = (a.h & 1) != 0;
     if (tid == 0) {
@@ -1017,8 +1021,8 @@ __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2
         const int plane = (int)(t / (ntx * nty)), rem = (int)(t - (long long)plane * (ntx * nty));
         const int ty = rem / ntx, tx = rem - ty * ntx;
         fence_proxy_async();
-        mbar_expect_tx(&sm.bar[buf], CVVDP_R2_IH * CVVDP_R2_IW * 16);
-        tma_load_3d(&sm.in[buf][0], &a.tm_in, 4 * (2 * tx * CVVDP_R2_TX - 2), 2 * ty * CVVDP_R2_TY - 2, plane, &sm.bar[buf]);
+        mbar_expect_tx(&sm.bar[buf], IH * CVVDP_R2_IW * 16);
+        tma_load_3d(&sm.in[buf][0], &a.tm_in, 4 * (2 * tx * CVVDP_R2_TX - 2), 2 * ty * TY - 2, plane, &sm.bar[buf]);
         mbar_emu_complete(&sm.bar[buf]);
     };
     if (tid == 0 && (long long)blockIdx.x < total) issue(blockIdx.x, 0);
@@ -1030,9 +1034,9 @@ __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2
         const float4 *in = sm.in[buf];
         const int plane = (int)(t / (ntx * nty)), rem = (int)(t - (long long)plane * (ntx * nty));
         const int ty = rem / ntx, tx = rem - ty * ntx;
-        const int ox0 = tx * CVVDP_R2_TX, oy0 = ty * CVVDP_R2_TY;
+        const int ox0 = tx * CVVDP_R2_TX, oy0 = ty * TY;
         const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
-        for (int i = tid; i < CVVDP_R2_TY * CVVDP_R2_IW; i += 256) {
+        for (int i = tid; i < TY * CVVDP_R2_IW; i += 256) {
             const int oy = i / CVVDP_R2_IW, c = i - oy * CVVDP_R2_IW;
             const int goy = oy0 + oy;
             float4 acc = f4(0.f);
@@ -1059,8 +1063,8 @@ __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2
             sm.ya[oy][c] = acc;
         }
         __syncthreads();
-        if (tid < CVVDP_R2_TX * CVVDP_R2_TY) {
-            const int ox = tid % CVVDP_R2_TX, oy = tid / CVVDP_R2_TX;
+        for (int o = tid; o < CVVDP_R2_TX * TY; o += 256) {  // one pass for TY = 8 (240 outputs), two for TY = 16
+            const int ox = o % CVVDP_R2_TX, oy = o / CVVDP_R2_TX;
             const int gox = ox0 + ox, goy = oy0 + oy;
             if (gox < a.wc && goy < a.hc) {
                 const int c = 2 * ox;
@@ -1516,37 +1520,46 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
 //     accesses of phase B stay free of bank conflicts, which a tensor-map box (dense rows, 128-byte
 //     aligned) cannot give.  Nothing outside the image is copied; those entries are never consumed.
 // =================================================================================================
-#define CVVDP_B3_SW 116
-#define CVVDP_B3_EW 128
 #define CVVDP_B3_RB 8
-#define CVVDP_B3_THREADS 256
 #define CVVDP_B3_HBR 20
 #define CVVDP_B3_DFR 16
 #define CVVDP_B3_CR (CVVDP_B3_RB / 2 + 2)  // 6 coarse rows per step
-#define CVVDP_B3_CC (CVVDP_B3_EW / 2 + 2)  // 66 coarse columns
-#define CVVDP_B3_FS (CVVDP_B3_EW + 1)      // padded row stride of the fine / mm rows
 #define CVVDP_B3_NCOPY (2 * CVVDP_B3_RB + 2 * CVVDP_B3_CR)  // bulk copies (= mbarrier arrivals) per step
+// Geometry by extended strip width EW: 128 -> 116 useful columns, 256 threads, 2 CTAs/SM (the variant
+// measured above); 64 -> 52 columns, 128 threads, 54 KB of shared memory = 4 CTAs (16 warps) per SM with
+// 4-warp barriers -- k_band2's geometry with k_band3's leaner shared-memory layout (opt-in
+// CVVDP_B200_BAND3_NARROW, not yet measured on a B200).
+template <int EW>
+struct B3Geom {
+    static constexpr int SW = EW - 2 * CVVDP_BHALO;  // useful columns
+    static constexpr int THREADS = 2 * EW;
+    static constexpr int CC = EW / 2 + 2;            // coarse columns
+    static constexpr int FS = EW + 1;                // padded row stride of the fine / mm rows
+    static constexpr int CTAS = EW == 64 ? 4 : 2;
+};
 
+template <int EW>
 struct Band3Smem {
     float4 lut[CVVDP_CSF_LUT_N];
-    float4 crs[2][CVVDP_B3_CR][CVVDP_B3_CC];
-    float4 fine[2][CVVDP_B3_RB][CVVDP_B3_FS];  // [0] = test rows, overwritten by min(|T'|,|R'|) in phase A
-    float4 hb[CVVDP_B3_HBR][CVVDP_B3_SW + 1];
-    float4 df[CVVDP_B3_DFR][CVVDP_B3_SW];
-    float red[CVVDP_B3_THREADS / 32][4];
+    float4 crs[2][CVVDP_B3_CR][B3Geom<EW>::CC];
+    float4 fine[2][CVVDP_B3_RB][B3Geom<EW>::FS];  // [0] = test rows, overwritten by min(|T'|,|R'|) in phase A
+    float4 hb[CVVDP_B3_HBR][B3Geom<EW>::SW + 1];
+    float4 df[CVVDP_B3_DFR][B3Geom<EW>::SW];
+    float red[B3Geom<EW>::THREADS / 32][4];
     unsigned long long bar;
 };
 
 // Copy `c` of the stage of rows [a0, a0+8): c < 8: test row c; c < 16: reference row c-8; else the
 // coarse rows under them (test, then reference).  Every copy arrives once on the barrier.
-__device__ __forceinline__ void band3_copy(const BandArgs &a, Band3Smem &sm, const float4 *fine_t, const float4 *crs_g,
+template <int EW>
+__device__ __forceinline__ void band3_copy(const BandArgs &a, Band3Smem<EW> &sm, const float4 *fine_t, const float4 *crs_g,
                                            long long npix, long long ncpix, int a0, int a_end, int ex0, int c) {
     void *dst = nullptr;
     const float4 *src = nullptr;
     int n = 0;
     if (c < 2 * CVVDP_B3_RB) {
         const int v = c / CVVDP_B3_RB, r = c - v * CVVDP_B3_RB, gy = a0 + r;
-        const int gx0 = max(ex0, 0), gx1 = min(ex0 + CVVDP_B3_EW, a.w);
+        const int gx0 = max(ex0, 0), gx1 = min(ex0 + EW, a.w);
         if (gy < a_end && gx1 > gx0) {
             n = gx1 - gx0;
             dst = &sm.fine[v][r][gx0 - ex0];
@@ -1555,7 +1568,7 @@ __device__ __forceinline__ void band3_copy(const BandArgs &a, Band3Smem &sm, con
     } else {
         const int cc = c - 2 * CVVDP_B3_RB, v = cc / CVVDP_B3_CR, r = cc - v * CVVDP_B3_CR;
         const int cy = a0 / 2 - 1 + r, cx0 = ex0 / 2 - 1;
-        const int gx0 = max(cx0, 0), gx1 = min(cx0 + CVVDP_B3_CC, a.wc);
+        const int gx0 = max(cx0, 0), gx1 = min(cx0 + B3Geom<EW>::CC, a.wc);
         if (cy >= 0 && cy < a.hc && gx1 > gx0) {
             n = gx1 - gx0;
             dst = &sm.crs[v][r][gx0 - cx0];
@@ -1571,27 +1584,30 @@ __device__ __forceinline__ void band3_copy(const BandArgs &a, Band3Smem &sm, con
 }
 // Issue copies [c0, c1) of a stage: one lane each on the device, one thread in the mock-device build
 // (whose copies are synchronous; the phase is completed after the last group).
-__device__ __forceinline__ void band3_issue(const BandArgs &a, Band3Smem &sm, const float4 *fine_t, const float4 *crs_g,
+template <int EW>
+__device__ __forceinline__ void band3_issue(const BandArgs &a, Band3Smem<EW> &sm, const float4 *fine_t, const float4 *crs_g,
                                             long long npix, long long ncpix, int a0, int a_end, int ex0, int tid, int c0, int c1,
                                             bool last) {
 #ifdef CVVDP_EMU
     if (tid == 0) {
-        for (int c = c0; c < c1; ++c) band3_copy(a, sm, fine_t, crs_g, npix, ncpix, a0, a_end, ex0, c);
+        for (int c = c0; c < c1; ++c) band3_copy<EW>(a, sm, fine_t, crs_g, npix, ncpix, a0, a_end, ex0, c);
         if (last) mbar_emu_complete(&sm.bar);
     }
 #else
     (void)last;
     if (tid < c1 - c0) {
         fence_proxy_async();  // the destination was last touched through the generic proxy
-        band3_copy(a, sm, fine_t, crs_g, npix, ncpix, a0, a_end, ex0, c0 + tid);
+        band3_copy<EW>(a, sm, fine_t, crs_g, npix, ncpix, a0, a_end, ex0, c0 + tid);
     }
 #endif
 }
 
-template <bool HM, bool BETA2>
-__global__ void __launch_bounds__(CVVDP_B3_THREADS, 2) k_band3(const __grid_constant__ BandArgs a) {
+template <int EW, bool HM, bool BETA2>
+__global__ void __launch_bounds__(B3Geom<EW>::THREADS, B3Geom<EW>::CTAS) k_band3(const __grid_constant__ BandArgs a) {
     CVVDP_DYN_SMEM(smem_raw);
-    Band3Smem &sm = *reinterpret_cast<Band3Smem *>(smem_raw);
+    Band3Smem<EW> &sm = *reinterpret_cast<Band3Smem<EW> *>(smem_raw);
+    constexpr int CVVDP_B3_SW = B3Geom<EW>::SW, CVVDP_B3_EW = EW, CVVDP_B3_THREADS = B3Geom<EW>::THREADS;
+    constexpr int CVVDP_B3_CC = B3Geom<EW>::CC, CVVDP_B3_FS = B3Geom<EW>::FS;
     const int tid = threadIdx.x;
     const int pair = blockIdx.z;
     constexpr int hal = CVVDP_BHALO;
@@ -1610,8 +1626,8 @@ __global__ void __launch_bounds__(CVVDP_B3_THREADS, 2) k_band3(const __grid_cons
     __syncthreads();
     unsigned phase = 0;
     // copies 0..7 (test rows) are issued apart from the rest: their destination doubles as mm
-    band3_issue(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, CVVDP_B3_RB, CVVDP_B3_NCOPY, false);
-    band3_issue(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, 0, CVVDP_B3_RB, true);
+    band3_issue<EW>(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, CVVDP_B3_RB, CVVDP_B3_NCOPY, false);
+    band3_issue<EW>(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, 0, CVVDP_B3_RB, true);
     float eps_q[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) eps_q[c] = f_pow(a.eps, a.q[c]);
@@ -1683,7 +1699,7 @@ __global__ void __launch_bounds__(CVVDP_B3_THREADS, 2) k_band3(const __grid_cons
         __syncthreads();
         const bool more = a0 + CVVDP_B3_RB < a_end;
         // the reference rows and the coarse rows are free: prefetch them for the next step
-        if (more) band3_issue(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B3_RB, a_end, ex0, tid, CVVDP_B3_RB, CVVDP_B3_NCOPY, false);
+        if (more) band3_issue<EW>(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B3_RB, a_end, ex0, tid, CVVDP_B3_RB, CVVDP_B3_NCOPY, false);
         // ---- phase B: horizontal pass of the phase-uncertainty Gaussian for the new rows ----
         if (have_a && tid < CVVDP_B3_RB * (CVVDP_B3_SW / 4)) {
             const int gy = a0 + b_r, gxb = x0 + b_xg * 4;
@@ -1714,7 +1730,7 @@ __global__ void __launch_bounds__(CVVDP_B3_THREADS, 2) k_band3(const __grid_cons
         }
         __syncthreads();
         // mm is consumed: prefetch the test rows of the next step into its place
-        if (more) band3_issue(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B3_RB, a_end, ex0, tid, 0, CVVDP_B3_RB, true);
+        if (more) band3_issue<EW>(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B3_RB, a_end, ex0, tid, 0, CVVDP_B3_RB, true);
         // ---- phase C: vertical pass, masking, clamp, pooling for the rows whose window is complete ----
         if (tid < 2 * CVVDP_B3_SW) {
             const int gx = x0 + c_ix;

@@ -221,6 +221,9 @@ int cvvdp_b200_set_feature_output(cvvdp_b200_ctx *ctx, float *features_dev);
 /* Column-strip width of the band kernel chosen for pyramid level `level` of the current plan (116: wide-strip
  * kernel, 52: narrow-strip kernel, 0: baseband or no plan).  Introspection for tests and profiling only. */
 int cvvdp_b200_band_strip_width(const cvvdp_b200_ctx *ctx, int level);
+/* Which band kernel: 2 = k_band2 (default), 3 = k_band3<128> (CVVDP_B200_WIDE), 4 = k_band3<64>
+ * (CVVDP_B200_BAND3_NARROW), 0 = baseband or no plan. */
+int cvvdp_b200_band_kernel_id(const cvvdp_b200_ctx *ctx, int level);
 
 #ifdef __cplusplus
 }
