@@ -36,6 +36,7 @@ struct LevelBuf {
     TensorMap3D tm_reduce_in;  // box {63 px, 19 rows, 1 plane}
     TensorMap3D tm_reduce_in16;  // box {63 px, 35 rows, 1 plane} (TY = 16 variant)
     bool tm_ok = false;
+    bool tm16_ok = false;
 };
 
 struct Staging {
@@ -508,7 +509,7 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         LaunchScope ls(ctx, st, CVVDP_K_REDUCE, i, (double)pairs * 2 * 16.0 * ((double)ra.h * ra.w + (double)ra.hc * ra.wc));
         static const bool no_tma_reduce = getenv("CVVDP_B200_NO_TMA") != nullptr;
         if (ctx->lv[i].tm_ok && !no_tma_reduce) {  // persistent, TMA-staged, double-buffered
-            const bool ty16 = getenv("CVVDP_B200_REDUCE_TY16") != nullptr && ra.hc >= 64;  // A/B switch (unmeasured)
+            const bool ty16 = getenv("CVVDP_B200_REDUCE_TY16") != nullptr && ra.hc >= 64 && ctx->lv[i].tm16_ok;  // A/B switch (unmeasured)
             const int ty = ty16 ? 16 : 8;
             Reduce2Args r2;
             r2.tm_in = ty16 ? ctx->lv[i].tm_reduce_in16 : ctx->lv[i].tm_reduce_in;
@@ -1006,8 +1007,9 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.lut = (float4 *)(base + off_l[i]);
         lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_EW, CVVDP_B2_RB) &&
                    make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_CC, CVVDP_B2_CR) &&
-                   make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<8>::IH, 1) &&
-                   make_tensor_map(&lv.tm_reduce_in16, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<16>::IH, 1);
+                   make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<8>::IH, 1);
+        // the A/B variant's map must never take the default path down with it
+        lv.tm16_ok = lv.tm_ok && make_tensor_map(&lv.tm_reduce_in16, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<16>::IH, 1);
         float rows[4][CVVDP_CSF_LUT_N];
         for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
         float packed[CVVDP_CSF_LUT_N][4];
