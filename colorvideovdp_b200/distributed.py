@@ -88,21 +88,25 @@ def predict_frame_sharded_exchange(metric, test_own, ref_own, n_frames, frames_p
         win[:, :, lo - wlo:hi - wlo].copy_(own, non_blocking=True)  # the only host->device traffic
         wins.append(win)
     if world > 1 and transfers:
-        ops, landing = [], []
+        # One message per (transfer, video, batch item, channel): win[b, c, f_lo:f_hi] is a contiguous run of
+        # whole frames, so it goes on the wire and lands in place without staging copies, and no message
+        # comes near 2 GiB (8 items x 15 4K frames of one video in one piece would be 3 GB).
+        ops = []
         for src, dst, flo, fhi in transfers:
-            for k, win in enumerate(wins):
-                if src == rank:  # frames are the 3rd axis: stage a contiguous copy for the wire
-                    buf = win[:, :, flo - wlo:fhi - wlo].contiguous()
-                    ops.append(dist.P2POp(dist.isend, buf, dst, group=group, tag=2 * flo + k))
-                elif dst == rank:
-                    buf = torch.empty(win.shape[:2] + (fhi - flo,) + win.shape[3:], dtype=win.dtype, device=dev)
-                    ops.append(dist.P2POp(dist.irecv, buf, src, group=group, tag=2 * flo + k))
-                    landing.append((win, flo, fhi, buf))
+            if rank not in (src, dst):
+                continue
+            for win in wins:
+                for b in range(win.shape[0]):
+                    for c in range(win.shape[1]):
+                        piece = win[b, c, flo - wlo:fhi - wlo]
+                        assert piece.is_contiguous()
+                        if src == rank:
+                            ops.append(dist.P2POp(dist.isend, piece, dst, group=group))
+                        else:
+                            ops.append(dist.P2POp(dist.irecv, piece, src, group=group))
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        for win, flo, fhi, buf in landing:
-            win[:, :, flo - wlo:fhi - wlo].copy_(buf)
     resident = True if dev.type != "cuda" else None  # mock device in the CPU tests: keep the resident code path
     Q, _ = metric.q_per_ch_from_tensors(wins[0], wins[1], n_frames, frames_per_second, (lo, hi), wlo, _resident=resident)
     Q = Q.to(metric.device)
