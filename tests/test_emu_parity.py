@@ -296,3 +296,18 @@ def test_reduce_tile_variants_are_bit_identical(mock_device, monkeypatch):
     monkeypatch.setenv("CVVDP_B200_REDUCE_TY16", "1")
     _, s16 = cv.cvvdp(display_name="standard_fhd").predict(tst, ref, frames_per_second=30)
     assert np.array_equal(s8["Q_per_ch"], s16["Q_per_ch"])
+
+
+@pytest.mark.parametrize("dtype,fps", [("f32", 60), ("f16", 30), ("f32", 24)])
+def test_two_stage_temporal_kernel_float_inputs(dtype, fps, mock_device):
+    """fp32 / fp16 clips with whole 64-pixel warp segments: the non-table variant of the two-stage temporal
+    kernel (per-pixel EOTF in the rolled front end, 2- and 4-byte raw stage, more pieces than lanes)."""
+    tst, ref = synth.make_pair_u8(80 + fps, 10, 16, 128)
+    tst, ref = tst.astype(np.float32) / 255, ref.astype(np.float32) / 255
+    if dtype == "f16":
+        tst, ref = tst.astype(np.float16), ref.astype(np.float16)
+    m = cv.cvvdp(display_name="standard_4k")
+    jod, stats = m.predict(tst, ref, frames_per_second=fps)
+    jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_4k")
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"{dtype} {fps}")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL

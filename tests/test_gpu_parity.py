@@ -50,6 +50,8 @@ CASES = [  # (seed, F, H, W, fps, display, padding, dtype)
     (34, 20, 100, 180, 60, "standard_hdr_pq", "replicate", "u16"),
     (35, 5, 270, 480, 120, "standard_4k", "replicate", "f16"),     # fl=31
     (36, 3, 97, 33, 25, "standard_phone", "symmetric", "u8"),      # tiles with ragged edges, tall image
+    (37, 20, 64, 128, 60, "standard_4k", "replicate", "f32"),      # whole 64-pixel segments: two-stage temporal kernel, fp32 input
+    (38, 12, 48, 128, 30, "standard_fhd", "symmetric", "f16"),     # two-stage temporal kernel, fp16 input, 9 taps
 ]
 
 
