@@ -311,3 +311,17 @@ def test_two_stage_temporal_kernel_float_inputs(dtype, fps, mock_device):
     jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_4k")
     gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"{dtype} {fps}")
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
+
+
+@pytest.mark.parametrize("F,H,W,fps", [(1, 8, 8, 0), (1, 7, 40, 0), (1, 6, 64, 0), (3, 13, 17, 30), (1, 4, 4, 0),
+                                       (2, 5, 300, 24), (1, 300, 5, 0)])
+def test_tiny_and_degenerate_sizes(F, H, W, fps, mock_device):
+    """Two- and three-band pyramids, levels too small for the phase-uncertainty blur (h or w <= 6,
+    cvvdp_metric.py:965), one-strip / one-segment grids, extreme aspect ratios.  The reference accepts all
+    of these (checked in the build container: oracle == reference within 1 % of the gate)."""
+    tst, ref = synth.make_pair_u8(90 + H + W, F, H, W)
+    m = cv.cvvdp(display_name="standard_fhd")
+    jod, stats = m.predict(tst, ref, frames_per_second=fps)
+    jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd")
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"{F}x{H}x{W}")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
