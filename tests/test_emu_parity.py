@@ -94,16 +94,17 @@ def test_dim_orders_and_strided_views(mock_device):
     assert float(j0) == float(j1) == float(j2)
 
 
-def test_plugin_video_source_matches_fast_path(mock_device):
+@pytest.mark.parametrize("H,W", [(36, 52), (32, 64)])  # (32, 64): whole warp segments -> two-stage temporal kernel on DKL input
+def test_plugin_video_source_matches_fast_path(H, W, mock_device):
     """A third-party video_source (frames pulled one by one in DKLd65) must agree with the fused path."""
-    tst, ref = synth.make_pair_u8(6, 7, 36, 52)
+    tst, ref = synth.make_pair_u8(6, 7, H, W)
     m = cv.cvvdp(display_name="standard_fhd")
     _, fast = m.predict(tst, ref, frames_per_second=30)
     dm, P = O.Display("standard_fhd"), None
 
     class OracleFrontendSource(cv.video_source):
         def get_video_size(self):
-            return (36, 52, 7)
+            return (H, W, 7)
 
         def get_frames_per_second(self):
             return 30
