@@ -1,6 +1,6 @@
 #!/bin/bash
 # Quick A/B on one GPU: device-resident bench only, once per environment setting given as arguments
-# (e.g. ./scripts_gpu_quick.sh "" "CVVDP_B200_NO_LOCKSTEP=1").
+# (e.g. ./tools/gpu_quick.sh "" "CVVDP_B200_NO_LOCKSTEP=1").
 mkdir -p gpurun_out
 : > gpurun_out/quick.txt
 timeout 120 python __graft_entry__.py --smoke >> gpurun_out/quick.txt 2>&1
