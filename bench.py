@@ -316,13 +316,12 @@ def main():
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         do_e2e = bool(flag.item())
     if do_e2e:
-        # Host-side data placement of the sharded job.  Short shards (history window >= 1.5x the shard, i.e. 4 or
-        # more ranks at 60 fps): every rank's host memory holds only the frames it owns and the fl-1 history frames
-        # come from their owners over NVLink (NCCL send/recv) -- each byte crosses PCIe once.  Long shards: the
-        # history is small next to the shard, so the rank uploads its whole window through the streaming C-ABI
-        # path, which overlaps the upload with compute (measured at N=2: 160 ms streamed vs 171 ms exchanged).
-        # The exchange path is opt-in (--e2e-exchange): it ran at N=2 (171 ms vs 160 ms streamed) but the one N=8
-        # attempt of this round did not finish within the GPU budget, so the proven streaming path stays default.
+        # Host-side data placement of the sharded job.  Default: every rank uploads its whole window (shard + fl-1
+        # history frames) through the streaming C-ABI path, which overlaps the upload with compute.
+        # --e2e-exchange (opt-in, for short shards, i.e. 4 or more ranks at 60 fps): every rank's host memory holds
+        # only the frames it owns and the history frames come from their owners over NVLink (NCCL send/recv), so
+        # each byte crosses PCIe once.  It ran at N=2 (171 ms vs 160 ms streamed); the one N=8 attempt of round 1
+        # did not finish within the GPU budget, so it is not the default until it has been seen to work there.
         exchange = args.e2e_exchange and world > 1 and (whi - wlo) >= 1.5 * (hi - lo)
         if exchange:
             own_t, own_r = tst[:, :, lo - wlo:hi - wlo], ref[:, :, lo - wlo:hi - wlo]
