@@ -455,8 +455,7 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_stg(const T
     if (p - lane >= npix) return;  // whole warps only (npix % 32 == 0)
     const ClipView &cv = a.clip[v];
     const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
-    const int row_bytes = 32 * esz;            // one (channel, frame) segment of this warp
-    const int frame_bytes = a.cin * row_bytes;  // <= 384
+    const int row_bytes = 32 * esz;            // one (channel, frame) segment of this warp (a frame: cin of them, <= 384 bytes)
     const int cpc = row_bytes / 16;             // 16-byte pieces per channel segment
     const int npieces = a.cin * cpc;            // lanes that copy
     unsigned char *wst = s_stage + warp * (CVVDP_TSTG_DEPTH * 3 * 32 * 4);
