@@ -14,6 +14,19 @@
 
 using namespace cvvdp;
 
+#ifndef CVVDP_BAND_EW_DEFAULT
+#define CVVDP_BAND_EW_DEFAULT 64      // strip geometry of the band kernel (B2Geom)
+#endif
+#ifndef CVVDP_BAND_CF_DEFAULT
+#define CVVDP_BAND_CF_DEFAULT false   // conflict-free phase A
+#endif
+#ifndef CVVDP_BAND_PA_DEFAULT
+#define CVVDP_BAND_PA_DEFAULT false   // power of the difference term in phase A
+#endif
+#ifndef CVVDP_BAND_LAG_DEFAULT
+#define CVVDP_BAND_LAG_DEFAULT false  // phase C trails by 16 rows (no barrier between phases B and C)
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -29,14 +42,11 @@ struct LevelBuf {
     float4 *lut = nullptr;      // [32]
     int tiles_x = 0, tiles_y = 0;  // band kernel grid: column strips x row segments
     int seg_rows = 0;
-    int band3 = 0;                 // band kernel: 0 = k_band2 (default); 128 / 64 = k_band3<EW> (opt-in variants)
     int do_blur = 0;
     TensorMap3D tm;  // fp32 view [planes][h][4w] of g; box depends on the role (see make_tensor_map)
     TensorMap3D tm_as_coarse;
     TensorMap3D tm_reduce_in;  // box {63 px, 19 rows, 1 plane}
-    TensorMap3D tm_reduce_in16;  // box {63 px, 35 rows, 1 plane} (TY = 16 variant)
     bool tm_ok = false;
-    bool tm16_ok = false;
 };
 
 struct Staging {
@@ -62,6 +72,8 @@ struct cvvdp_b200_ctx {
     int blur_pad = 0;
     int max_smem_optin = 0;
     int num_sms = 148;
+    int band_ew = CVVDP_BAND_EW_DEFAULT;   // band kernel strip geometry of the current plan
+    int band_variant = -1;                 // A/B builds: CVVDP_B200_BAND_VARIANT
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;
     Staging stage[2];
     float *feat_out = nullptr;    // caller's device buffer for the feature tensors (feature mode)
@@ -364,6 +376,48 @@ ClipView to_view(const cvvdp_b200_clip *c) {
     return v;
 }
 
+// ---- band kernel dispatch ------------------------------------------------------------------------
+// Strip geometry (EW) and the conflict-free phase A (CF) are fixed per plan (ctx->band_ew / band_cf); the
+// level-dependent flags (blur, heat map, beta == 2) and the feature mode select the instantiation.
+template <int EW, bool CF, bool PA, bool LAG, bool FEAT>
+void launch_band_v(const BandArgs &ba, dim3 grid, cudaStream_t st, int variant) {
+    typedef void (*BandFn)(const BandArgs);
+    static const BandFn table[8] = {
+        k_band2<EW, CF, PA, LAG, false, false, false, FEAT>, k_band2<EW, CF, PA, LAG, false, false, true, FEAT>,
+        k_band2<EW, CF, PA, LAG, false, true, false, FEAT>,  k_band2<EW, CF, PA, LAG, false, true, true, FEAT>,
+        k_band2<EW, CF, PA, LAG, true, false, false, FEAT>,  k_band2<EW, CF, PA, LAG, true, false, true, FEAT>,
+        k_band2<EW, CF, PA, LAG, true, true, false, FEAT>,   k_band2<EW, CF, PA, LAG, true, true, true, FEAT>};
+    static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+    typedef Band2Smem<EW, B2Lag<LAG>::DFR> Smem;
+    BandFn kfn = table[variant];
+    if (!attr_set[variant]) {  // one context per device and process in practice; the attribute is per function
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        attr_set[variant] = true;
+    }
+    CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Smem), st, ba);
+}
+
+#define CVVDP_BAND_DEFAULTS CVVDP_BAND_EW_DEFAULT, CVVDP_BAND_CF_DEFAULT, CVVDP_BAND_PA_DEFAULT, CVVDP_BAND_LAG_DEFAULT
+void launch_band(cvvdp_b200_ctx *ctx, const BandArgs &ba, dim3 grid, cudaStream_t st, int variant, bool feat) {
+    if (feat) {
+        launch_band_v<CVVDP_BAND_DEFAULTS, true>(ba, grid, st, variant);
+        return;
+    }
+#ifdef CVVDP_BAND_AB  // A/B builds carry several (geometry, CF, PA, LAG) combinations: bit 0 CF, 1 EW60, 2 PA, 3 LAG
+    switch (ctx->band_variant) {
+        case 0: return launch_band_v<64, false, false, false, false>(ba, grid, st, variant);
+        case 3: return launch_band_v<60, true, false, false, false>(ba, grid, st, variant);
+        case 5: return launch_band_v<64, true, true, false, false>(ba, grid, st, variant);
+        case 7: return launch_band_v<60, true, true, false, false>(ba, grid, st, variant);
+        case 11: return launch_band_v<60, true, false, true, false>(ba, grid, st, variant);
+        case 15: return launch_band_v<60, true, true, true, false>(ba, grid, st, variant);
+        default: break;
+    }
+#endif
+    (void)ctx;
+    launch_band_v<CVVDP_BAND_DEFAULTS, false>(ba, grid, st, variant);
+}
+
 // One block of frames [f0, f1) (f1 - f0 <= block_frames), inputs resident on the device.
 int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref, int f0, int f1,
               float *q_dev, void *hm_dev, cudaStream_t st, int ring = 0) {
@@ -415,87 +469,57 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         fill_yuv(job.yuv, job.width, job.height, &ta.yuv);
         const bool use_lut = !is_yuv && job.dtype == CVVDP_DTYPE_U8 &&
                              (e == CVVDP_EOTF_SRGB || e == CVVDP_EOTF_PQ || e == CVVDP_EOTF_LINEAR || e == CVVDP_EOTF_GAMMA);
-        // staged (cp.async) variant: dense, 16-byte aligned planes and whole warps
-        bool staged = !is_yuv && npix % 32 == 0 && job.in_channels <= 3;
-        static const bool no_stage = getenv("CVVDP_B200_NO_TSTAGE") != nullptr;
-        if (no_stage) staged = false;
-        for (int v = 0; v < 2 && staged; ++v) {
+        // two-stage packed kernel: dense, 16-byte aligned planes made of whole 64-pixel warp segments
+        bool dense = !is_yuv && npix % 64 == 0 && job.in_channels <= 3;
+        for (int v = 0; v < 2 && dense; ++v) {
             const ClipView &cvw = ta.clip[v];
             const long long es = (long long)dtype_size(job.dtype);
-            if (cvw.s[4] != 1 || cvw.s[3] != job.width) staged = false;
-            if (((uintptr_t)cvw.data) % 16 || (cvw.s[0] * es) % 16 || (cvw.s[1] * es) % 16 || (cvw.s[2] * es) % 16) staged = false;
+            if (cvw.s[4] != 1 || cvw.s[3] != job.width) dense = false;
+            if (((uintptr_t)cvw.data) % 16 || (cvw.s[0] * es) % 16 || (cvw.s[1] * es) % 16 || (cvw.s[2] * es) % 16) dense = false;
         }
-        // packed two-pixels-per-thread variant: additionally whole 64-pixel warp segments
-        static const bool no_x2 = getenv("CVVDP_B200_NO_TX2") != nullptr;
-        const bool packed = staged && !no_x2 && npix % 64 == 0;
-        // A/B switch: measured slower than the 4-warp CTAs (15.1 vs 14.4 ms per 120 4K frames on the same box), off by default
-        static const bool want_lockstep = getenv("CVVDP_B200_LOCKSTEP") != nullptr;
-        const bool lockstep = want_lockstep && npix % (64 * 12) == 0;
-        dim3 grid_x12((unsigned)(npix / (64 * 12)), (unsigned)(B * 2));
-        dim3 grid_x2((unsigned)((npix / 64 + CVVDP_TX2_THREADS / 32 - 1) / (CVVDP_TX2_THREADS / 32)), (unsigned)(B * 2));
-        // two-stage variant (rolled front end, unrolled FIR only): needs its dynamic shared memory
-        static const bool no_2s = getenv("CVVDP_B200_NO_T2S") != nullptr;  // A/B switch
         const int t_esz = use_lut ? 1 : (int)dtype_size(job.dtype);
         const size_t smem_2s = t2s_smem_bytes(info.filter_len, t_esz);
         bool taps_symmetric = true;  // exact: the two-stage kernel adds mirrored frames before multiplying
         for (int c = 0; c < 4; ++c)
             for (int k = 0; k < info.filter_len / 2; ++k)
                 if (ta.taps[c][k] != ta.taps[c][info.filter_len - 1 - k]) taps_symmetric = false;
-        const bool two_stage = packed && !no_2s && info.filter_len >= 3 && taps_symmetric;
+        static const bool force_generic = getenv("CVVDP_B200_GENERIC_TEMPORAL") != nullptr;  // test hook: exercise the fallback
+        const bool two_stage = dense && info.filter_len >= 3 && info.filter_len <= 17 && taps_symmetric && !force_generic;
         dim3 grid_2s((unsigned)((npix / 64 + CVVDP_T2S_THREADS / 32 - 1) / (CVVDP_T2S_THREADS / 32)), (unsigned)(B * 2));
-#define CVVDP_TEMPORAL_CASE(FLV)                                                              \
-    case FLV: {                                                                               \
-        if (two_stage && use_lut) {                                                           \
-            auto kfn = k_temporal_2s<FLV, true>;                                              \
+        bool launched = false;
+#define CVVDP_TEMPORAL_CASE(FLV)                                                                  \
+    case FLV: {                                                                                   \
+        if (use_lut) {                                                                            \
+            auto kfn = k_temporal_2s<FLV, true>;                                                  \
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2s); \
-            CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);             \
-        } else if (two_stage) {                                                               \
-            auto kfn = k_temporal_2s<FLV, false>;                                             \
+            CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);                 \
+        } else {                                                                                  \
+            auto kfn = k_temporal_2s<FLV, false>;                                                 \
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2s); \
-            CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);             \
-        } else if (packed && use_lut && lockstep) {                                           \
-            auto kfn = k_temporal_x2<FLV, true, 12>;                                          \
-            CVVDP_LAUNCH(kfn, grid_x12, dim3(12 * 32), 0, st, ta);                            \
-        } else if (packed && use_lut) {                                                       \
-            auto kfn = k_temporal_x2<FLV, true, 4>;                                           \
-            CVVDP_LAUNCH(kfn, grid_x2, dim3(CVVDP_TX2_THREADS), 0, st, ta);                   \
-        } else if (packed) {                                                                  \
-            auto kfn = k_temporal_x2<FLV, false, 4>;                                          \
-            CVVDP_LAUNCH(kfn, grid_x2, dim3(CVVDP_TX2_THREADS), 0, st, ta);                   \
-        } else if (staged && use_lut) {                                                       \
-            auto kfn = k_temporal_stg<FLV, true>;                                             \
-            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
-        } else if (staged) {                                                                  \
-            auto kfn = k_temporal_stg<FLV, false>;                                            \
-            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
-        } else if (use_lut) {                                                                 \
-            auto kfn = k_temporal_reg<FLV, true>;                                             \
-            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
-        } else {                                                                              \
-            auto kfn = k_temporal_reg<FLV, false>;                                            \
-            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), 0, st, ta);                 \
-        }                                                                                     \
+            CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);                 \
+        }                                                                                         \
+        launched = true;                                                                          \
     } break;
-        switch (info.filter_len) {
-#ifndef CVVDP_DEV_FAST  // development builds keep only 30 and 60 fps specialisations (the rest takes the generic kernel)
-            CVVDP_TEMPORAL_CASE(1)
-            CVVDP_TEMPORAL_CASE(3)
-            CVVDP_TEMPORAL_CASE(5)
-            CVVDP_TEMPORAL_CASE(7)
-            CVVDP_TEMPORAL_CASE(11)
-            CVVDP_TEMPORAL_CASE(13)
-            CVVDP_TEMPORAL_CASE(15)
+        if (two_stage) {
+            switch (info.filter_len) {
+#ifndef CVVDP_DEV_FAST  // development builds keep only the 30 and 60 fps specialisations
+                CVVDP_TEMPORAL_CASE(3)
+                CVVDP_TEMPORAL_CASE(5)
+                CVVDP_TEMPORAL_CASE(7)
+                CVVDP_TEMPORAL_CASE(11)
+                CVVDP_TEMPORAL_CASE(13)
+                CVVDP_TEMPORAL_CASE(15)
 #endif
-#ifndef CVVDP_DEV_NO_TEMPORAL  // SASS-inspection builds of the other kernels
-            CVVDP_TEMPORAL_CASE(9)
-            CVVDP_TEMPORAL_CASE(17)
-#endif
-            default: {  // long filters (> 64 fps): generic shared-memory ring
-                auto kfn = k_temporal;
-                CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
+                CVVDP_TEMPORAL_CASE(9)
+                CVVDP_TEMPORAL_CASE(17)
+                default: break;
             }
         }
 #undef CVVDP_TEMPORAL_CASE
+        if (!launched) {  // images, strided / permuted views, planar YUV, filters beyond 17 taps (> 64 fps)
+            auto kfn = k_temporal;
+            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
+        }
     }
     // ---- Gaussian pyramid ----
     for (int i = 0; i + 1 < L; ++i) {
@@ -507,27 +531,20 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ra.hc = ctx->lv[i + 1].h;
         ra.wc = ctx->lv[i + 1].w;
         LaunchScope ls(ctx, st, CVVDP_K_REDUCE, i, (double)pairs * 2 * 16.0 * ((double)ra.h * ra.w + (double)ra.hc * ra.wc));
-        static const bool no_tma_reduce = getenv("CVVDP_B200_NO_TMA") != nullptr;
+        static const bool no_tma_reduce = getenv("CVVDP_B200_NO_TMA") != nullptr;  // test hook: exercise the fallbacks
         if (ctx->lv[i].tm_ok && !no_tma_reduce) {  // persistent, TMA-staged, double-buffered
-            const bool ty16 = getenv("CVVDP_B200_REDUCE_TY16") != nullptr && ra.hc >= 64 && ctx->lv[i].tm16_ok;  // A/B switch (unmeasured)
-            const int ty = ty16 ? 16 : 8;
             Reduce2Args r2;
-            r2.tm_in = ty16 ? ctx->lv[i].tm_reduce_in16 : ctx->lv[i].tm_reduce_in;
+            r2.tm_in = ctx->lv[i].tm_reduce_in;
             r2.out = ra.out;
             r2.h = ra.h;
             r2.w = ra.w;
             r2.hc = ra.hc;
             r2.wc = ra.wc;
             r2.planes = pairs * 2;
-            const long long tiles = (long long)((ra.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX) * ((ra.hc + ty - 1) / ty) * r2.planes;
-            const int grid2 = (int)std::min<long long>(tiles, (long long)ctx->num_sms * (ty16 ? 2 : 4));
-            if (ty16) {
-                auto kfn = k_reduce2<16>;
-                CVVDP_LAUNCH(kfn, dim3(grid2), dim3(256), sizeof(Reduce2Smem<16>), st, r2);
-            } else {
-                auto kfn = k_reduce2<8>;
-                CVVDP_LAUNCH(kfn, dim3(grid2), dim3(256), sizeof(Reduce2Smem<8>), st, r2);
-            }
+            const long long tiles = (long long)((ra.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX) * ((ra.hc + 7) / 8) * r2.planes;
+            const int grid2 = (int)std::min<long long>(tiles, (long long)ctx->num_sms * 4);
+            auto kfn = k_reduce2<8>;
+            CVVDP_LAUNCH(kfn, dim3(grid2), dim3(256), sizeof(Reduce2Smem<8>), st, r2);
         } else {
             dim3 grid((ra.wc + CVVDP_RTX - 1) / CVVDP_RTX, (ra.hc + CVVDP_RTY - 1) / CVVDP_RTY, pairs * 2);
             auto kfn = k_reduce;
@@ -571,6 +588,7 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ba.p = P.mask_p;
         for (int k = 0; k < 16; ++k) ba.X[k] = powf(2.f, P.xcm_weights[k]);
         ba.dmax = powf(10.f, P.d_max);
+        ba.inv_dmax = 1.0f / ba.dmax;
         ba.eps = eps;
         ba.beta = P.beta;
         for (int c = 0; c < 4; ++c) ba.hm_w[c] = ch_w[c] * t_int;
@@ -587,48 +605,8 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         LaunchScope ls(ctx, st, CVVDP_K_BAND, i,
                        (double)pairs * 2 * 16.0 * ((double)ba.h * ba.w + (double)ba.hc * ba.wc) +
                            (do_hm ? (double)pairs * 4.0 * ba.h * ba.w : 0.0));
-        if (do_feat) {  // feature mode: the narrow-strip kernel with the three extra planes
-            const int vf = (ba.do_blur ? 4 : 0) | (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
-            void (*kf[8])(const BandArgs) = {k_band2<false, false, false, true>, k_band2<false, false, true, true>,
-                                             k_band2<false, true, false, true>,  k_band2<false, true, true, true>,
-                                             k_band2<true, false, false, true>,  k_band2<true, false, true, true>,
-                                             k_band2<true, true, false, true>,   k_band2<true, true, true, true>};
-            auto kfn = kf[vf];
-            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Band2Smem), st, ba);
-            continue;
-        }
-        if (lv.band3) {
-            const int v3 = (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
-            if (lv.band3 == 128) {
-                void (*k3[4])(const BandArgs) = {k_band3<128, false, false>, k_band3<128, false, true>, k_band3<128, true, false>,
-                                                 k_band3<128, true, true>};
-                auto kfn = k3[v3];
-                CVVDP_LAUNCH(kfn, grid, dim3(B3Geom<128>::THREADS), sizeof(Band3Smem<128>), st, ba);
-            } else {
-                void (*k3[4])(const BandArgs) = {k_band3<64, false, false>, k_band3<64, false, true>, k_band3<64, true, false>,
-                                                 k_band3<64, true, true>};
-                auto kfn = k3[v3];
-                CVVDP_LAUNCH(kfn, grid, dim3(B3Geom<64>::THREADS), sizeof(Band3Smem<64>), st, ba);
-            }
-            continue;
-        }
         const int variant = (ba.do_blur ? 4 : 0) | (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
-#define CVVDP_BAND_CASE(V)                                                                         \
-    case V: {                                                                                      \
-        auto kfn = k_band2<((V) & 4) != 0, ((V) & 2) != 0, ((V) & 1) != 0>;                        \
-        CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Band2Smem), st, ba);                \
-    } break;
-        switch (variant) {
-            CVVDP_BAND_CASE(0)
-            CVVDP_BAND_CASE(1)
-            CVVDP_BAND_CASE(2)
-            CVVDP_BAND_CASE(3)
-            CVVDP_BAND_CASE(4)
-            CVVDP_BAND_CASE(5)
-            CVVDP_BAND_CASE(6)
-            CVVDP_BAND_CASE(7)
-        }
-#undef CVVDP_BAND_CASE
+        launch_band(ctx, ba, grid, st, variant, do_feat);
     }
     {
         BasebandArgs bb;
@@ -804,27 +782,8 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
         cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming);
     }
-    {
-        void (*kb[8])(const BandArgs) = {k_band2<false, false, false>, k_band2<false, false, true>, k_band2<false, true, false>,
-                                         k_band2<false, true, true>,   k_band2<true, false, false>, k_band2<true, false, true>,
-                                         k_band2<true, true, false>,   k_band2<true, true, true>};
-        for (auto k : kb) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
-        void (*kf[8])(const BandArgs) = {k_band2<false, false, false, true>, k_band2<false, false, true, true>,
-                                         k_band2<false, true, false, true>,  k_band2<false, true, true, true>,
-                                         k_band2<true, false, false, true>,  k_band2<true, false, true, true>,
-                                         k_band2<true, true, false, true>,   k_band2<true, true, true, true>};
-        for (auto k : kf) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band2Smem));
-        void (*k3w[4])(const BandArgs) = {k_band3<128, false, false>, k_band3<128, false, true>, k_band3<128, true, false>,
-                                          k_band3<128, true, true>};
-        for (auto k : k3w) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band3Smem<128>));
-        void (*k3n[4])(const BandArgs) = {k_band3<64, false, false>, k_band3<64, false, true>, k_band3<64, true, false>,
-                                          k_band3<64, true, true>};
-        for (auto k : k3n) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Band3Smem<64>));
-    }
     auto kr2 = k_reduce2<8>;
     cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem<8>));
-    auto kr16 = k_reduce2<16>;
-    cudaFuncSetAttribute(kr16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem<16>));
     auto kt = k_temporal;
     cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          std::min(ctx->max_smem_optin, 227 * 1024));
@@ -903,6 +862,17 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     if ((size_t)info.filter_len * 3 * CVVDP_TEMPORAL_THREADS * sizeof(float) > (size_t)std::min(ctx->max_smem_optin, 227 * 1024))
         return fail(ctx, CVVDP_ERR_UNSUPPORTED, "temporal filter of %d taps does not fit in shared memory", info.filter_len);
 
+    ctx->band_ew = CVVDP_BAND_EW_DEFAULT;
+    ctx->band_variant = -1;
+#ifdef CVVDP_BAND_AB
+    if (const char *bv = getenv("CVVDP_B200_BAND_VARIANT")) {  // A/B builds only
+        const int v = atoi(bv);
+        if (!job->features && (v == 0 || v == 3 || v == 5 || v == 7 || v == 11 || v == 15)) {
+            ctx->band_variant = v;
+            ctx->band_ew = (v & 2) ? 60 : 64;
+        }
+    }
+#endif
     // workspace per frame of a block (all batch items)
     const size_t B = (size_t)job->batch;
     const bool do_hm = job->heatmap == CVVDP_HEATMAP_RAW;
@@ -911,7 +881,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         const size_t npix = (size_t)info.band_height[i] * info.band_width[i];
         per_frame += align_up(B * 2 * npix * sizeof(float4), 256);
         const size_t tiles = (i == L - 1) ? 1
-                                          : (size_t)((info.band_width[i] + CVVDP_B2_SW - 1) / CVVDP_B2_SW) *
+                                          : (size_t)((info.band_width[i] + 47) / 48) *
                                                 (info.band_height[i] / 16 + 1);  // upper bound
         per_frame += align_up(B * tiles * 4 * sizeof(float), 256);
         if (do_hm) per_frame += align_up(npix * sizeof(float), 256);
@@ -935,20 +905,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.h = info.band_height[i];
         lv.w = info.band_width[i];
         lv.do_blur = (ctx->blur_pad > 0 && lv.h > ctx->blur_pad && lv.w > ctx->blur_pad) ? 1 : 0;  // cvvdp_metric.py:965
-        {   // strips of 116 columns (levels at least two such strips wide) or 52 columns; the rows are split
-            // into segments only when there are too few CTAs
-            // k_band3 is opt-in: on B200 it measured 4 % slower than k_band2 at 4K (18.9 vs 18.2 ms per 120 frames
-            // on the same box; ncu: 3x the barrier stalls with 8-warp CTAs, +9 instructions per pixel of ring
-            // arithmetic) -- see DESIGN.md section 5.  Read at plan time.
-            const bool want_wide = getenv("CVVDP_B200_WIDE") != nullptr;
-            // CVVDP_B200_BAND3_NARROW: k_band3 at k_band2's strip width (4 CTAs/SM), not yet measured
-            const bool want_narrow3 = getenv("CVVDP_B200_BAND3_NARROW") != nullptr;
-            lv.band3 = 0;
-            if (!job->features && lv.do_blur && lv.h >= 32) {
-                if (want_wide && lv.w >= 2 * B3Geom<128>::SW) lv.band3 = 128;
-                else if (want_narrow3 && lv.w >= 2 * B3Geom<64>::SW) lv.band3 = 64;
-            }
-            const int sw = lv.band3 == 128 ? B3Geom<128>::SW : CVVDP_B2_SW;
+        {   // column strips of EW - 12 pixels; the rows are split into segments only when there are too few CTAs
+            const int sw = ctx->band_ew - 2 * CVVDP_BHALO;
             lv.tiles_x = (lv.w + sw - 1) / sw;
             // the split depends on the level geometry only, never on the batch or block size, so that
             // the summation order (hence every bit of Q_per_ch) is independent of how frames are
@@ -1005,11 +963,9 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.hm = do_hm ? (float *)(base + off_h[i]) : nullptr;
         lv.feat = job->features ? (float4 *)(base + off_f[i]) : nullptr;
         lv.lut = (float4 *)(base + off_l[i]);
-        lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_EW, CVVDP_B2_RB) &&
-                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_B2_CC, CVVDP_B2_CR) &&
+        lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), ctx->band_ew, CVVDP_B2_RB) &&
+                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), ctx->band_ew / 2 + 2, CVVDP_B2_CR) &&
                    make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<8>::IH, 1);
-        // the A/B variant's map must never take the default path down with it
-        lv.tm16_ok = lv.tm_ok && make_tensor_map(&lv.tm_reduce_in16, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<16>::IH, 1);
         float rows[4][CVVDP_CSF_LUT_N];
         for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
         float packed[CVVDP_CSF_LUT_N][4];
@@ -1408,12 +1364,12 @@ int cvvdp_b200_set_feature_output(cvvdp_b200_ctx *ctx, float *features_dev) {
 
 int cvvdp_b200_band_strip_width(const cvvdp_b200_ctx *ctx, int level) {
     if (!ctx || !ctx->planned || level < 0 || level + 1 >= (int)ctx->lv.size()) return 0;
-    return ctx->lv[level].band3 == 128 ? B3Geom<128>::SW : CVVDP_B2_SW;
+    return ctx->band_ew - 2 * CVVDP_BHALO;
 }
 
 int cvvdp_b200_band_kernel_id(const cvvdp_b200_ctx *ctx, int level) {
     if (!ctx || !ctx->planned || level < 0 || level + 1 >= (int)ctx->lv.size()) return 0;
-    return ctx->lv[level].band3 == 128 ? 3 : (ctx->lv[level].band3 == 64 ? 4 : 2);
+    return 2;
 }
 
 int cvvdp_b200_profile_enable(cvvdp_b200_ctx *ctx, int enable) {

@@ -192,13 +192,13 @@ __global__ void __launch_bounds__(256) k_frontend(const FrontendArgs a) {
 // =================================================================================================
 // Temporal stage: front end fused with the causal FIR  (cvvdp_metric.py:453-561)
 // Every input frame is read and EOTF-ed exactly once per block (+ fl-1 history frames at the start of
-// the block).  Five generations of the kernel live here; the host picks the fastest one whose
-// requirements hold (cvvdp_api.cu, run_block):
-//   k_temporal_2s  two pixels per thread (fp32x2), rolled front end + unrolled symmetric FIR   [default]
-//   k_temporal_x2  two pixels per thread, fully unrolled time loop (asymmetric taps)
-//   k_temporal_stg one pixel per thread, cp.async-staged raw values (planes not whole 64-pixel segments)
-//   k_temporal_reg one pixel per thread, direct loads (strided / permuted views, planar YUV)
-//   k_temporal     generic shared-memory ring (more than 17 taps, i.e. above 64 fps)
+// the block).  Two kernels; the host picks (cvvdp_api.cu, run_block):
+//   k_temporal_2s  two pixels per thread (fp32x2), rolled front end + unrolled symmetric FIR: dense,
+//                  16-byte aligned planes of whole 64-pixel segments, 3..17 symmetric taps (8..64 fps)  [default]
+//   k_temporal     generic shared-memory ring: any layout (strided / permuted views, planar YUV), any
+//                  filter length, images
+// (round 1 carried three more generations -- one pixel per thread with direct loads, cp.async-staged, packed
+// but fully unrolled -- all superseded by the two-stage kernel and removed; measurements in DESIGN.md.)
 // =================================================================================================
 struct TemporalArgs {
     ClipView clip[2];
@@ -256,11 +256,6 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
     }
 }
 
-// Fast variant for the common filter lengths (fl = 2*ceil(fps/8)+1 <= 17, i.e. up to 64 fps): the
-// ring lives in registers (the time loop is unrolled by one ring period, so every index is static
-// and the taps are constant-bank FFMA operands), 8-bit inputs go through a 256-entry EOTF table in
-// shared memory built with the exact arithmetic, and the raw values of frame t+1 are prefetched
-// while frame t is filtered.  k_temporal above stays as the generic fallback (any fl).
 __device__ __forceinline__ float bits_as_float(unsigned b) {
 #ifdef __CUDA_ARCH__
     return __uint_as_float(b);
@@ -271,424 +266,16 @@ __device__ __forceinline__ float bits_as_float(unsigned b) {
 #endif
 }
 
-// Raw element bits of one pixel (1 or 3 channels).  Kept as integers so that the load of frame t+1
-// can stay in flight while frame t is filtered: nothing consumes the registers until bits_to_dkl.
-__device__ __forceinline__ unsigned float_as_bits(float f) {
-#ifdef __CUDA_ARCH__
-    return __float_as_uint(f);
-#else
-    unsigned u;
-    memcpy(&u, &f, 4);
-    return u;
-#endif
-}
-template <bool USE_LUT>
-__device__ __forceinline__ void load_bits(const TemporalArgs &a, const ClipView &cv, long long base, int fidx,
-                                          unsigned bits[3], int b = 0, int y = 0, int x = 0) {
-    if (!USE_LUT && a.yuv.chroma != 0) {  // planar YUV: upsample + matrix now, carry the RGB floats
-        float rgb[3];
-        yuv_fetch_rgb(cv, a.yuv, a.dtype, b * cv.s[0] + (long long)fidx * cv.s[2], y, x, rgb);
-        bits[0] = float_as_bits(rgb[0]);
-        bits[1] = float_as_bits(rgb[1]);
-        bits[2] = float_as_bits(rgb[2]);
-        return;
-    }
-    const long long off = base + (long long)fidx * cv.s[2];
-    const long long o1 = a.cin == 3 ? off + cv.s[1] : off, o2 = a.cin == 3 ? off + 2 * cv.s[1] : off;
-    if (USE_LUT || a.dtype == CVVDP_DTYPE_U8) {
-        const unsigned char *p = (const unsigned char *)cv.data;
-        bits[0] = p[off];
-        bits[1] = p[o1];
-        bits[2] = p[o2];
-    } else if (a.dtype == CVVDP_DTYPE_F32) {
-        const unsigned *p = (const unsigned *)cv.data;
-        bits[0] = p[off];
-        bits[1] = p[o1];
-        bits[2] = p[o2];
-    } else {
-        const unsigned short *p = (const unsigned short *)cv.data;
-        bits[0] = p[off];
-        bits[1] = p[o1];
-        bits[2] = p[o2];
-    }
-}
-
-template <bool USE_LUT>
-__device__ __forceinline__ void bits_to_dkl(const TemporalArgs &a, const float *lut, const unsigned bits[3], float &d0,
-                                            float &d1, float &d2) {
-    float v[3];
-    if (USE_LUT) {
-        v[0] = lut[bits[0]];
-        v[1] = lut[bits[1]];
-        v[2] = lut[bits[2]];
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            switch (a.yuv.chroma != 0 ? CVVDP_DTYPE_F32 : a.dtype) {
-                case CVVDP_DTYPE_U8: v[i] = (float)bits[i] / 255.0f; break;
-                case CVVDP_DTYPE_U16: v[i] = (float)bits[i] * (1.0f / 65535.0f); break;
-                case CVVDP_DTYPE_F16: v[i] = half_bits_to_float((unsigned short)bits[i]); break;
-                default: v[i] = bits_as_float(bits[i]);
-            }
-        }
-        eotf_forward(v, a.cin, a.dd);
-    }
-    if (a.cin == 3) {
-        d0 = (v[0] * a.dd.M[0] + v[1] * a.dd.M[1]) + v[2] * a.dd.M[2];
-        d1 = (v[0] * a.dd.M[3] + v[1] * a.dd.M[4]) + v[2] * a.dd.M[5];
-        d2 = (v[0] * a.dd.M[6] + v[1] * a.dd.M[7]) + v[2] * a.dd.M[8];
-    } else {
-        d0 = d1 = d2 = v[0];
-    }
-}
-
 __device__ __forceinline__ int temporal_source_frame(const TemporalArgs &a, int t) {
     if (t >= 0) return t;
     return (a.padding == CVVDP_PAD_REPLICATE) ? 0 : symmetric_frame_index(t, a.F_total);
 }
 
-template <int FL, bool USE_LUT>
-__global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_reg(const TemporalArgs a) {
-    __shared__ float s_lut[256];
-    const int tid = threadIdx.x;
-    if (USE_LUT) {  // exact per-code EOTF: same arithmetic as the per-pixel path
-        float v[1] = {(float)tid / 255.0f};
-        eotf_forward(v, 1, a.dd);
-        s_lut[tid] = v[0];
-        __syncthreads();
-    }
-    const long long npix = (long long)a.H * a.W;
-    const long long p = (long long)blockIdx.x * CVVDP_TEMPORAL_THREADS + tid;
-    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
-    if (p >= npix) return;
-    const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
-    const ClipView &cv = a.clip[v];
-    const long long base = b * cv.s[0] + y * cv.s[3] + x * cv.s[4];
-    const int n = a.f1 - a.f0;
-    float4 *out = a.out + ((long long)b * n * 2 + v) * npix + p;
-    // ring period RP = FL + 1 (even): one spare slot keeps the parity of the unrolled position static,
-    // so the two raw-value register sets (even/odd frames) never have to be moved while a load is in flight
-    constexpr int RP = FL + 1;
-    float r0[RP], r1[RP], r2[RP];
-#pragma unroll
-    for (int i = 0; i < RP; ++i) r0[i] = r1[i] = r2[i] = 0.f;
-    unsigned bits[3];
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-    (void)n;
-    // ---- warm-up: the FL-1 frames before f0 (temporal padding before frame 0) fill slots 0..FL-2 ----
-    int src = temporal_source_frame(a, a.f0 - (FL - 1)), last_src = -1;
-    load_bits<USE_LUT>(a, cv, base, frame_slot(cv, src), bits, b, y, x);
-#pragma unroll
-    for (int s = 0; s < FL - 1; ++s) {
-        if (src != last_src) {
-            bits_to_dkl<USE_LUT>(a, s_lut, bits, d0, d1, d2);
-            last_src = src;
-        }
-        const int nsrc = temporal_source_frame(a, a.f0 - (FL - 1) + s + 1);
-        if (nsrc != src) load_bits<USE_LUT>(a, cv, base, frame_slot(cv, nsrc), bits, b, y, x);
-        src = nsrc;
-        r0[s] = d0;
-        r1[s] = d1;
-        r2[s] = d2;
-    }
-    // ---- steady state: frame t = f0 + j goes to ring slot (FL-1+j) mod RP.  Frames at even j use the raw
-    // set `bits`, odd j the set `bitsB`; the load of frame t+2 is issued into the set that frame t has
-    // just vacated, so every load has two full iterations (~250 instructions of this warp) to land.
-    int nslot = frame_slot(cv, a.f0);  // clip slot of the frame being prefetched, advanced incrementally
-    const int slots = cv.ring > 0 ? cv.ring : 0x7fffffff;
-    unsigned bitsB[3] = {0u, 0u, 0u};
-    nslot = nslot + 1 == slots ? 0 : nslot + 1;
-    if (a.f0 + 1 < a.f1) load_bits<USE_LUT>(a, cv, base, nslot, bitsB, b, y, x);
-    float4 *outp = out;
-    const long long ostep = 2 * npix;
-    for (int tb = a.f0; tb < a.f1; tb += RP) {
-#pragma unroll
-        for (int j = 0; j < RP; ++j) {
-            const int t = tb + j;
-            if (t < a.f1) {  // uniform
-                const int s = (FL - 1 + j) % RP;
-                nslot = nslot + 1 == slots ? 0 : nslot + 1;
-                if ((j & 1) == 0) {
-                    bits_to_dkl<USE_LUT>(a, s_lut, bits, r0[s], r1[s], r2[s]);
-                    if (t + 2 < a.f1) load_bits<USE_LUT>(a, cv, base, nslot, bits, b, y, x);  // prefetch, distance 2
-                } else {
-                    bits_to_dkl<USE_LUT>(a, s_lut, bitsB, r0[s], r1[s], r2[s]);
-                    if (t + 2 < a.f1) load_bits<USE_LUT>(a, cv, base, nslot, bitsB, b, y, x);
-                }
-                float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-#pragma unroll
-                for (int k = 0; k < FL; ++k) {  // tap k <-> frame t-(FL-1)+k <-> slot (s-(FL-1)+k) mod RP
-                    const int sl = (s + RP - (FL - 1) + k) % RP;
-                    o0 = fmaf(a.taps[0][k], r0[sl], o0);
-                    o1 = fmaf(a.taps[1][k], r1[sl], o1);
-                    o2 = fmaf(a.taps[2][k], r2[sl], o2);
-                    o3 = fmaf(a.taps[3][k], r0[sl], o3);
-                }
-                *outp = make_float4(o0, o1, o2, o3);
-                outp += ostep;
-            }
-        }
-    }
-}
-
-// Staged variant: the raw pixels reach the thread through a per-warp ring in shared memory that is
-// filled with cp.async (LDGSTS) CVVDP_TSTG_DEPTH-1 frames ahead, so the prefetch distance is set by
-// `cp.async.wait_group`, not by how the compiler schedules loads and scoreboards.  A warp owns 32
-// consecutive pixels; for every frame a few lanes each copy one 16-byte piece of the warp's
-// (channel, frame) row segment.  Needs dense planes (stride_W = 1, stride_H = W), H*W % 32 == 0 and
-// 16-byte aligned planes -- the host checks that and otherwise launches k_temporal_reg.
-#define CVVDP_TSTG_DEPTH 4
-template <int FL, bool USE_LUT>
-__global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal_stg(const TemporalArgs a) {
-    __shared__ float s_lut[256];
-    __shared__ __align__(16) unsigned char s_stage[(CVVDP_TEMPORAL_THREADS / 32) * CVVDP_TSTG_DEPTH * 3 * 32 * 4];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (USE_LUT) {
-        float v[1] = {(float)tid / 255.0f};
-        eotf_forward(v, 1, a.dd);
-        s_lut[tid] = v[0];
-        __syncthreads();
-    }
-    const long long npix = (long long)a.H * a.W;
-    const long long p = (long long)blockIdx.x * CVVDP_TEMPORAL_THREADS + tid;
-    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
-    if (p - lane >= npix) return;  // whole warps only (npix % 32 == 0)
-    const ClipView &cv = a.clip[v];
-    const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
-    const int row_bytes = 32 * esz;            // one (channel, frame) segment of this warp (a frame: cin of them, <= 384 bytes)
-    const int cpc = row_bytes / 16;             // 16-byte pieces per channel segment
-    const int npieces = a.cin * cpc;            // lanes that copy
-    unsigned char *wst = s_stage + warp * (CVVDP_TSTG_DEPTH * 3 * 32 * 4);
-    // this lane's piece: source byte offset (without the frame term) and destination offset in a stage slot
-    const int pch = lane / cpc, ppart = lane - pch * cpc;
-    const long long wbase = b * cv.s[0] + (p - lane);  // element offset of the warp's first pixel (dense plane)
-    const unsigned char *psrc = (const unsigned char *)cv.data + (wbase + (long long)pch * cv.s[1]) * esz + ppart * 16;
-    const int pdst = pch * row_bytes + ppart * 16;
-    const long long fstride = cv.s[2] * esz;
-    const int n = a.f1 - a.f0;
-    const int NI = (FL - 1) + n;  // iterations: warm-up frames, then the block's frames
-    float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + p;
-    const long long ostep = 2 * npix;
-    constexpr int RP = FL + 1;
-    float r0[RP], r1[RP], r2[RP];
-#pragma unroll
-    for (int i = 0; i < RP; ++i) r0[i] = r1[i] = r2[i] = 0.f;
-
-    // issue the copies of the next iteration (frame t = f0-(FL-1)+pf_it, padded before frame 0) into stage
-    // slot pf_it % DEPTH; from frame f0 on the clip slot advances incrementally (no modulo per frame)
-    int pf_it = 0, pf_slot = frame_slot(cv, a.f0);
-    const int slots = cv.ring > 0 ? cv.ring : 0x7fffffff;
-    auto issue = [&]() {
-        if (pf_it < NI && lane < npieces) {
-            const int slot = pf_it < FL - 1 ? frame_slot(cv, temporal_source_frame(a, a.f0 - (FL - 1) + pf_it)) : pf_slot;
-            cp_async16(wst + (pf_it & (CVVDP_TSTG_DEPTH - 1)) * (3 * 32 * 4) + pdst, psrc + (long long)slot * fstride);
-        }
-        if (pf_it >= FL - 1) pf_slot = pf_slot + 1 == slots ? 0 : pf_slot + 1;
-        ++pf_it;
-        cp_async_commit();
-    };
-    // wait for iteration `it`, read this lane's raw values
-    auto fetch = [&](int it, unsigned bits[3]) {
-        issue();
-        cp_async_wait_n<CVVDP_TSTG_DEPTH - 1>();
-        __syncwarp();
-        const unsigned char *q = wst + (it & (CVVDP_TSTG_DEPTH - 1)) * (3 * 32 * 4);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const unsigned char *qc = q + (a.cin == 3 ? c : 0) * row_bytes;
-            if (esz == 1) bits[c] = qc[lane];
-            else if (esz == 2) bits[c] = ((const unsigned short *)qc)[lane];
-            else bits[c] = ((const unsigned *)qc)[lane];
-        }
-        __syncwarp();  // every lane has read the slot before it is refilled
-    };
-#pragma unroll
-    for (int i = 0; i < CVVDP_TSTG_DEPTH - 1; ++i) issue();
-    unsigned bits[3];
-    int it = 0;
-    // ---- warm-up: slots 0..FL-2 ----
-#pragma unroll
-    for (int s = 0; s < FL - 1; ++s) {
-        fetch(it++, bits);
-        bits_to_dkl<USE_LUT>(a, s_lut, bits, r0[s], r1[s], r2[s]);
-    }
-    // ---- steady state ----
-    for (int tb = a.f0; tb < a.f1; tb += RP) {
-#pragma unroll
-        for (int j = 0; j < RP; ++j) {
-            const int t = tb + j;
-            if (t < a.f1) {  // uniform
-                const int s = (FL - 1 + j) % RP;
-                fetch(it++, bits);
-                bits_to_dkl<USE_LUT>(a, s_lut, bits, r0[s], r1[s], r2[s]);
-                float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-#pragma unroll
-                for (int k = 0; k < FL; ++k) {
-                    const int sl = (s + RP - (FL - 1) + k) % RP;
-                    o0 = fmaf(a.taps[0][k], r0[sl], o0);
-                    o1 = fmaf(a.taps[1][k], r1[sl], o1);
-                    o2 = fmaf(a.taps[2][k], r2[sl], o2);
-                    o3 = fmaf(a.taps[3][k], r0[sl], o3);
-                }
-                *outp = make_float4(o0, o1, o2, o3);
-                outp += ostep;
-            }
-        }
-    }
-    cp_async_wait_all();
-}
-
-// Packed variant of the staged kernel: a thread owns TWO pixels of the warp's 64-pixel segment (lane l:
-// pixels l and l+32, so both 128-bit stores of a warp cover 512 contiguous bytes) and keeps them as the
-// two halves of fp32x2 registers.  The FIR then costs one FFMA2 per (tap, channel) for both pixels --
-// the tap is a uniform-register broadcast operand -- and every staging / addressing instruction is
-// shared by the pair: ~1/3 of the warp instructions of k_temporal_stg per pixel.  The per-lane
-// arithmetic (EOTF table or eotf_forward, matrix order, tap order) is the one of the other variants.
-// Needs what k_temporal_stg needs, with H*W % 64 == 0.
-#define CVVDP_TX2_THREADS 128
-#define CVVDP_TX2_DEPTH 4
-#define CVVDP_TX2_SLOT (3 * 64 * 4)  // bytes of one stage slot: 3 channels x 64 pixels x up to 4 bytes
-template <int FL, bool USE_LUT, int NWARPS>
-__global__ void __launch_bounds__(NWARPS * 32, NWARPS == 4 ? 3 : 1) k_temporal_x2(const __grid_constant__ TemporalArgs a) {
-    constexpr bool CTA_SYNC = NWARPS != 4;  // lockstep variant: one 12-warp CTA per SM
-    __shared__ float s_lut[256];
-    __shared__ __align__(16) unsigned char s_stage[NWARPS * CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (USE_LUT) {
-        for (int i = tid; i < 256; i += NWARPS * 32) {
-            float v[1] = {(float)i / 255.0f};
-            eotf_forward(v, 1, a.dd);
-            s_lut[i] = v[0];
-        }
-        __syncthreads();
-    }
-    const long long npix = (long long)a.H * a.W;
-    const long long wp = ((long long)blockIdx.x * NWARPS + warp) * 64;  // first pixel of the warp
-    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
-    if (wp >= npix) return;  // whole 64-pixel segments only (npix % 64 == 0); CTA_SYNC: npix % (64 NWARPS) == 0, no partial CTA
-    const ClipView &cv = a.clip[v];
-    const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
-    const int row_bytes = 64 * esz;   // one (channel, frame) segment of this warp
-    const int cpc = row_bytes / 16;   // 16-byte pieces per channel segment: 4, 8 or 16
-    const int npieces = a.cin * cpc;  // <= 48: lanes copy one piece, lanes < npieces-32 a second one
-    unsigned char *wst = s_stage + warp * (CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT);
-    const long long fstride = cv.s[2] * esz;
-    const unsigned char *wsrc = (const unsigned char *)cv.data + (b * cv.s[0] + wp) * esz;
-    const int pc0 = lane / cpc, pc1 = (lane + 32) / cpc;
-    const unsigned char *psrc0 = wsrc + (long long)pc0 * cv.s[1] * esz + (lane - pc0 * cpc) * 16;
-    const unsigned char *psrc1 = wsrc + (long long)pc1 * cv.s[1] * esz + (lane + 32 - pc1 * cpc) * 16;
-    const int pdst0 = lane * 16, pdst1 = (lane + 32) * 16;  // channel segments are contiguous in a slot
-    const int n = a.f1 - a.f0;
-    const int NI = (FL - 1) + n;
-    float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + wp + lane;
-    const long long ostep = 2 * npix;
-    constexpr int RP = FL + 1;
-    float2 r0[RP], r1[RP], r2[RP];
-#pragma unroll
-    for (int i = 0; i < RP; ++i) r0[i] = r1[i] = r2[i] = make_float2(0.f, 0.f);
-
-    // Stage bookkeeping: iteration i (frame f0-(FL-1)+i, padded before frame 0) lands in stage slot i % DEPTH.
-    // The copies run DEPTH-1 iterations ahead.  Warm-up iterations resolve the temporal padding (integer
-    // divisions); from iteration FL-1 on the clip slot just advances, so the steady-state loop carries no
-    // padding logic.  (FL-1 warm-up fetches each issue one copy: the warm-up issues cover iterations
-    // < FL-1 + DEPTH-1, hence the `i < FL - 1` test below and a plain increment afterwards.)
-    const int slots = cv.ring > 0 ? cv.ring : 0x7fffffff;
-    int pf_it = 0, pf_slot = frame_slot(cv, a.f0), pf_off = 0, rd_off = 0;
-    auto copy_frame = [&](int slot) {
-        unsigned char *dst = wst + pf_off;
-        if (lane < npieces) cp_async16(dst + pdst0, psrc0 + (long long)slot * fstride);
-        if (lane + 32 < npieces) cp_async16(dst + pdst1, psrc1 + (long long)slot * fstride);
-    };
-    auto advance = [&]() {
-        pf_off = pf_off + CVVDP_TX2_SLOT == CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT ? 0 : pf_off + CVVDP_TX2_SLOT;
-        ++pf_it;
-        cp_async_commit();
-    };
-    auto issue_warm = [&]() {  // any iteration
-        if (pf_it < NI) {
-            if (pf_it < FL - 1) {
-                copy_frame(frame_slot(cv, temporal_source_frame(a, a.f0 - (FL - 1) + pf_it)));
-            } else {
-                copy_frame(pf_slot);
-                pf_slot = pf_slot + 1 == slots ? 0 : pf_slot + 1;
-            }
-        }
-        advance();
-    };
-    auto issue_steady = [&]() {  // iterations >= FL-1 only
-        if (pf_it < NI) {
-            copy_frame(pf_slot);
-            pf_slot = pf_slot + 1 == slots ? 0 : pf_slot + 1;
-        }
-        advance();
-    };
-    // wait for the oldest outstanding iteration, convert this lane's two pixels to DKL
-    auto fetch = [&](float2 &d0, float2 &d1, float2 &d2) {
-        cp_async_wait_n<CVVDP_TX2_DEPTH - 1>();
-        __syncwarp();
-        const unsigned char *q = wst + rd_off;
-        rd_off = rd_off + CVVDP_TX2_SLOT == CVVDP_TX2_DEPTH * CVVDP_TX2_SLOT ? 0 : rd_off + CVVDP_TX2_SLOT;
-        unsigned ba[3], bb[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const unsigned char *qc = q + (a.cin == 3 ? c : 0) * row_bytes;
-            if (esz == 1) {
-                ba[c] = qc[lane];
-                bb[c] = qc[lane + 32];
-            } else if (esz == 2) {
-                ba[c] = ((const unsigned short *)qc)[lane];
-                bb[c] = ((const unsigned short *)qc)[lane + 32];
-            } else {
-                ba[c] = ((const unsigned *)qc)[lane];
-                bb[c] = ((const unsigned *)qc)[lane + 32];
-            }
-        }
-        // every lane has read the slot before it is refilled.  In the 12-warp variant a CTA-wide barrier
-        // replaces __syncwarp: it keeps all warps of the SM at the same place of the fully unrolled (~60 KB)
-        // time loop, so the three warps of a scheduler share one instruction stream through its 6 KB L0
-        // instruction cache (ncu on the 4-warp variant: 2.4 stall cycles per issue waiting for instructions)
-        if (CTA_SYNC) __syncthreads();
-        else __syncwarp();
-        bits_to_dkl<USE_LUT>(a, s_lut, ba, d0.x, d1.x, d2.x);
-        bits_to_dkl<USE_LUT>(a, s_lut, bb, d0.y, d1.y, d2.y);
-    };
-#pragma unroll
-    for (int i = 0; i < CVVDP_TX2_DEPTH - 1; ++i) issue_warm();
-#pragma unroll
-    for (int s = 0; s < FL - 1; ++s) {
-        issue_warm();
-        fetch(r0[s], r1[s], r2[s]);
-    }
-    // here pf_it = FL-1 + DEPTH-1 >= FL-1: only steady issues from now on
-    for (int tb = a.f0; tb < a.f1; tb += RP) {
-#pragma unroll
-        for (int j = 0; j < RP; ++j) {
-            const int t = tb + j;
-            if (t < a.f1) {  // uniform
-                const int s = (FL - 1 + j) % RP;
-                issue_steady();
-                fetch(r0[s], r1[s], r2[s]);
-                float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
-#pragma unroll
-                for (int k = 0; k < FL; ++k) {
-                    const int sl = (s + RP - (FL - 1) + k) % RP;
-                    o0 = fma2(bc2(a.taps[0][k]), r0[sl], o0);
-                    o1 = fma2(bc2(a.taps[1][k]), r1[sl], o1);
-                    o2 = fma2(bc2(a.taps[2][k]), r2[sl], o2);
-                    o3 = fma2(bc2(a.taps[3][k]), r0[sl], o3);
-                }
-                outp[0] = make_float4(o0.x, o1.x, o2.x, o3.x);
-                outp[32] = make_float4(o0.y, o1.y, o2.y, o3.y);
-                outp += ostep;
-            }
-        }
-    }
-    cp_async_wait_all();
-}
-
-// Two-stage variant of the packed kernel.  The fully unrolled time loop of k_temporal_x2 is ~60 KB of
-// straight-line code, twice the SM's 32 KB L1.5 instruction cache: ncu shows it waiting for instructions
-// 2.4 cycles per issue.  Here only the FIR is unrolled.  Time advances in chunks of G = (FL+1)/2 frames:
+// Two-stage packed temporal kernel.  A thread owns TWO pixels of its warp's 64-pixel segment (lane l: pixels
+// l and l+32, so both 128-bit stores of a warp cover 512 contiguous bytes) as the halves of fp32x2 registers;
+// the ring of the last FL frames lives in registers.  Unrolling the whole time loop by one ring period
+// (round 1's first packed kernel) gave ~60 KB of straight-line code, twice the SM's 32 KB L1.5 instruction
+// cache: ncu showed it waiting for instructions 2.4 cycles per issue.  Here only the FIR is unrolled.  Time advances in chunks of G = (FL+1)/2 frames:
 //   stage 1 (a rolled loop, one copy of the code): raw values of the chunk (already in shared memory,
 //            copied with cp.async during the previous chunk) -> EOTF -> DKL -> a per-thread slab of
 //            shared memory (each thread reads back only what it wrote: no synchronisation);
@@ -696,7 +283,7 @@ __global__ void __launch_bounds__(NWARPS * 32, NWARPS == 4 ? 3 : 1) k_temporal_x
 //            slot, 4*FL FFMA2, two 128-bit stores.
 // The unrolled part shrinks to ~25 KB, the front end (including the generic per-pixel EOTF switch of
 // the non-table variant) exists once, and the warps of a CTA never synchronise with each other.
-// Same requirements and the same per-lane arithmetic as k_temporal_x2.
+// Per-lane arithmetic (EOTF table or eotf_forward, matrix order, tap order) as in the generic kernel.
 // One byte from shared memory straight into a 32-bit register (the compiler otherwise packs pairs of
 // 8-bit loads into 16-bit halves and unpacks them again).
 __device__ __forceinline__ unsigned lds_u8(const unsigned char *p) {
@@ -861,7 +448,7 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
                     r1[s] = dkl[(g * 3 + 1) * CVVDP_T2S_THREADS];
                     r2[s] = dkl[(g * 3 + 2) * CVVDP_T2S_THREADS];
                     if (it >= FL - 1) {   // uniform
-                        // the filters are exactly symmetric (the host checks, else k_temporal_x2 runs): frames at
+                        // the filters are exactly symmetric (the host checks, else the generic kernel runs): frames at
                         // mirrored taps are added first, which also lets A-sust and A-trans share the sums
                         // (splitting each sum into two chains for more ILP was tried: +29 instructions per pixel of
                         // rematerialised addresses under register pressure, 13 % slower)
@@ -1097,7 +684,7 @@ __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2
 //   (csf.py:28-51) -> mult-mutual masking with the 13x13 phase-uncertainty Gaussian, cross-channel
 //   pooling and soft clamp (cvvdp_metric.py:817-856, 963-971, 753-764, 945-950) -> spatial
 //   p-norm partial sums (cvvdp_metric.py:722, 1032-1048) [-> per-band heat-map plane, 724-734].
-// The per-pixel helpers below are shared by the strip-marching kernels k_band2 / k_band3 (the first
+// The per-pixel helpers below are used by the strip-marching kernel k_band2 (the first
 // version of this file had a 32x32-tile kernel on top of them; it was 2.7x slower and is gone).
 // =================================================================================================
 #define CVVDP_BHALO 6
@@ -1122,14 +709,15 @@ struct BandArgs {
     float mc;              // 10^mask_c
     float p;
     float dmax;            // 10^d_max
+    float inv_dmax;        // 1 / dmax
     float eps;
     float beta;
     float hm_w[4];         // heat map: channel weights (x image_int)
     float hm_beta, hm_scale;  // beta_tch, 1/band_mul (lpyr_dec.py:308-314)
     int seg_rows;          // k_band2: rows per vertical segment (multiple of 8)
     int use_tma;           // k_band2: stage the rows with TMA (else cp.async)
-    TensorMap3D tm_fine;   // fp32 view [planes][h][4w] of level i,   box {256, 8, 2}
-    TensorMap3D tm_coarse; // fp32 view [planes][hc][4wc] of level i+1, box {136, 6, 2}
+    TensorMap3D tm_fine;   // fp32 view [planes][h][4w] of level i,   box {4 EW, 8, 2}
+    TensorMap3D tm_coarse; // fp32 view [planes][hc][4wc] of level i+1, box {4 CC, 6, 2}
 };
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' padding
@@ -1139,9 +727,12 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' p
 }
 
 // Contrast / CSF / mutual-masking inputs of one pixel (phase 1).
-template <bool FEAT = false>
+// PA: df returns safe_pow(|T'-R'|, p) (the numerator of D, cvvdp_metric.py:855) instead of |T'-R'|: its two MUFU
+// operations per channel then run in phase A, whose XU pipe has slack, instead of phase C, which is XU-bound.
+template <bool FEAT = false, bool PA = false>
 __device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lut, float4 gt, float4 gr, float4 et,
-                                           float4 er, float4 &mm, float4 &df, float4 *feat_t = nullptr, float4 *feat_r = nullptr) {
+                                           float4 er, float4 &mm, float4 &df, float4 *feat_t = nullptr, float4 *feat_r = nullptr,
+                                           float eps_p = 0.f) {
     const float4 lt = gt - et, lr = gr - er;  // Laplacian (lpyr_dec.py:387)
     const float Lt = fmaxf(et.x, 0.01f), Lr = fmaxf(er.x, 0.01f);  // l.394
     const float it = a.mul * f_rcp(Lt), ir = a.mul * f_rcp(Lr);
@@ -1151,8 +742,16 @@ __device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lu
     const float4 cr = make_float4(fminf(cru.x, cl), fminf(cru.y, cl), fminf(cru.z, cl), fminf(cru.w, cl));
     // CSF: always from the reference background (cvvdp_metric.py:709); interp.py:55-60, 92-100
     float ind = fminf(fmaxf(fmaf(f_lg2(Lr), a.lut_a, a.lut_b), 0.f), (float)(CVVDP_CSF_LUT_N - 1));
+#ifdef __CUDA_ARCH__
+    // floor through the FP32 adder (round-toward-zero add of 2^23) instead of F2I + I2F: the conversion
+    // instructions share the quarter-rate XU pipe with the MUFU operations this kernel is short of
+    const float tf = __fadd_rz(ind, 8388608.0f);
+    const int i0 = __float_as_int(tf) & (CVVDP_CSF_LUT_N - 1);
+    const float fr = ind - (tf - 8388608.0f);
+#else
     const int i0 = (int)ind;
     const float fr = ind - (float)i0;
+#endif
     const int i1 = min(i0 + 1, CVVDP_CSF_LUT_N - 1);
     const float4 va = s_lut[i0], vb = s_lut[i1];
     const float w0 = 1.f - fr;
@@ -1165,6 +764,13 @@ __device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lu
                      fminf(fabsf(T23.x), fabsf(R23.x)), fminf(fabsf(T23.y), fabsf(R23.y)));
     const float2 d01 = add2(T01, make_float2(-R01.x, -R01.y)), d23 = add2(T23, make_float2(-R23.x, -R23.y));
     df = make_float4(fabsf(d01.x), fabsf(d01.y), fabsf(d23.x), fabsf(d23.y));
+    if (PA) {
+        const float2 eps2 = bc2(a.eps), p2 = bc2(a.p), nep = bc2(-eps_p);
+        const float2 q01 = add2(make_float2(df.x, df.y), eps2), q23 = add2(make_float2(df.z, df.w), eps2);
+        const float2 g01 = mul2(p2, make_float2(f_lg2(q01.x), f_lg2(q01.y))), g23 = mul2(p2, make_float2(f_lg2(q23.x), f_lg2(q23.y)));
+        const float2 P01 = add2(make_float2(f_ex2(g01.x), f_ex2(g01.y)), nep), P23 = add2(make_float2(f_ex2(g23.x), f_ex2(g23.y)), nep);
+        df = make_float4(P01.x, P01.y, P23.x, P23.y);
+    }
     if (FEAT) {  // |T_f| S and |R_f| S without the masking gain
         *feat_t = make_float4(fabsf(T01.x) * a.inv_gain[0], fabsf(T01.y) * a.inv_gain[1], fabsf(T23.x) * a.inv_gain[2], fabsf(T23.y) * a.inv_gain[3]);
         *feat_r = make_float4(fabsf(R01.x) * a.inv_gain[0], fabsf(R01.y) * a.inv_gain[1], fabsf(R23.x) * a.inv_gain[2], fabsf(R23.y) * a.inv_gain[3]);
@@ -1176,6 +782,7 @@ __device__ __forceinline__ float spow_fast(float x, float p, float eps, float ep
 }
 
 // Masking + clamp + pooling term of one pixel (phase 4).  m = blurred mutual-masking signal.
+template <bool PA = false>
 __device__ __forceinline__ float4 band_mask(const BandArgs &a, float4 m, float4 df, const float *eps_q, float eps_p) {
     // channel pairs (A-sust, RG) and (YV, A-trans) go through packed fp32x2 arithmetic; MUFU stays scalar
     const float2 mc2 = bc2(a.mc), eps2 = bc2(a.eps);
@@ -1184,122 +791,158 @@ __device__ __forceinline__ float4 band_mask(const BandArgs &a, float4 m, float4 
     const float2 e23 = mul2(make_float2(a.q[2], a.q[3]), make_float2(f_lg2(b23.x), f_lg2(b23.y)));
     const float2 t01 = add2(make_float2(f_ex2(e01.x), f_ex2(e01.y)), make_float2(-eps_q[0], -eps_q[1]));
     const float2 t23 = add2(make_float2(f_ex2(e23.x), f_ex2(e23.y)), make_float2(-eps_q[2], -eps_q[3]));
-    // M[c] = sum_i t_i X[i][c]  (cvvdp_metric.py:758-760), two masked channels per operation
-    float2 M01 = mul2(bc2(t01.x), make_float2(a.X[0], a.X[1]));
-    float2 M23 = mul2(bc2(t01.x), make_float2(a.X[2], a.X[3]));
+    // 1 + M[c], M[c] = sum_i t_i X[i][c]  (cvvdp_metric.py:758-760), two masked channels per operation
+    const float2 one2 = bc2(1.f);
+    float2 M01 = fma2(bc2(t01.x), make_float2(a.X[0], a.X[1]), one2);
+    float2 M23 = fma2(bc2(t01.x), make_float2(a.X[2], a.X[3]), one2);
     M01 = fma2(bc2(t01.y), make_float2(a.X[4], a.X[5]), M01);
     M23 = fma2(bc2(t01.y), make_float2(a.X[6], a.X[7]), M23);
     M01 = fma2(bc2(t23.x), make_float2(a.X[8], a.X[9]), M01);
     M23 = fma2(bc2(t23.x), make_float2(a.X[10], a.X[11]), M23);
     M01 = fma2(bc2(t23.y), make_float2(a.X[12], a.X[13]), M01);
     M23 = fma2(bc2(t23.y), make_float2(a.X[14], a.X[15]), M23);
-    const float2 d01 = add2(make_float2(df.x, df.y), eps2), d23 = add2(make_float2(df.z, df.w), eps2);
-    const float2 p2 = bc2(a.p), nep = bc2(-eps_p);
-    const float2 g01 = mul2(p2, make_float2(f_lg2(d01.x), f_lg2(d01.y))), g23 = mul2(p2, make_float2(f_lg2(d23.x), f_lg2(d23.y)));
-    const float2 P01 = add2(make_float2(f_ex2(g01.x), f_ex2(g01.y)), nep), P23 = add2(make_float2(f_ex2(g23.x), f_ex2(g23.y)), nep);
-    // D_u = P / (1 + M);  D = Dmax * D_u / (Dmax + D_u)  ==  Dmax * P / (Dmax * (1 + M) + P)
-    const float2 dm2 = bc2(a.dmax), one2 = bc2(1.f);
-    const float2 n01 = fma2(dm2, add2(one2, M01), P01), n23 = fma2(dm2, add2(one2, M23), P23);
-    const float2 D01 = mul2(mul2(dm2, P01), make_float2(f_rcp(n01.x), f_rcp(n01.y)));
-    const float2 D23 = mul2(mul2(dm2, P23), make_float2(f_rcp(n23.x), f_rcp(n23.y)));
+    float2 P01, P23;
+    if (PA) {  // df already is safe_pow(|T'-R'|, p)
+        P01 = make_float2(df.x, df.y);
+        P23 = make_float2(df.z, df.w);
+    } else {
+        const float2 d01 = add2(make_float2(df.x, df.y), eps2), d23 = add2(make_float2(df.z, df.w), eps2);
+        const float2 p2 = bc2(a.p), nep = bc2(-eps_p);
+        const float2 g01 = mul2(p2, make_float2(f_lg2(d01.x), f_lg2(d01.y))), g23 = mul2(p2, make_float2(f_lg2(d23.x), f_lg2(d23.y)));
+        P01 = add2(make_float2(f_ex2(g01.x), f_ex2(g01.y)), nep);
+        P23 = add2(make_float2(f_ex2(g23.x), f_ex2(g23.y)), nep);
+    }
+    // D_u = P / (1 + M);  D = Dmax * D_u / (Dmax + D_u)  ==  P / ((1 + M) + P / Dmax)   (cvvdp_metric.py:855, 948-950)
+    const float2 idm2 = bc2(a.inv_dmax);
+    const float2 n01 = fma2(P01, idm2, M01), n23 = fma2(P23, idm2, M23);
+    const float2 D01 = mul2(P01, make_float2(f_rcp(n01.x), f_rcp(n01.y)));
+    const float2 D23 = mul2(P23, make_float2(f_rcp(n23.x), f_rcp(n23.y)));
     return make_float4(D01.x, D01.y, D23.x, D23.y);
 }
 
 // =================================================================================================
-// Fused band kernel, strip-marching version (the default band kernel).
-// A CTA of 128 threads owns a vertical strip of 52 columns (64 with the +-6 halo of the 13x13 Gaussian)
-// of one (item, frame) and marches down a segment of rows, 8 rows per step, keeping rolling windows in
-// shared memory:
+// Fused band kernel, strip-marching.
+// A CTA of 128 threads owns a vertical strip of SW = EW - 12 columns (EW with the +-6 halo of the 13x13
+// Gaussian) of one (item, frame) and marches down a segment of rows, 8 rows per step, keeping rolling
+// windows in shared memory:
 //   fine, crs : the 8 fine rows of this step and the 6 coarse rows under them (TMA stage, one step ahead)
-//   mm        : min(|T'|,|R'|) of the 8 rows of this step (64 columns)
-//   hb        : ring of the last 32 rows of the horizontally blurred mm (52 columns)
+//   mm        : min(|T'|,|R'|) of the 8 rows of this step (EW columns)
+//   hb        : ring of the last 32 rows of the horizontally blurred mm (SW columns)
 //   df        : ring of the last 16 rows of |T'-R'| waiting for their blurred mask
-// so the 13x13 Gaussian costs 13+13 taps and the vertical halo is paid once per segment.  72 KB of shared
-// memory and 112 registers: 3 CTAs (12 warps) per SM.
+// so the 13x13 Gaussian costs 13+13 taps and the vertical halo is paid once per segment.
 // Step k: rows A = [a0, a0+8) get contrast/CSF/mm/df (2x2 quads, one per thread) and their horizontal
 // blur; rows C = [a0-6, a0+2) -- whose 13-row window is now complete -- get the vertical blur,
 // masking, clamp and pooling.
+// Geometry (template EW): 64 -> 52-column strips, phases B/C use 104 of 128 threads; 60 -> 48-column
+// strips, phase A uses 120 threads and phases B/C exactly three warps (no idle lanes in a running warp).
+// The kernel is bound by the shared-memory pipe (~70 % busy at 4K) ahead of the FP32 pipe (~52 %), so
+// shared-memory wavefronts per pixel are the figure of merit.
 // =================================================================================================
-#define CVVDP_B2_SW 52
-#define CVVDP_B2_EW 64
 #define CVVDP_B2_RB 8
 #define CVVDP_B2_THREADS 128
 #define CVVDP_B2_HBR 32
 #define CVVDP_B2_DFR 16
 #define CVVDP_B2_CR (CVVDP_B2_RB / 2 + 2)  // 6 coarse rows per step
-#define CVVDP_B2_CC (CVVDP_B2_EW / 2 + 2)  // 34 coarse columns
 
+template <int EW>
+struct B2Geom {
+    static constexpr int SW = EW - 2 * CVVDP_BHALO;          // useful columns: 52 / 48
+    static constexpr int QW = EW / 2;                        // quads per row: 32 / 30
+    static constexpr int CC = EW / 2 + 2;                    // coarse columns: 34 / 32
+    static constexpr int A_THREADS = QW * (CVVDP_B2_RB / 2);  // 128 / 120
+    static constexpr int B_TASKS = CVVDP_B2_RB * (SW / 4);   // 104 / 96
+    static constexpr int C_TASKS = 2 * SW;                   // 104 / 96
+    static_assert(EW % 4 == 0 && SW % 4 == 0 && A_THREADS <= CVVDP_B2_THREADS && 4 * EW <= 256, "band strip geometry");
+};
+
+template <int EW, int DFR = CVVDP_B2_DFR>
 struct Band2Smem {
     float4 lut[CVVDP_CSF_LUT_N];                      // 512 B: keeps the TMA destinations 128-byte aligned
-    float4 crs[2][CVVDP_B2_CR][CVVDP_B2_CC];          // coarse rows of the current step (cp.async stage)
-    float4 fine[2][CVVDP_B2_RB][CVVDP_B2_EW];         // fine rows of the current step (cp.async stage)
-    float4 mm[CVVDP_B2_RB][CVVDP_B2_EW + 1];
-    float4 hb[CVVDP_B2_HBR][CVVDP_B2_SW + 1];
-    float4 df[CVVDP_B2_DFR][CVVDP_B2_SW];
+    float4 crs[2][CVVDP_B2_CR][B2Geom<EW>::CC];       // coarse rows of the current step (TMA / cp.async stage)
+    float4 fine[2][CVVDP_B2_RB][EW];                  // fine rows of the current step   (TMA / cp.async stage)
+    float4 mm[CVVDP_B2_RB][EW + 1];
+    float4 hb[CVVDP_B2_HBR][B2Geom<EW>::SW + 1];
+    float4 df[DFR][B2Geom<EW>::SW];
     float red[CVVDP_B2_THREADS / 32][4];
     unsigned long long bar;                           // mbarrier of the TMA stage
 };
-#define CVVDP_B2_STAGE_BYTES ((unsigned)(sizeof(float4) * 2 * (CVVDP_B2_CR * CVVDP_B2_CC + CVVDP_B2_RB * CVVDP_B2_EW)))
 
-// Asynchronous stage of one step: the 8 fine rows [a0, a0+8) x 64 columns of both videos and the 6
+// Asynchronous stage of one step: the 8 fine rows [a0, a0+8) x EW columns of both videos and the 6
 // coarse rows under them (replicate-clamped, lpyr_dec.py:136-141).  Issued one step ahead.
-__device__ __forceinline__ void band2_stage(const BandArgs &a, Band2Smem &sm, const float4 *fine_t, const float4 *crs_g,
+template <int EW, int DFR>
+__device__ __forceinline__ void band2_stage(const BandArgs &a, Band2Smem<EW, DFR> &sm, const float4 *fine_t, const float4 *crs_g,
                                             long long npix, long long ncpix, int a0, int a_end, int ex0, int tid, int pair) {
+    constexpr int CC = B2Geom<EW>::CC;
     const int cy0 = a0 / 2 - 1, cx0 = ex0 / 2 - 1;
     if (a.use_tma) {  // two bulk tensor copies issued by one thread; out-of-range elements arrive as zeros
         if (tid == 0) {
             fence_proxy_async();
-            mbar_expect_tx(&sm.bar, CVVDP_B2_STAGE_BYTES);
+            mbar_expect_tx(&sm.bar, (unsigned)(sizeof(float4) * 2 * (CVVDP_B2_CR * CC + CVVDP_B2_RB * EW)));
             tma_load_3d(&sm.fine[0][0][0], &a.tm_fine, 4 * ex0, a0, 2 * pair, &sm.bar);
             tma_load_3d(&sm.crs[0][0][0], &a.tm_coarse, 4 * cx0, cy0, 2 * pair, &sm.bar);
             mbar_emu_complete(&sm.bar);
         }
         return;
     }
-    for (int i = tid; i < 2 * CVVDP_B2_CR * CVVDP_B2_CC; i += CVVDP_B2_THREADS) {
-        const int v = i / (CVVDP_B2_CR * CVVDP_B2_CC), rem = i - v * (CVVDP_B2_CR * CVVDP_B2_CC);
-        const int r = rem / CVVDP_B2_CC, c = rem - r * CVVDP_B2_CC;
+    for (int i = tid; i < 2 * CVVDP_B2_CR * CC; i += CVVDP_B2_THREADS) {
+        const int v = i / (CVVDP_B2_CR * CC), rem = i - v * (CVVDP_B2_CR * CC);
+        const int r = rem / CC, c = rem - r * CC;
         const int cy = min(max(cy0 + r, 0), a.hc - 1), cx = min(max(cx0 + c, 0), a.wc - 1);
         cp_async16(&sm.crs[v][r][c], crs_g + v * ncpix + (long long)cy * a.wc + cx);
     }
-    const int c = tid & (CVVDP_B2_EW - 1), r0 = tid / CVVDP_B2_EW;  // 128 threads: 2 rows x 64 columns
-    const int gx = ex0 + c;
-    if (gx >= 0 && gx < a.w) {
-#pragma unroll
-        for (int i = 0; i < CVVDP_B2_RB / 2; ++i) {
-            const int r = r0 + 2 * i, gy = a0 + r;
-            if (gy < a_end) {
-                const float4 *src = fine_t + (long long)gy * a.w + gx;
-                cp_async16(&sm.fine[0][r][c], src);
-                cp_async16(&sm.fine[1][r][c], src + npix);
-            }
+    for (int i = tid; i < CVVDP_B2_RB * EW; i += CVVDP_B2_THREADS) {
+        const int r = i / EW, c = i - r * EW;
+        const int gx = ex0 + c, gy = a0 + r;
+        if (gx >= 0 && gx < a.w && gy < a_end) {
+            const float4 *src = fine_t + (long long)gy * a.w + gx;
+            cp_async16(&sm.fine[0][r][c], src);
+            cp_async16(&sm.fine[1][r][c], src + npix);
         }
     }
     cp_async_commit();
 }
 
-// Template flags: BLUR = phase-uncertainty Gaussian on (off only for levels with h <= 6 or w <= 6, Q7),
-// HM = write the per-band heat-map plane, BETA2 = spatial pooling exponent is exactly 2 (shipped value).
-// The per-pixel bodies of phases A and C are straight-line code (no per-pixel branches): rows and
-// columns outside the segment are computed on whatever the stage holds and discarded by a select, so
-// the compiler can interleave the MUFU chains of a thread's four pixels.
-// FEAT = feature mode: additionally write |T|S, |R|S (phase A) and D (phase C) of every pixel of the segment's
-// interior to three planes that k_feature_pool turns into the per-patch statistics of the ML heads.
-template <bool BLUR, bool HM, bool BETA2, bool FEAT = false>
+// Template flags: EW = strip geometry (above); CF = conflict-free phase A (below); BLUR = phase-uncertainty
+// Gaussian on (off only for levels with h <= 6 or w <= 6, Q7); HM = write the per-band heat-map plane;
+// BETA2 = spatial pooling exponent is exactly 2 (shipped value); FEAT = feature mode: additionally write
+// |T|S, |R|S (phase A) and D (phase C) of every pixel of the segment's interior to three planes that
+// k_feature_pool turns into the per-patch statistics of the ML heads.
+// The per-pixel bodies of phases A and C are straight-line code (no per-pixel branches): rows and columns
+// outside the segment are computed on whatever the stage holds and discarded by a select, so the compiler
+// can interleave the MUFU chains of a thread's four pixels.
+// CF: a thread's quad covers fine columns 2qx and 2qx+1, so the eight lanes of a quarter-warp touch 128-bit
+// words at a stride of two -- a two-way bank conflict on every fine-row load and every mm / df store of phase
+// A (ncu, round 1: 20 % of all shared-memory wavefronts of the kernel).  With CF the lanes whose bit 2 is set
+// take the ODD column of their quad first and the even one second; the eight lanes of a quarter-warp then
+// cover eight distinct 16-byte bank groups.  The column parity only enters the horizontal expand weights
+// ((.1,.8,.1) even, (0,.5,.5) odd), which become per-lane values: bit-identical results, one extra
+// packed multiply per (row, video).
+// PA: the power of the difference term runs in phase A (see band_pixel).
+// LAG: phase C trails phase B by 16 rows instead of 6, so every row of its 13-row window was written in an EARLIER
+// step and phases B and C need no barrier between them (two barriers per step instead of three; the FP32-only
+// horizontal blur of some warps overlaps the MUFU-heavy masking of others).  The |T'-R'| ring then holds 24 rows.
+template <bool LAG>
+struct B2Lag {
+    static constexpr int DFR = LAG ? 24 : CVVDP_B2_DFR;
+};
+template <int EW, bool CF, bool PA, bool LAG, bool BLUR, bool HM, bool BETA2, bool FEAT = false>
 __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_constant__ BandArgs a) {
     CVVDP_DYN_SMEM(smem_raw);
-    Band2Smem &sm = *reinterpret_cast<Band2Smem *>(smem_raw);
+    constexpr bool LAGC = LAG && BLUR;           // without the blur phase C reads the rows of its own step
+    constexpr int DFR = B2Lag<LAG>::DFR;
+    Band2Smem<EW, DFR> &sm = *reinterpret_cast<Band2Smem<EW, DFR> *>(smem_raw);
+    constexpr int SW = B2Geom<EW>::SW, QW = B2Geom<EW>::QW, CC = B2Geom<EW>::CC;
     const int tid = threadIdx.x;
     const int pair = blockIdx.z;
     constexpr int hal = BLUR ? CVVDP_BHALO : 0;
-    const int x0 = blockIdx.x * CVVDP_B2_SW, ex0 = x0 - hal;  // even
+    const int x0 = blockIdx.x * SW, ex0 = x0 - hal;  // even
     const int ys = blockIdx.y * a.seg_rows, ye = min(ys + a.seg_rows, a.h);
     const int y_begin = max(ys - hal, 0);                     // even
     const int a_end = min(ye + hal, a.h);                     // rows [y_begin, a_end) feed this segment
     const long long npix = (long long)a.h * a.w, ncpix = (long long)a.hc * a.wc;
     const float4 *fine_t = a.fine + (long long)pair * 2 * npix;
     const float4 *crs_g = a.coarse + (long long)pair * 2 * ncpix;
-    const bool x_edge = (ex0 < 0) || (x0 + CVVDP_B2_SW + hal > a.w);  // strip touches the left/right border
+    const bool x_edge = (ex0 < 0) || (x0 + SW + hal > a.w);  // strip touches the left/right border
 
     if (a.use_tma) {
         if (tid == 0) mbar_init(&sm.bar, 1);
@@ -1307,7 +950,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
     }
     unsigned tma_phase = 0;
     const int cx0 = ex0 / 2 - 1;
-    band2_stage(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, pair);
+    band2_stage<EW, DFR>(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, pair);
     if (tid < CVVDP_CSF_LUT_N) sm.lut[tid] = a.lut[tid];
     float eps_q[4];
 #pragma unroll
@@ -1316,13 +959,19 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
     const float eps_b = BETA2 ? 0.f : f_pow(a.eps, a.beta);
     float4 acc = f4(0.f);
     // loop-invariant thread roles
-    const int qy = tid / (CVVDP_B2_EW / 2), qx = tid - qy * (CVVDP_B2_EW / 2);  // phase A: one 2x2 quad
+    const int qy = tid / QW, qx = tid - qy * QW;                               // phase A: one 2x2 quad
     const int b_r = tid % CVVDP_B2_RB, b_xg = tid / CVVDP_B2_RB;               // phase B: row, group of 4 columns
-    const int c_ix = tid % CVVDP_B2_SW, c_rg = tid / CVVDP_B2_SW;              // phase C: column, group of 4 rows
+    const int c_ix = tid % SW, c_rg = tid / SW;                                // phase C: column, group of 4 rows
     const int a_gx = ex0 + 2 * qx;
-    const bool a_cols = a_gx + 1 >= 0 && a_gx < a.w;
+    const bool a_cols = a_gx + 1 >= 0 && a_gx < a.w && tid < B2Geom<EW>::A_THREADS;
+    // CF: column order inside the quad and the matching horizontal expand weights of this lane
+    const int sw_odd = CF ? ((tid >> 2) & 1) : 0;  // 1: this lane takes the odd column of its quad first
+    const float wA0 = sw_odd ? 0.f : 0.1f, wA1 = sw_odd ? 0.5f : 0.8f, wA2 = sw_odd ? 0.5f : 0.1f;  // first column
+    const float wB0 = sw_odd ? 0.1f : 0.f, wB1 = sw_odd ? 0.8f : 0.5f, wB2 = sw_odd ? 0.1f : 0.5f;  // second column
 
-    for (int a0 = y_begin; a0 - hal < ye; a0 += CVVDP_B2_RB) {
+    constexpr int clag = LAGC ? 16 : hal;  // phase C of a step handles rows [a0 - clag, a0 - clag + 8)
+    int dslot = 0;                         // LAG: ring slot of row a0 = (a0 - y_begin) mod 24
+    for (int a0 = y_begin; a0 - clag < ye; a0 += CVVDP_B2_RB) {
         const bool have_a = a0 < a_end;
         if (a.use_tma) {
             if (have_a) {
@@ -1331,12 +980,12 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                 // TMA zero-fills outside the coarse image; the reference pads by replication
                 // (lpyr_dec.py:136-141): patch those entries from the nearest valid row/column
                 const int cy0 = a0 / 2 - 1;
-                if (cy0 < 0 || cy0 + CVVDP_B2_CR > a.hc || cx0 < 0 || cx0 + CVVDP_B2_CC > a.wc) {
-                    for (int i = tid; i < 2 * CVVDP_B2_CR * CVVDP_B2_CC; i += CVVDP_B2_THREADS) {
-                        const int v = i / (CVVDP_B2_CR * CVVDP_B2_CC), rem = i - v * (CVVDP_B2_CR * CVVDP_B2_CC);
-                        const int r = rem / CVVDP_B2_CC, c = rem - r * CVVDP_B2_CC;
+                if (cy0 < 0 || cy0 + CVVDP_B2_CR > a.hc || cx0 < 0 || cx0 + CC > a.wc) {
+                    for (int i = tid; i < 2 * CVVDP_B2_CR * CC; i += CVVDP_B2_THREADS) {
+                        const int v = i / (CVVDP_B2_CR * CC), rem = i - v * (CVVDP_B2_CR * CC);
+                        const int r = rem / CC, c = rem - r * CC;
                         const int rr = min(max(cy0 + r, 0), a.hc - 1) - cy0, cc = min(max(cx0 + c, 0), a.wc - 1) - cx0;
-                        if ((rr != r || cc != c) && rr >= 0 && rr < CVVDP_B2_CR && cc >= 0 && cc < CVVDP_B2_CC)
+                        if ((rr != r || cc != c) && rr >= 0 && rr < CVVDP_B2_CR && cc >= 0 && cc < CC)
                             sm.crs[v][r][c] = sm.crs[v][rr][cc];
                     }
                 }
@@ -1359,26 +1008,33 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                         ve[c] = fma4(0.1f, c2, fma4(0.8f, c1, 0.1f * c0));
                         vo[c] = fma4(0.5f, c2, 0.5f * c1);
                     }
-                    e[v][0] = fma4(0.1f, ve[2], fma4(0.8f, ve[1], 0.1f * ve[0]));
-                    e[v][1] = fma4(0.5f, ve[2], 0.5f * ve[1]);
-                    e[v][2] = fma4(0.1f, vo[2], fma4(0.8f, vo[1], 0.1f * vo[0]));
-                    e[v][3] = fma4(0.5f, vo[2], 0.5f * vo[1]);
+                    if (CF) {  // e[v][k]: k & 1 = first / second column of this lane
+                        e[v][0] = fma4(wA2, ve[2], fma4(wA1, ve[1], wA0 * ve[0]));
+                        e[v][1] = fma4(wB2, ve[2], fma4(wB1, ve[1], wB0 * ve[0]));
+                        e[v][2] = fma4(wA2, vo[2], fma4(wA1, vo[1], wA0 * vo[0]));
+                        e[v][3] = fma4(wB2, vo[2], fma4(wB1, vo[1], wB0 * vo[0]));
+                    } else {
+                        e[v][0] = fma4(0.1f, ve[2], fma4(0.8f, ve[1], 0.1f * ve[0]));
+                        e[v][1] = fma4(0.5f, ve[2], 0.5f * ve[1]);
+                        e[v][2] = fma4(0.1f, vo[2], fma4(0.8f, vo[1], 0.1f * vo[0]));
+                        e[v][3] = fma4(0.5f, vo[2], 0.5f * vo[1]);
+                    }
                 }
                 // pixels beyond the image / segment are evaluated on the stage's fill values and never read back
                 // (phase B reflects at the borders, phase C selects); their df slot belongs to rows long consumed
                 float4 mm[4], df[4], ft[4], fr[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
-                    band_pixel<FEAT>(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm[k], df[k], &ft[k], &fr[k]);
+                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + ((k & 1) ^ sw_odd);
+                    band_pixel<FEAT, PA>(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm[k], df[k], &ft[k], &fr[k], eps_p);
                 }
                 const int ix = ex0 + 2 * qx - x0;  // even; the pair (ix, ix+1) is inside or outside the strip together
-                const bool in_strip = ix >= 0 && ix < CVVDP_B2_SW;
+                const bool in_strip = ix >= 0 && ix < SW;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
+                    const int ry = 2 * qy + (k >> 1), cofs = (k & 1) ^ sw_odd, rx = 2 * qx + cofs;
                     sm.mm[ry][rx] = mm[k];
-                    if (in_strip) sm.df[(a0 + ry) & (CVVDP_B2_DFR - 1)][ix + (k & 1)] = df[k];
+                    if (in_strip) sm.df[LAG ? dslot + ry : ((a0 + ry) & (CVVDP_B2_DFR - 1))][ix + cofs] = df[k];
                     if (FEAT) {  // every pixel belongs to the interior of exactly one (strip, segment)
                         const int py = a0 + ry, px = ex0 + rx;
                         if (in_strip && py >= ys && py < ye && px < a.w) {
@@ -1392,9 +1048,9 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
         }
         __syncthreads();
         // ---- prefetch the next step's stage while phases B and C run ----
-        if (a0 + CVVDP_B2_RB < a_end) band2_stage(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B2_RB, a_end, ex0, tid, pair);
+        if (a0 + CVVDP_B2_RB < a_end) band2_stage<EW, DFR>(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B2_RB, a_end, ex0, tid, pair);
         // ---- phase B: horizontal pass of the phase-uncertainty Gaussian for the new rows ----
-        if (BLUR && have_a && tid < CVVDP_B2_RB * (CVVDP_B2_SW / 4)) {
+        if (BLUR && have_a && tid < B2Geom<EW>::B_TASKS) {
             const int gy = a0 + b_r, gxb = x0 + b_xg * 4;
             if (gy < a_end && gxb < a.w) {
                 float4 win[2 * CVVDP_BHALO + 4];
@@ -1402,7 +1058,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
                         int lx = reflect_idx(gxb + j - CVVDP_BHALO, a.w) - ex0;
-                        lx = min(max(lx, 0), CVVDP_B2_EW - 1);  // only for outputs beyond the image (discarded)
+                        lx = min(max(lx, 0), EW - 1);  // only for outputs beyond the image (discarded)
                         win[j] = sm.mm[b_r][lx];
                     }
                 } else {
@@ -1419,11 +1075,13 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                 }
             }
         }
-        __syncthreads();
+        if (!LAGC) __syncthreads();
         // ---- phase C: vertical pass, masking, clamp, pooling for the rows whose window is complete ----
-        if (tid < 2 * CVVDP_B2_SW) {
+        if (tid < B2Geom<EW>::C_TASKS) {
             const int gx = x0 + c_ix;
-            const int cyb = a0 - hal + c_rg * 4;  // 4 consecutive rows per thread
+            const int cyb = a0 - clag + c_rg * 4;  // 4 consecutive rows per thread
+            int dbase = dslot + (LAGC ? 8 : 0) + 4 * c_rg;  // LAG: ring slot of row cyb = (cyb - y_begin) mod 24
+            dbase -= dbase >= 24 ? 24 : 0;
             if (gx < a.w && cyb + 3 >= ys && cyb < ye) {
                 float4 win[2 * CVVDP_BHALO + 4];
                 if (BLUR) {
@@ -1453,7 +1111,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                     } else {
                         m = sm.mm[(gy - a0) & (CVVDP_B2_RB - 1)][gx - ex0];
                     }
-                    D[o] = band_mask(a, m, sm.df[gy & (CVVDP_B2_DFR - 1)][c_ix], eps_q, eps_p);
+                    D[o] = band_mask<PA>(a, m, sm.df[LAG ? dbase + o : (gy & (CVVDP_B2_DFR - 1))][c_ix], eps_q, eps_p);
                 }
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
@@ -1482,6 +1140,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                 }
             }
         }
+        dslot = dslot == 16 ? 0 : dslot + 8;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1501,316 +1160,6 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < CVVDP_B2_THREADS / 32; ++w) s += sm.red[w][tid];
-        const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
-        a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
-    }
-}
-
-// =================================================================================================
-// Fused band kernel, wide strips (levels at least two strips wide, blur on).  Same arithmetic and the
-// same three phases per step as k_band2, re-proportioned for FP32-pipe efficiency and occupancy:
-//   * a CTA of 256 threads owns 116 columns (128 with the +-6 halo): the redundant halo columns of
-//     phase A drop from 23 % to 10 %, phases B and C keep 232 of 256 threads busy (81 % -> 91 %);
-//   * 110 KB of shared memory per CTA -> 2 CTAs = 16 warps per SM (k_band2: 12): the mutual-masking
-//     rows overwrite the test rows of the stage in place (each thread consumes exactly the four pixels
-//     it then overwrites), the ring of horizontally blurred rows holds exactly the 20 live rows;
-//   * the stage is filled by 1-D bulk copies (cp.async.bulk, one row each, issued by 28 lanes and
-//     counted on one mbarrier): rows land with a padded stride (129 float4), so the row-per-lane
-//     accesses of phase B stay free of bank conflicts, which a tensor-map box (dense rows, 128-byte
-//     aligned) cannot give.  Nothing outside the image is copied; those entries are never consumed.
-// =================================================================================================
-#define CVVDP_B3_RB 8
-#define CVVDP_B3_HBR 20
-#define CVVDP_B3_DFR 16
-#define CVVDP_B3_CR (CVVDP_B3_RB / 2 + 2)  // 6 coarse rows per step
-#define CVVDP_B3_NCOPY (2 * CVVDP_B3_RB + 2 * CVVDP_B3_CR)  // bulk copies (= mbarrier arrivals) per step
-// Geometry by extended strip width EW: 128 -> 116 useful columns, 256 threads, 2 CTAs/SM (the variant
-// measured above); 64 -> 52 columns, 128 threads, 54 KB of shared memory = 4 CTAs (16 warps) per SM with
-// 4-warp barriers -- k_band2's geometry with k_band3's leaner shared-memory layout (opt-in
-// CVVDP_B200_BAND3_NARROW, not yet measured on a B200).
-template <int EW>
-struct B3Geom {
-    static constexpr int SW = EW - 2 * CVVDP_BHALO;  // useful columns
-    static constexpr int THREADS = 2 * EW;
-    static constexpr int CC = EW / 2 + 2;            // coarse columns
-    static constexpr int FS = EW + 1;                // padded row stride of the fine / mm rows
-    static constexpr int CTAS = EW == 64 ? 4 : 2;
-};
-
-template <int EW>
-struct Band3Smem {
-    float4 lut[CVVDP_CSF_LUT_N];
-    float4 crs[2][CVVDP_B3_CR][B3Geom<EW>::CC];
-    float4 fine[2][CVVDP_B3_RB][B3Geom<EW>::FS];  // [0] = test rows, overwritten by min(|T'|,|R'|) in phase A
-    float4 hb[CVVDP_B3_HBR][B3Geom<EW>::SW + 1];
-    float4 df[CVVDP_B3_DFR][B3Geom<EW>::SW];
-    float red[B3Geom<EW>::THREADS / 32][4];
-    unsigned long long bar;
-};
-
-// Copy `c` of the stage of rows [a0, a0+8): c < 8: test row c; c < 16: reference row c-8; else the
-// coarse rows under them (test, then reference).  Every copy arrives once on the barrier.
-template <int EW>
-__device__ __forceinline__ void band3_copy(const BandArgs &a, Band3Smem<EW> &sm, const float4 *fine_t, const float4 *crs_g,
-                                           long long npix, long long ncpix, int a0, int a_end, int ex0, int c) {
-    void *dst = nullptr;
-    const float4 *src = nullptr;
-    int n = 0;
-    if (c < 2 * CVVDP_B3_RB) {
-        const int v = c / CVVDP_B3_RB, r = c - v * CVVDP_B3_RB, gy = a0 + r;
-        const int gx0 = max(ex0, 0), gx1 = min(ex0 + EW, a.w);
-        if (gy < a_end && gx1 > gx0) {
-            n = gx1 - gx0;
-            dst = &sm.fine[v][r][gx0 - ex0];
-            src = fine_t + v * npix + (long long)gy * a.w + gx0;
-        }
-    } else {
-        const int cc = c - 2 * CVVDP_B3_RB, v = cc / CVVDP_B3_CR, r = cc - v * CVVDP_B3_CR;
-        const int cy = a0 / 2 - 1 + r, cx0 = ex0 / 2 - 1;
-        const int gx0 = max(cx0, 0), gx1 = min(cx0 + B3Geom<EW>::CC, a.wc);
-        if (cy >= 0 && cy < a.hc && gx1 > gx0) {
-            n = gx1 - gx0;
-            dst = &sm.crs[v][r][gx0 - cx0];
-            src = crs_g + v * ncpix + (long long)cy * a.wc + gx0;
-        }
-    }
-    if (n > 0) {
-        mbar_expect_tx(&sm.bar, 16u * n);
-        bulk_copy_g2s(dst, src, 16u * n, &sm.bar);
-    } else {
-        mbar_arrive(&sm.bar);
-    }
-}
-// Issue copies [c0, c1) of a stage: one lane each on the device, one thread in the mock-device build
-// (whose copies are synchronous; the phase is completed after the last group).
-template <int EW>
-__device__ __forceinline__ void band3_issue(const BandArgs &a, Band3Smem<EW> &sm, const float4 *fine_t, const float4 *crs_g,
-                                            long long npix, long long ncpix, int a0, int a_end, int ex0, int tid, int c0, int c1,
-                                            bool last) {
-#ifdef CVVDP_EMU
-    if (tid == 0) {
-        for (int c = c0; c < c1; ++c) band3_copy<EW>(a, sm, fine_t, crs_g, npix, ncpix, a0, a_end, ex0, c);
-        if (last) mbar_emu_complete(&sm.bar);
-    }
-#else
-    (void)last;
-    if (tid < c1 - c0) {
-        fence_proxy_async();  // the destination was last touched through the generic proxy
-        band3_copy<EW>(a, sm, fine_t, crs_g, npix, ncpix, a0, a_end, ex0, c0 + tid);
-    }
-#endif
-}
-
-template <int EW, bool HM, bool BETA2>
-__global__ void __launch_bounds__(B3Geom<EW>::THREADS, B3Geom<EW>::CTAS) k_band3(const __grid_constant__ BandArgs a) {
-    CVVDP_DYN_SMEM(smem_raw);
-    Band3Smem<EW> &sm = *reinterpret_cast<Band3Smem<EW> *>(smem_raw);
-    constexpr int CVVDP_B3_SW = B3Geom<EW>::SW, CVVDP_B3_EW = EW, CVVDP_B3_THREADS = B3Geom<EW>::THREADS;
-    constexpr int CVVDP_B3_CC = B3Geom<EW>::CC, CVVDP_B3_FS = B3Geom<EW>::FS;
-    const int tid = threadIdx.x;
-    const int pair = blockIdx.z;
-    constexpr int hal = CVVDP_BHALO;
-    const int x0 = blockIdx.x * CVVDP_B3_SW, ex0 = x0 - hal;  // even
-    const int ys = blockIdx.y * a.seg_rows, ye = min(ys + a.seg_rows, a.h);
-    const int y_begin = max(ys - hal, 0);  // even
-    const int a_end = min(ye + hal, a.h);
-    const long long npix = (long long)a.h * a.w, ncpix = (long long)a.hc * a.wc;
-    const float4 *fine_t = a.fine + (long long)pair * 2 * npix;
-    const float4 *crs_g = a.coarse + (long long)pair * 2 * ncpix;
-    const bool x_edge = (ex0 < 0) || (x0 + CVVDP_B3_SW + hal > a.w);
-    const int cx0 = ex0 / 2 - 1;
-
-    if (tid == 0) mbar_init(&sm.bar, CVVDP_B3_NCOPY);
-    if (tid < CVVDP_CSF_LUT_N) sm.lut[tid] = a.lut[tid];
-    __syncthreads();
-    unsigned phase = 0;
-    // copies 0..7 (test rows) are issued apart from the rest: their destination doubles as mm
-    band3_issue<EW>(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, CVVDP_B3_RB, CVVDP_B3_NCOPY, false);
-    band3_issue<EW>(a, sm, fine_t, crs_g, npix, ncpix, y_begin, a_end, ex0, tid, 0, CVVDP_B3_RB, true);
-    float eps_q[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) eps_q[c] = f_pow(a.eps, a.q[c]);
-    const float eps_p = f_pow(a.eps, a.p);
-    const float eps_b = BETA2 ? 0.f : f_pow(a.eps, a.beta);
-    float4 acc = f4(0.f);
-    const int qy = tid / (CVVDP_B3_EW / 2), qx = tid - qy * (CVVDP_B3_EW / 2);  // phase A: one 2x2 quad
-    const int b_r = tid % CVVDP_B3_RB, b_xg = tid / CVVDP_B3_RB;               // phase B: row, group of 4 columns
-    const int c_ix = tid % CVVDP_B3_SW, c_rg = tid / CVVDP_B3_SW;              // phase C: column, group of 4 rows
-    const int a_gx = ex0 + 2 * qx;
-    const bool a_cols = a_gx + 1 >= 0 && a_gx < a.w;
-    float4(*mm)[CVVDP_B3_FS] = sm.fine[0];
-    int ring0 = 0;  // hb slot of row a0 = (a0 - y_begin) mod 20
-
-    for (int a0 = y_begin; a0 - hal < ye; a0 += CVVDP_B3_RB) {
-        const bool have_a = a0 < a_end;
-        if (have_a) {
-            mbar_wait(&sm.bar, phase);
-            phase ^= 1u;
-            // the reference pads the coarse level by replication (lpyr_dec.py:136-141): fill the entries
-            // outside the coarse image from the nearest valid row / column
-            const int cy0 = a0 / 2 - 1;
-            if (cy0 < 0 || cy0 + CVVDP_B3_CR > a.hc || cx0 < 0 || cx0 + CVVDP_B3_CC > a.wc) {
-                for (int i = tid; i < 2 * CVVDP_B3_CR * CVVDP_B3_CC; i += CVVDP_B3_THREADS) {
-                    const int v = i / (CVVDP_B3_CR * CVVDP_B3_CC), rem = i - v * (CVVDP_B3_CR * CVVDP_B3_CC);
-                    const int r = rem / CVVDP_B3_CC, c = rem - r * CVVDP_B3_CC;
-                    const int rr = min(max(cy0 + r, 0), a.hc - 1) - cy0, cc = min(max(cx0 + c, 0), a.wc - 1) - cx0;
-                    if ((rr != r || cc != c) && rr >= 0 && rr < CVVDP_B3_CR && cc >= 0 && cc < CVVDP_B3_CC)
-                        sm.crs[v][r][c] = sm.crs[v][rr][cc];
-                }
-            }
-        }
-        __syncthreads();
-        // ---- phase A: one 2x2 quad per thread: expand, contrast, CSF -> mm (in place of the test rows), df ----
-        if (have_a) {
-            const int gy = a0 + 2 * qy;
-            if (gy < a_end && a_cols) {
-                float4 e[2][4];
-#pragma unroll
-                for (int v = 0; v < 2; ++v) {
-                    float4 ve[3], vo[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float4 c0 = sm.crs[v][qy][qx + c], c1 = sm.crs[v][qy + 1][qx + c], c2 = sm.crs[v][qy + 2][qx + c];
-                        ve[c] = fma4(0.1f, c2, fma4(0.8f, c1, 0.1f * c0));
-                        vo[c] = fma4(0.5f, c2, 0.5f * c1);
-                    }
-                    e[v][0] = fma4(0.1f, ve[2], fma4(0.8f, ve[1], 0.1f * ve[0]));
-                    e[v][1] = fma4(0.5f, ve[2], 0.5f * ve[1]);
-                    e[v][2] = fma4(0.1f, vo[2], fma4(0.8f, vo[1], 0.1f * vo[0]));
-                    e[v][3] = fma4(0.5f, vo[2], 0.5f * vo[1]);
-                }
-                float4 mmv[4], dfv[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
-                    band_pixel(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mmv[k], dfv[k]);
-                }
-                const int ix = ex0 + 2 * qx - x0;
-                const bool in_strip = ix >= 0 && ix < CVVDP_B3_SW;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + (k & 1);
-                    mm[ry][rx] = mmv[k];
-                    if (in_strip) sm.df[(a0 + ry) & (CVVDP_B3_DFR - 1)][ix + (k & 1)] = dfv[k];
-                }
-            }
-        }
-        __syncthreads();
-        const bool more = a0 + CVVDP_B3_RB < a_end;
-        // the reference rows and the coarse rows are free: prefetch them for the next step
-        if (more) band3_issue<EW>(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B3_RB, a_end, ex0, tid, CVVDP_B3_RB, CVVDP_B3_NCOPY, false);
-        // ---- phase B: horizontal pass of the phase-uncertainty Gaussian for the new rows ----
-        if (have_a && tid < CVVDP_B3_RB * (CVVDP_B3_SW / 4)) {
-            const int gy = a0 + b_r, gxb = x0 + b_xg * 4;
-            if (gy < a_end && gxb < a.w) {
-                float4 win[2 * CVVDP_BHALO + 4];
-                if (x_edge) {
-#pragma unroll
-                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
-                        int lx = reflect_idx(gxb + j - CVVDP_BHALO, a.w) - ex0;
-                        lx = min(max(lx, 0), CVVDP_B3_EW - 1);  // only for outputs beyond the image (discarded)
-                        win[j] = mm[b_r][lx];
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) win[j] = mm[b_r][b_xg * 4 + j];
-                }
-                int slot = ring0 + b_r;
-                slot -= slot >= CVVDP_B3_HBR ? CVVDP_B3_HBR : 0;
-                float4 *dst = &sm.hb[slot][b_xg * 4];
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    float4 sacc = f4(0.f);
-#pragma unroll
-                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) sacc = fma4(a.kern[k], win[o + k], sacc);
-                    dst[o] = sacc;
-                }
-            }
-        }
-        __syncthreads();
-        // mm is consumed: prefetch the test rows of the next step into its place
-        if (more) band3_issue<EW>(a, sm, fine_t, crs_g, npix, ncpix, a0 + CVVDP_B3_RB, a_end, ex0, tid, 0, CVVDP_B3_RB, true);
-        // ---- phase C: vertical pass, masking, clamp, pooling for the rows whose window is complete ----
-        if (tid < 2 * CVVDP_B3_SW) {
-            const int gx = x0 + c_ix;
-            const int cyb = a0 - hal + c_rg * 4;  // 4 consecutive rows per thread
-            if (gx < a.w && cyb + 3 >= ys && cyb < ye) {
-                float4 win[2 * CVVDP_BHALO + 4];
-                const bool y_edge = (cyb - CVVDP_BHALO < 0) || (cyb + 3 + CVVDP_BHALO >= a.h);
-                if (y_edge) {
-#pragma unroll
-                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
-                        int yy = reflect_idx(cyb + j - CVVDP_BHALO, a.h);
-                        yy = min(max(yy, y_begin), a.h - 1);
-                        win[j] = sm.hb[(yy - y_begin) % CVVDP_B3_HBR][c_ix];
-                    }
-                } else {
-                    // row cyb-6 = a0-12+4*c_rg sits 8+4*c_rg slots after the slot of row a0 (mod 20)
-                    int s0 = ring0 + 8 + 4 * c_rg;
-                    s0 -= s0 >= CVVDP_B3_HBR ? CVVDP_B3_HBR : 0;
-#pragma unroll
-                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
-                        int sl = s0 + j;
-                        sl -= sl >= CVVDP_B3_HBR ? CVVDP_B3_HBR : 0;
-                        win[j] = sm.hb[sl][c_ix];
-                    }
-                }
-                float4 D[4];
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const int gy = cyb + o;
-                    float4 m = f4(0.f);
-#pragma unroll
-                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) m = fma4(a.kern[k], win[o + k], m);
-                    D[o] = band_mask(a, m, sm.df[gy & (CVVDP_B3_DFR - 1)][c_ix], eps_q, eps_p);
-                }
-#pragma unroll
-                for (int o = 0; o < 4; ++o) {
-                    const int gy = cyb + o;
-                    const bool live = gy >= ys && gy < ye;
-                    float4 t;
-                    if (BETA2) {
-                        const float e2 = 2.f * a.eps;
-                        t = make_float4(D[o].x * (D[o].x + e2), D[o].y * (D[o].y + e2), D[o].z * (D[o].z + e2), D[o].w * (D[o].w + e2));
-                    } else {
-                        t = make_float4(f_pow(D[o].x + a.eps, a.beta) - eps_b, f_pow(D[o].y + a.eps, a.beta) - eps_b,
-                                        f_pow(D[o].z + a.eps, a.beta) - eps_b, f_pow(D[o].w + a.eps, a.beta) - eps_b);
-                    }
-                    acc.x += live ? t.x : 0.f;
-                    acc.y += live ? t.y : 0.f;
-                    acc.z += live ? t.z : 0.f;
-                    acc.w += live ? t.w : 0.f;
-                    if (HM && live) {
-                        const float eb = f_pow(a.eps, a.hm_beta);
-                        float s = (f_pow(D[o].x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
-                                  (f_pow(D[o].z * a.hm_w[2] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].w * a.hm_w[3] + a.eps, a.hm_beta) - eb);
-                        const float ib = 1.f / a.hm_beta;
-                        a.hm[(long long)pair * npix + (long long)gy * a.w + gx] = (f_pow(s + a.eps, ib) - f_pow(a.eps, ib)) * a.hm_scale;
-                    }
-                }
-            }
-        }
-        ring0 += CVVDP_B3_RB;
-        ring0 -= ring0 >= CVVDP_B3_HBR ? CVVDP_B3_HBR : 0;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-    }
-    if ((tid & 31) == 0) {
-        sm.red[tid >> 5][0] = acc.x;
-        sm.red[tid >> 5][1] = acc.y;
-        sm.red[tid >> 5][2] = acc.z;
-        sm.red[tid >> 5][3] = acc.w;
-    }
-    __syncthreads();
-    if (tid < 4) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < CVVDP_B3_THREADS / 32; ++w) s += sm.red[w][tid];
         const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
         a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
     }

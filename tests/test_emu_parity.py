@@ -42,23 +42,17 @@ def test_identical_pair_is_exactly_10(mock_device):
 
 
 @pytest.mark.parametrize("shape,fps,heatmap", [((1, 150, 360), 0, None), ((1, 131, 250), 0, "raw"), ((5, 64, 236), 30, None)])
-@pytest.mark.parametrize("wide", [False, True, "narrow3"])
-def test_band_kernel_variants_and_packed_temporal_kernel(shape, fps, heatmap, wide, mock_device, monkeypatch):
-    """Both band kernels on levels at least 232 pixels wide: the default 52-column strip kernel and the
-    opt-in 116-column one (CVVDP_B200_WIDE: several row segments, a ragged last strip, the 20-row ring
-    wrapping, the heat-map variant); clips whose planes are whole 64-pixel warp segments take the packed
-    two-stage temporal kernel.  Checked against the oracle."""
+@pytest.mark.parametrize("variant", [0, 3, 5, 7, 11, 15])
+def test_band_kernel_variants_and_packed_temporal_kernel(shape, fps, heatmap, variant, mock_device, monkeypatch):
+    """The band kernel on levels several strips wide (several row segments, a ragged last strip, the heat-map
+    variant) in its A/B geometries (CVVDP_B200_BAND_VARIANT: bit 1 = 48-column strips, bit 0 = conflict-free
+    phase A; only honoured by builds with -DCVVDP_BAND_AB, otherwise every value runs the default); clips whose
+    planes are whole 64-pixel warp segments take the packed two-stage temporal kernel.  Checked against the oracle."""
     F, H, W = shape
     tst, ref = synth.make_pair_u8(11, F, H, W)
-    monkeypatch.delenv("CVVDP_B200_WIDE", raising=False)
-    monkeypatch.delenv("CVVDP_B200_BAND3_NARROW", raising=False)
-    if wide is True:
-        monkeypatch.setenv("CVVDP_B200_WIDE", "1")
-    elif wide == "narrow3":
-        monkeypatch.setenv("CVVDP_B200_BAND3_NARROW", "1")
+    monkeypatch.setenv("CVVDP_B200_BAND_VARIANT", str(variant))
     m = cv.cvvdp(display_name="standard_fhd", heatmap=heatmap)
     jod, stats = m.predict(tst, ref, frames_per_second=fps)
-    assert m._ctx.band_kernel_id(0) == {False: 2, True: 3, "narrow3": 4}[wide]
     jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd", heatmap=heatmap)
     gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], str(shape))
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
@@ -287,16 +281,6 @@ def test_every_temporal_specialisation_against_oracle(fps, mock_device):
     jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd", "symmetric")
     gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"{fps} fps")
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
-
-
-def test_reduce_tile_variants_are_bit_identical(mock_device, monkeypatch):
-    """The opt-in 30x16 reduce tile (CVVDP_B200_REDUCE_TY16) must not change a single bit."""
-    tst, ref = synth.make_pair_u8(71, 2, 150, 360)
-    monkeypatch.delenv("CVVDP_B200_REDUCE_TY16", raising=False)
-    _, s8 = cv.cvvdp(display_name="standard_fhd").predict(tst, ref, frames_per_second=30)
-    monkeypatch.setenv("CVVDP_B200_REDUCE_TY16", "1")
-    _, s16 = cv.cvvdp(display_name="standard_fhd").predict(tst, ref, frames_per_second=30)
-    assert np.array_equal(s8["Q_per_ch"], s16["Q_per_ch"])
 
 
 @pytest.mark.parametrize("dtype,fps", [("f32", 60), ("f16", 30), ("f32", 24)])
