@@ -84,7 +84,7 @@ SYMBOLS = {
                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_launch_count": (C.c_int64, [C.c_void_p]),
     "cvvdp_b200_band_strip_width": (C.c_int, [C.c_void_p, C.c_int]),
-    "cvvdp_b200_band_kernel_id": (C.c_int, [C.c_void_p, C.c_int]),
+    "cvvdp_b200_input_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "cvvdp_b200_temporal_filters": (C.c_int, [C.c_void_p, C.c_float, C.POINTER(C.c_float)]),
     "cvvdp_b200_feature_layout": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int64)]),
@@ -93,14 +93,18 @@ SYMBOLS = {
     "cvvdp_b200_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
 }
 
-KERNEL_KINDS = ["temporal", "reduce", "band", "baseband", "finalize", "heatmap", "pool", "frontend"]
+KERNEL_KINDS = ["temporal", "reduce", "band", "baseband", "finalize", "heatmap", "pool", "frontend", "features"]
 
 
 class KernelStat(C.Structure):
     _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("launches", C.c_int32), ("total_ms", C.c_float),
                 ("algo_bytes", C.c_double)]
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+
+
+class InputReport(C.Structure):
+    _fields_ = [("out_of_range", C.c_int64), ("nan", C.c_int64), ("inf", C.c_int64), ("first_frame_sum", C.c_double)]
 
 
 class NativeError(RuntimeError):
@@ -211,11 +215,14 @@ class Context:
     def set_feature_output(self, ptr):
         self._check(self._lib.cvvdp_b200_set_feature_output(self._h, ptr), "set_feature_output")
 
-    def band_kernel_id(self, level):
-        return int(self._lib.cvvdp_b200_band_kernel_id(self._h, int(level)))
+    def band_strip_width(self, level):
+        return int(self._lib.cvvdp_b200_band_strip_width(self._h, int(level)))
 
-    def band_is_wide(self, level):
-        return int(self._lib.cvvdp_b200_band_strip_width(self._h, int(level))) == 116
+    def input_stats(self, reset=True):
+        """Validation counters of the fused front end since the last reset (synchronises the device)."""
+        rep = InputReport()
+        self._check(self._lib.cvvdp_b200_input_stats(self._h, C.byref(rep), 1 if reset else 0), "input_stats")
+        return rep
 
     def profile_enable(self, on=True):
         self._check(self._lib.cvvdp_b200_profile_enable(self._h, 1 if on else 0), "profile_enable")

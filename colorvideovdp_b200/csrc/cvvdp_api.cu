@@ -14,18 +14,10 @@
 
 using namespace cvvdp;
 
-#ifndef CVVDP_BAND_EW_DEFAULT
-#define CVVDP_BAND_EW_DEFAULT 64      // strip geometry of the band kernel (B2Geom)
-#endif
-#ifndef CVVDP_BAND_CF_DEFAULT
-#define CVVDP_BAND_CF_DEFAULT false   // conflict-free phase A
-#endif
-#ifndef CVVDP_BAND_PA_DEFAULT
-#define CVVDP_BAND_PA_DEFAULT false   // power of the difference term in phase A
-#endif
-#ifndef CVVDP_BAND_LAG_DEFAULT
-#define CVVDP_BAND_LAG_DEFAULT false  // phase C trails by 16 rows (no barrier between phases B and C)
-#endif
+// Band kernel configuration (B2Geom / k_band2): 48-column strips, conflict-free phase A, phase C trailing by 16 rows.
+#define CVVDP_BAND_EW 60
+#define CVVDP_BAND_CF true
+#define CVVDP_BAND_LAG true
 
 namespace {
 
@@ -72,8 +64,6 @@ struct cvvdp_b200_ctx {
     int blur_pad = 0;
     int max_smem_optin = 0;
     int num_sms = 148;
-    int band_ew = CVVDP_BAND_EW_DEFAULT;   // band kernel strip geometry of the current plan
-    int band_variant = -1;                 // A/B builds: CVVDP_B200_BAND_VARIANT
     cudaStream_t copy_stream = nullptr, work_stream = nullptr;
     Staging stage[2];
     float *feat_out = nullptr;    // caller's device buffer for the feature tensors (feature mode)
@@ -83,6 +73,7 @@ struct cvvdp_b200_ctx {
     size_t q_dev_bytes = 0;
     void *hm_dev = nullptr;
     size_t hm_dev_bytes = 0;
+    int *flags_dev = nullptr;     // [0..2] input validation counters, [3] clip frame 0 seen; then one float: DKL-A sum of test frame 0
     long long launches = 0;
     bool prof = false;
     struct ProfRec {
@@ -377,16 +368,15 @@ ClipView to_view(const cvvdp_b200_clip *c) {
 }
 
 // ---- band kernel dispatch ------------------------------------------------------------------------
-// Strip geometry (EW) and the conflict-free phase A (CF) are fixed per plan (ctx->band_ew / band_cf); the
-// level-dependent flags (blur, heat map, beta == 2) and the feature mode select the instantiation.
-template <int EW, bool CF, bool PA, bool LAG, bool FEAT>
+// The level-dependent flags (blur, heat map, beta == 2) and the feature mode select the instantiation.
+template <int EW, bool CF, bool LAG, bool FEAT>
 void launch_band_v(const BandArgs &ba, dim3 grid, cudaStream_t st, int variant) {
     typedef void (*BandFn)(const BandArgs);
     static const BandFn table[8] = {
-        k_band2<EW, CF, PA, LAG, false, false, false, FEAT>, k_band2<EW, CF, PA, LAG, false, false, true, FEAT>,
-        k_band2<EW, CF, PA, LAG, false, true, false, FEAT>,  k_band2<EW, CF, PA, LAG, false, true, true, FEAT>,
-        k_band2<EW, CF, PA, LAG, true, false, false, FEAT>,  k_band2<EW, CF, PA, LAG, true, false, true, FEAT>,
-        k_band2<EW, CF, PA, LAG, true, true, false, FEAT>,   k_band2<EW, CF, PA, LAG, true, true, true, FEAT>};
+        k_band2<EW, CF, LAG, false, false, false, FEAT>, k_band2<EW, CF, LAG, false, false, true, FEAT>,
+        k_band2<EW, CF, LAG, false, true, false, FEAT>,  k_band2<EW, CF, LAG, false, true, true, FEAT>,
+        k_band2<EW, CF, LAG, true, false, false, FEAT>,  k_band2<EW, CF, LAG, true, false, true, FEAT>,
+        k_band2<EW, CF, LAG, true, true, false, FEAT>,   k_band2<EW, CF, LAG, true, true, true, FEAT>};
     static bool attr_set[8] = {false, false, false, false, false, false, false, false};
     typedef Band2Smem<EW, B2Lag<LAG>::DFR> Smem;
     BandFn kfn = table[variant];
@@ -397,25 +387,9 @@ void launch_band_v(const BandArgs &ba, dim3 grid, cudaStream_t st, int variant) 
     CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(Smem), st, ba);
 }
 
-#define CVVDP_BAND_DEFAULTS CVVDP_BAND_EW_DEFAULT, CVVDP_BAND_CF_DEFAULT, CVVDP_BAND_PA_DEFAULT, CVVDP_BAND_LAG_DEFAULT
-void launch_band(cvvdp_b200_ctx *ctx, const BandArgs &ba, dim3 grid, cudaStream_t st, int variant, bool feat) {
-    if (feat) {
-        launch_band_v<CVVDP_BAND_DEFAULTS, true>(ba, grid, st, variant);
-        return;
-    }
-#ifdef CVVDP_BAND_AB  // A/B builds carry several (geometry, CF, PA, LAG) combinations: bit 0 CF, 1 EW60, 2 PA, 3 LAG
-    switch (ctx->band_variant) {
-        case 0: return launch_band_v<64, false, false, false, false>(ba, grid, st, variant);
-        case 3: return launch_band_v<60, true, false, false, false>(ba, grid, st, variant);
-        case 5: return launch_band_v<64, true, true, false, false>(ba, grid, st, variant);
-        case 7: return launch_band_v<60, true, true, false, false>(ba, grid, st, variant);
-        case 11: return launch_band_v<60, true, false, true, false>(ba, grid, st, variant);
-        case 15: return launch_band_v<60, true, true, true, false>(ba, grid, st, variant);
-        default: break;
-    }
-#endif
-    (void)ctx;
-    launch_band_v<CVVDP_BAND_DEFAULTS, false>(ba, grid, st, variant);
+void launch_band(const BandArgs &ba, dim3 grid, cudaStream_t st, int variant, bool feat) {
+    if (feat) launch_band_v<CVVDP_BAND_EW, CVVDP_BAND_CF, CVVDP_BAND_LAG, true>(ba, grid, st, variant);
+    else launch_band_v<CVVDP_BAND_EW, CVVDP_BAND_CF, CVVDP_BAND_LAG, false>(ba, grid, st, variant);
 }
 
 // One block of frames [f0, f1) (f1 - f0 <= block_frames), inputs resident on the device.
@@ -450,6 +424,8 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ta.fl = info.filter_len;
         ta.padding = job.padding;
         ta.out = ctx->lv[0].g;
+        ta.flags = ctx->flags_dev;
+        ta.mean0 = reinterpret_cast<float *>(ctx->flags_dev + 4);
         if (job.n_frames == 1) {  // image: R = DKL, no transient channel (cvvdp_metric.py:462-465)
             ta.taps[0][0] = ta.taps[1][0] = ta.taps[2][0] = 1.f;
             ta.taps[3][0] = 0.f;
@@ -606,7 +582,7 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
                        (double)pairs * 2 * 16.0 * ((double)ba.h * ba.w + (double)ba.hc * ba.wc) +
                            (do_hm ? (double)pairs * 4.0 * ba.h * ba.w : 0.0));
         const int variant = (ba.do_blur ? 4 : 0) | (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
-        launch_band(ctx, ba, grid, st, variant, do_feat);
+        launch_band(ba, grid, st, variant, do_feat);
     }
     {
         BasebandArgs bb;
@@ -782,6 +758,10 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
         cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming);
     }
+    if (cudaMalloc(&ctx->flags_dev, 32) != cudaSuccess || cudaMemset(ctx->flags_dev, 0, 32) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, CVVDP_ERR_NOMEM, "cannot allocate the validation flags");
+    }
     auto kr2 = k_reduce2<8>;
     cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem<8>));
     auto kt = k_temporal;
@@ -798,6 +778,7 @@ void cvvdp_b200_destroy(cvvdp_b200_ctx *ctx) {
     free_plan(ctx);
     if (ctx->q_dev) cudaFree(ctx->q_dev);
     if (ctx->hm_dev) cudaFree(ctx->hm_dev);
+    if (ctx->flags_dev) cudaFree(ctx->flags_dev);
     for (auto &s : ctx->stage) {
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.consumed) cudaEventDestroy(s.consumed);
@@ -862,17 +843,6 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     if ((size_t)info.filter_len * 3 * CVVDP_TEMPORAL_THREADS * sizeof(float) > (size_t)std::min(ctx->max_smem_optin, 227 * 1024))
         return fail(ctx, CVVDP_ERR_UNSUPPORTED, "temporal filter of %d taps does not fit in shared memory", info.filter_len);
 
-    ctx->band_ew = CVVDP_BAND_EW_DEFAULT;
-    ctx->band_variant = -1;
-#ifdef CVVDP_BAND_AB
-    if (const char *bv = getenv("CVVDP_B200_BAND_VARIANT")) {  // A/B builds only
-        const int v = atoi(bv);
-        if (!job->features && (v == 0 || v == 3 || v == 5 || v == 7 || v == 11 || v == 15)) {
-            ctx->band_variant = v;
-            ctx->band_ew = (v & 2) ? 60 : 64;
-        }
-    }
-#endif
     // workspace per frame of a block (all batch items)
     const size_t B = (size_t)job->batch;
     const bool do_hm = job->heatmap == CVVDP_HEATMAP_RAW;
@@ -906,7 +876,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.w = info.band_width[i];
         lv.do_blur = (ctx->blur_pad > 0 && lv.h > ctx->blur_pad && lv.w > ctx->blur_pad) ? 1 : 0;  // cvvdp_metric.py:965
         {   // column strips of EW - 12 pixels; the rows are split into segments only when there are too few CTAs
-            const int sw = ctx->band_ew - 2 * CVVDP_BHALO;
+            const int sw = CVVDP_BAND_EW - 2 * CVVDP_BHALO;
             lv.tiles_x = (lv.w + sw - 1) / sw;
             // the split depends on the level geometry only, never on the batch or block size, so that
             // the summation order (hence every bit of Q_per_ch) is independent of how frames are
@@ -963,8 +933,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.hm = do_hm ? (float *)(base + off_h[i]) : nullptr;
         lv.feat = job->features ? (float4 *)(base + off_f[i]) : nullptr;
         lv.lut = (float4 *)(base + off_l[i]);
-        lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), ctx->band_ew, CVVDP_B2_RB) &&
-                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), ctx->band_ew / 2 + 2, CVVDP_B2_CR) &&
+        lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_BAND_EW, CVVDP_B2_RB) &&
+                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_BAND_EW / 2 + 2, CVVDP_B2_CR) &&
                    make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<8>::IH, 1);
         float rows[4][CVVDP_CSF_LUT_N];
         for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
@@ -1324,6 +1294,22 @@ int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, con
     return CVVDP_OK;
 }
 
+int cvvdp_b200_input_stats(cvvdp_b200_ctx *ctx, cvvdp_b200_input_report *out, int reset) {
+    if (!ctx || !out) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    CU_CHECK(ctx, cudaDeviceSynchronize());  // the temporal kernels of every stream of this context have finished
+    int h[8];
+    CU_CHECK(ctx, cudaMemcpy(h, ctx->flags_dev, sizeof(h), cudaMemcpyDeviceToHost));
+    out->out_of_range = h[0];
+    out->nan = h[1];
+    out->inf = h[2];
+    float sum;
+    memcpy(&sum, &h[4], sizeof(float));
+    out->first_frame_sum = (double)sum;
+    if (reset) CU_CHECK(ctx, cudaMemset(ctx->flags_dev, 0, 32));
+    return CVVDP_OK;
+}
+
 int64_t cvvdp_b200_launch_count(const cvvdp_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 int cvvdp_b200_temporal_filters(const cvvdp_b200_ctx *ctx, float fps, float *filters) {
@@ -1364,12 +1350,7 @@ int cvvdp_b200_set_feature_output(cvvdp_b200_ctx *ctx, float *features_dev) {
 
 int cvvdp_b200_band_strip_width(const cvvdp_b200_ctx *ctx, int level) {
     if (!ctx || !ctx->planned || level < 0 || level + 1 >= (int)ctx->lv.size()) return 0;
-    return ctx->band_ew - 2 * CVVDP_BHALO;
-}
-
-int cvvdp_b200_band_kernel_id(const cvvdp_b200_ctx *ctx, int level) {
-    if (!ctx || !ctx->planned || level < 0 || level + 1 >= (int)ctx->lv.size()) return 0;
-    return 2;
+    return CVVDP_BAND_EW - 2 * CVVDP_BHALO;
 }
 
 int cvvdp_b200_profile_enable(cvvdp_b200_ctx *ctx, int enable) {

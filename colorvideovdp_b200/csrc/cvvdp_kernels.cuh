@@ -120,10 +120,30 @@ __device__ __forceinline__ void yuv_fetch_rgb(const ClipView &cv, const YuvDev &
     rgb[2] = fminf(fmaxf(Y + yu.m_bu * uv[0], 0.f), 1.f);
 }
 
-// Raw pixel of frame `fidx` (index inside the view) -> DKL triple.
+// Input validation of the fused path (display_model.py:335-337, video_source.py:48-59): bit 0 = a value outside
+// 0..1 reaches an EOTF that clamps, bit 1 = NaN, bit 2 = Inf.  Only floating-point clips can carry any of them.
+__device__ __forceinline__ unsigned input_bits(float v, bool check_range) {
+    unsigned f = (check_range && (v > 1.f || v < 0.f)) ? 1u : 0u;
+    f |= (v != v) ? 2u : 0u;
+    f |= (fabsf(v) == INFINITY) ? 4u : 0u;
+    return f;
+}
+// Warp-aggregated publication of the validity bits: one atomic per set bit and warp, only when something is wrong.
+__device__ __forceinline__ void publish_input_bits(unsigned bits, int *flags) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bits |= __shfl_xor_sync(0xffffffffu, bits, o);
+    if ((threadIdx.x & 31) == 0 && bits != 0u && flags != nullptr) {
+        if (bits & 1u) atomicAdd(&flags[0], 1);
+        if (bits & 2u) atomicAdd(&flags[1], 1);
+        if (bits & 4u) atomicAdd(&flags[2], 1);
+    }
+}
+
+// Raw pixel of frame `fidx` (index inside the view) -> DKL triple.  vbits (optional) collects input_bits.
 __device__ __forceinline__ void pixel_to_dkl(const ClipView &cv, long long base, int fidx, int cin, int dtype,
                                              const DisplayDev &d, float &o0, float &o1, float &o2,
-                                             const YuvDev *yu = nullptr, int b = 0, int y = 0, int x = 0) {
+                                             const YuvDev *yu = nullptr, int b = 0, int y = 0, int x = 0,
+                                             unsigned *vbits = nullptr) {
     float v[3];
     const long long off = base + (long long)fidx * cv.s[2];
     if (yu != nullptr && yu->chroma != 0) {
@@ -133,6 +153,10 @@ __device__ __forceinline__ void pixel_to_dkl(const ClipView &cv, long long base,
         if (cin == 3) {
             v[1] = load_unpack(cv.data, off + cv.s[1], dtype);
             v[2] = load_unpack(cv.data, off + 2 * cv.s[1], dtype);
+        }
+        if (vbits != nullptr && dtype >= CVVDP_DTYPE_F16) {
+            const bool rng = d.eotf != CVVDP_EOTF_LINEAR && d.eotf != CVVDP_EOTF_NONE;
+            for (int i = 0; i < cin; ++i) *vbits |= input_bits(v[i], rng);
         }
     }
     eotf_forward(v, cin, d);  // CVVDP_EOTF_NONE: values pass through (the host then sets M = identity)
@@ -208,6 +232,8 @@ struct TemporalArgs {
     int F_total, f0, f1, fl, padding;
     YuvDev yuv;
     float4 *out;  // level 0: [B][n][2][H*W]
+    int *flags;   // [0..2]: warps that saw out-of-range / NaN / Inf input values (null: no validation)
+    float *mean0; // sum over the pixels of clip frame 0 of the TEST video of its achromatic DKL channel (video_source.py:64-71)
     float taps[4][CVVDP_MAX_FILTER_LEN];  // taps[c][k] multiplies frame f-(fl-1)+k (= F_c flipped, l.556)
 };
 
@@ -227,13 +253,15 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
     float4 *out = a.out + ((long long)b * n * 2 + v) * npix + p;
     int slot = 0, last_s = -1;
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    unsigned vbits = 0u;
     for (int t = a.f0 - (fl - 1); t < a.f1; ++t) {
         int s = t;
         if (s < 0) s = (a.padding == CVVDP_PAD_REPLICATE) ? 0 : symmetric_frame_index(s, a.F_total);
         if (s != last_s) {
-            pixel_to_dkl(cv, base, frame_slot(cv, s), a.cin, a.dtype, a.dd, d0, d1, d2, &a.yuv, b, y, x);
+            pixel_to_dkl(cv, base, frame_slot(cv, s), a.cin, a.dtype, a.dd, d0, d1, d2, &a.yuv, b, y, x, &vbits);
             last_s = s;
         }
+        if (t == 0 && v == 0 && a.mean0 != nullptr) atomicAdd(a.mean0, d0);  // rare path: images and odd layouts
         ring[(slot * 3 + 0) * CVVDP_TEMPORAL_THREADS + tid] = d0;
         ring[(slot * 3 + 1) * CVVDP_TEMPORAL_THREADS + tid] = d1;
         ring[(slot * 3 + 2) * CVVDP_TEMPORAL_THREADS + tid] = d2;
@@ -253,6 +281,11 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
             out[(long long)(t - a.f0) * 2 * npix] = make_float4(o0, o1, o2, o3);
         }
         slot = slot + 1 == fl ? 0 : slot + 1;
+    }
+    if (vbits != 0u && a.flags != nullptr) {  // per thread: this kernel has partial warps, and the case is an error path
+        if (vbits & 1u) atomicAdd(&a.flags[0], 1);
+        if (vbits & 2u) atomicAdd(&a.flags[1], 1);
+        if (vbits & 4u) atomicAdd(&a.flags[2], 1);
     }
 }
 
@@ -299,7 +332,7 @@ __device__ __forceinline__ unsigned lds_u8(const unsigned char *p) {
 // order as bits_to_dkl (v1*M1, then fma with v0*M0, then fma with v2*M2), two lanes per instruction.
 template <bool USE_LUT>
 __device__ __forceinline__ void bits_to_dkl2(const TemporalArgs &a, const float *lut, const unsigned ba[3], const unsigned bb[3],
-                                             float2 &d0, float2 &d1, float2 &d2) {
+                                             float2 &d0, float2 &d1, float2 &d2, unsigned &vbits) {
     float va[3], vb[3];
     if (USE_LUT) {
 #pragma unroll
@@ -316,6 +349,11 @@ __device__ __forceinline__ void bits_to_dkl2(const TemporalArgs &a, const float 
                 case CVVDP_DTYPE_F16: va[i] = half_bits_to_float((unsigned short)ba[i]); vb[i] = half_bits_to_float((unsigned short)bb[i]); break;
                 default: va[i] = bits_as_float(ba[i]); vb[i] = bits_as_float(bb[i]);
             }
+        }
+        if (a.dtype >= CVVDP_DTYPE_F16) {  // integer code values cannot be out of range, NaN or Inf
+            const bool rng = a.dd.eotf != CVVDP_EOTF_LINEAR && a.dd.eotf != CVVDP_EOTF_NONE;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) vbits |= input_bits(va[i], rng) | input_bits(vb[i], rng);
         }
         eotf_forward(va, a.cin, a.dd);
         eotf_forward(vb, a.cin, a.dd);
@@ -404,7 +442,10 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
         cp_async_commit();
     };
     // stage 1: raw -> DKL for the G frames of the chunk in the raw stage (rolled; three frames in flight)
-    auto convert_chunk = [&]() {
+    unsigned vbits = 0u;  // input validity bits seen by this thread (floating-point clips only)
+    float msum = 0.f;     // achromatic DKL sum of this thread's two pixels of clip frame 0 (test video)
+    const int it_zero = v == 0 && a.mean0 != nullptr ? FL - 1 - a.f0 : -1;  // iteration that holds clip frame 0
+    auto convert_chunk = [&](int it0) {
 #pragma unroll 3
         for (int g = 0; g < G; ++g) {
             const unsigned char *q = raw + g * frame_bytes;
@@ -424,7 +465,8 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
                 }
             }
             float2 d0, d1, d2;
-            bits_to_dkl2<USE_LUT>(a, s_lut, ba, bb, d0, d1, d2);
+            bits_to_dkl2<USE_LUT>(a, s_lut, ba, bb, d0, d1, d2, vbits);
+            if (it0 + g == it_zero) msum = d0.x + d0.y;  // uniform
             dkl[(g * 3 + 0) * CVVDP_T2S_THREADS] = d0;
             dkl[(g * 3 + 1) * CVVDP_T2S_THREADS] = d1;
             dkl[(g * 3 + 2) * CVVDP_T2S_THREADS] = d2;
@@ -437,7 +479,7 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
         for (int h = 0; h < 2; ++h) {  // the two chunks of one ring period
             cp_async_wait_all();
             __syncwarp();          // the chunk's raw values (copied by all lanes) are visible
-            convert_chunk();
+            convert_chunk((c + h) * G);
             __syncwarp();          // every lane is done with the raw stage before it is refilled
             issue_chunk(c + h + 1);
 #pragma unroll
@@ -480,6 +522,12 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
         }
     }
     cp_async_wait_all();
+    if (!USE_LUT) publish_input_bits(vbits, a.flags);
+    if (it_zero >= 0 && it_zero < NI) {  // uniform per CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+        if (lane == 0) atomicAdd(a.mean0, msum);
+    }
 }
 
 // =================================================================================================
@@ -727,12 +775,9 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' p
 }
 
 // Contrast / CSF / mutual-masking inputs of one pixel (phase 1).
-// PA: df returns safe_pow(|T'-R'|, p) (the numerator of D, cvvdp_metric.py:855) instead of |T'-R'|: its two MUFU
-// operations per channel then run in phase A, whose XU pipe has slack, instead of phase C, which is XU-bound.
-template <bool FEAT = false, bool PA = false>
+template <bool FEAT = false>
 __device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lut, float4 gt, float4 gr, float4 et,
-                                           float4 er, float4 &mm, float4 &df, float4 *feat_t = nullptr, float4 *feat_r = nullptr,
-                                           float eps_p = 0.f) {
+                                           float4 er, float4 &mm, float4 &df, float4 *feat_t = nullptr, float4 *feat_r = nullptr) {
     const float4 lt = gt - et, lr = gr - er;  // Laplacian (lpyr_dec.py:387)
     const float Lt = fmaxf(et.x, 0.01f), Lr = fmaxf(er.x, 0.01f);  // l.394
     const float it = a.mul * f_rcp(Lt), ir = a.mul * f_rcp(Lr);
@@ -764,13 +809,6 @@ __device__ __forceinline__ void band_pixel(const BandArgs &a, const float4 *s_lu
                      fminf(fabsf(T23.x), fabsf(R23.x)), fminf(fabsf(T23.y), fabsf(R23.y)));
     const float2 d01 = add2(T01, make_float2(-R01.x, -R01.y)), d23 = add2(T23, make_float2(-R23.x, -R23.y));
     df = make_float4(fabsf(d01.x), fabsf(d01.y), fabsf(d23.x), fabsf(d23.y));
-    if (PA) {
-        const float2 eps2 = bc2(a.eps), p2 = bc2(a.p), nep = bc2(-eps_p);
-        const float2 q01 = add2(make_float2(df.x, df.y), eps2), q23 = add2(make_float2(df.z, df.w), eps2);
-        const float2 g01 = mul2(p2, make_float2(f_lg2(q01.x), f_lg2(q01.y))), g23 = mul2(p2, make_float2(f_lg2(q23.x), f_lg2(q23.y)));
-        const float2 P01 = add2(make_float2(f_ex2(g01.x), f_ex2(g01.y)), nep), P23 = add2(make_float2(f_ex2(g23.x), f_ex2(g23.y)), nep);
-        df = make_float4(P01.x, P01.y, P23.x, P23.y);
-    }
     if (FEAT) {  // |T_f| S and |R_f| S without the masking gain
         *feat_t = make_float4(fabsf(T01.x) * a.inv_gain[0], fabsf(T01.y) * a.inv_gain[1], fabsf(T23.x) * a.inv_gain[2], fabsf(T23.y) * a.inv_gain[3]);
         *feat_r = make_float4(fabsf(R01.x) * a.inv_gain[0], fabsf(R01.y) * a.inv_gain[1], fabsf(R23.x) * a.inv_gain[2], fabsf(R23.y) * a.inv_gain[3]);
@@ -782,7 +820,6 @@ __device__ __forceinline__ float spow_fast(float x, float p, float eps, float ep
 }
 
 // Masking + clamp + pooling term of one pixel (phase 4).  m = blurred mutual-masking signal.
-template <bool PA = false>
 __device__ __forceinline__ float4 band_mask(const BandArgs &a, float4 m, float4 df, const float *eps_q, float eps_p) {
     // channel pairs (A-sust, RG) and (YV, A-trans) go through packed fp32x2 arithmetic; MUFU stays scalar
     const float2 mc2 = bc2(a.mc), eps2 = bc2(a.eps);
@@ -801,17 +838,10 @@ __device__ __forceinline__ float4 band_mask(const BandArgs &a, float4 m, float4 
     M23 = fma2(bc2(t23.x), make_float2(a.X[10], a.X[11]), M23);
     M01 = fma2(bc2(t23.y), make_float2(a.X[12], a.X[13]), M01);
     M23 = fma2(bc2(t23.y), make_float2(a.X[14], a.X[15]), M23);
-    float2 P01, P23;
-    if (PA) {  // df already is safe_pow(|T'-R'|, p)
-        P01 = make_float2(df.x, df.y);
-        P23 = make_float2(df.z, df.w);
-    } else {
-        const float2 d01 = add2(make_float2(df.x, df.y), eps2), d23 = add2(make_float2(df.z, df.w), eps2);
-        const float2 p2 = bc2(a.p), nep = bc2(-eps_p);
-        const float2 g01 = mul2(p2, make_float2(f_lg2(d01.x), f_lg2(d01.y))), g23 = mul2(p2, make_float2(f_lg2(d23.x), f_lg2(d23.y)));
-        P01 = add2(make_float2(f_ex2(g01.x), f_ex2(g01.y)), nep);
-        P23 = add2(make_float2(f_ex2(g23.x), f_ex2(g23.y)), nep);
-    }
+    const float2 d01 = add2(make_float2(df.x, df.y), eps2), d23 = add2(make_float2(df.z, df.w), eps2);
+    const float2 p2 = bc2(a.p), nep = bc2(-eps_p);
+    const float2 g01 = mul2(p2, make_float2(f_lg2(d01.x), f_lg2(d01.y))), g23 = mul2(p2, make_float2(f_lg2(d23.x), f_lg2(d23.y)));
+    const float2 P01 = add2(make_float2(f_ex2(g01.x), f_ex2(g01.y)), nep), P23 = add2(make_float2(f_ex2(g23.x), f_ex2(g23.y)), nep);
     // D_u = P / (1 + M);  D = Dmax * D_u / (Dmax + D_u)  ==  P / ((1 + M) + P / Dmax)   (cvvdp_metric.py:855, 948-950)
     const float2 idm2 = bc2(a.inv_dmax);
     const float2 n01 = fma2(P01, idm2, M01), n23 = fma2(P23, idm2, M23);
@@ -835,8 +865,11 @@ __device__ __forceinline__ float4 band_mask(const BandArgs &a, float4 m, float4 
 // masking, clamp and pooling.
 // Geometry (template EW): 64 -> 52-column strips, phases B/C use 104 of 128 threads; 60 -> 48-column
 // strips, phase A uses 120 threads and phases B/C exactly three warps (no idle lanes in a running warp).
-// The kernel is bound by the shared-memory pipe (~70 % busy at 4K) ahead of the FP32 pipe (~52 %), so
-// shared-memory wavefronts per pixel are the figure of merit.
+// Shipped configuration: EW = 60, CF and LAG on (round-2 A/B on one box, 4K x 120 frames, level 0: 17.96 ms for
+// round 1's kernel, 17.52 with EW = 60 + CF, 17.11 with LAG added; profiles/r02_ab_band_variants_pa_lag.txt).
+// The kernel is bound by the FP32 pipe with additive dispatch interference from MUFU / ALU-pipe instructions
+// and a ~70 % busy shared-memory pipe; profiles/r02_microbench_smsp_pipes.txt has the measured per-instruction
+// costs (FFMA2 2 cycles, ALU-pipe op 2, MUFU 8, LDS.128 16 per scheduler) behind DESIGN.md section 5.
 // =================================================================================================
 #define CVVDP_B2_RB 8
 #define CVVDP_B2_THREADS 128
@@ -917,7 +950,6 @@ __device__ __forceinline__ void band2_stage(const BandArgs &a, Band2Smem<EW, DFR
 // cover eight distinct 16-byte bank groups.  The column parity only enters the horizontal expand weights
 // ((.1,.8,.1) even, (0,.5,.5) odd), which become per-lane values: bit-identical results, one extra
 // packed multiply per (row, video).
-// PA: the power of the difference term runs in phase A (see band_pixel).
 // LAG: phase C trails phase B by 16 rows instead of 6, so every row of its 13-row window was written in an EARLIER
 // step and phases B and C need no barrier between them (two barriers per step instead of three; the FP32-only
 // horizontal blur of some warps overlaps the MUFU-heavy masking of others).  The |T'-R'| ring then holds 24 rows.
@@ -925,7 +957,7 @@ template <bool LAG>
 struct B2Lag {
     static constexpr int DFR = LAG ? 24 : CVVDP_B2_DFR;
 };
-template <int EW, bool CF, bool PA, bool LAG, bool BLUR, bool HM, bool BETA2, bool FEAT = false>
+template <int EW, bool CF, bool LAG, bool BLUR, bool HM, bool BETA2, bool FEAT = false>
 __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_constant__ BandArgs a) {
     CVVDP_DYN_SMEM(smem_raw);
     constexpr bool LAGC = LAG && BLUR;           // without the blur phase C reads the rows of its own step
@@ -1026,7 +1058,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int ry = 2 * qy + (k >> 1), rx = 2 * qx + ((k & 1) ^ sw_odd);
-                    band_pixel<FEAT, PA>(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm[k], df[k], &ft[k], &fr[k], eps_p);
+                    band_pixel<FEAT>(a, sm.lut, sm.fine[0][ry][rx], sm.fine[1][ry][rx], e[0][k], e[1][k], mm[k], df[k], &ft[k], &fr[k]);
                 }
                 const int ix = ex0 + 2 * qx - x0;  // even; the pair (ix, ix+1) is inside or outside the strip together
                 const bool in_strip = ix >= 0 && ix < SW;
@@ -1111,7 +1143,7 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
                     } else {
                         m = sm.mm[(gy - a0) & (CVVDP_B2_RB - 1)][gx - ex0];
                     }
-                    D[o] = band_mask<PA>(a, m, sm.df[LAG ? dbase + o : (gy & (CVVDP_B2_DFR - 1))][c_ix], eps_q, eps_p);
+                    D[o] = band_mask(a, m, sm.df[LAG ? dbase + o : (gy & (CVVDP_B2_DFR - 1))][c_ix], eps_q, eps_p);
                 }
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {

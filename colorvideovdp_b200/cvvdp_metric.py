@@ -287,6 +287,30 @@ class cvvdp(vq_metric):
                                hmh.data_ptr() if hmh is not None else None)
         return Qh, hmh
 
+    def report_input_problems(self, vid_source, n_pixels, saw_frame0):
+        """The input checks the reference makes frame by frame on the host, from the counters the fused front end
+        keeps on the device: 'Pixel outside the valid range 0-1' (display_model.py:335-337), NaN and photometric-scale
+        warnings (video_source.py:48-72, once per video source) and the failure on non-finite differences
+        (cvvdp_metric.py:906-907: a NaN pixel always reaches D).  Synchronises the device; call after the hot loop."""
+        rep = self._ctx.input_stats(reset=True)
+        shown = getattr(vid_source, "warning_shown", False) if vid_source is not None else False
+        if rep.out_of_range:
+            logging.warning("Pixel outside the valid range 0-1")
+        if rep.nan and not shown:
+            shown = True
+            logging.warning("Image contains one or more NaN values")
+        if saw_frame0 and n_pixels > 0 and not shown:
+            f_mean = rep.first_frame_sum / n_pixels
+            logging.debug(f"Content mean={f_mean}")
+            if f_mean <= 1:
+                logging.warning("The mean color value is less than 1 - the image may not be scaled in absolute "
+                                "photometric units!")
+        if vid_source is not None:
+            vid_source.warning_shown = shown
+            vid_source.first_frame = False
+        if rep.nan:
+            raise AssertionError("Must not be nan")
+
     def _alloc_outputs(self, B, C, F, L, H, W):
         Q = torch.zeros((B, C, F, L), dtype=torch.float32, device=self.device)
         hm = torch.zeros((1, 1, F, H, W), dtype=torch.float16, device=self.device) if self.do_heatmap else None
@@ -385,6 +409,7 @@ class cvvdp(vq_metric):
         display model is the plugin's business)."""
         fl = 1 if F == 1 else int(math.ceil(0.250 * fps / 2) * 2) + 1  # cvvdp_metric.py:1059
         cache_t, cache_r = {}, {}
+        vs._frames_pulled_through_plugin = True  # the source's own get_*_frame did the input checks
 
         def fetch(f):
             if f not in cache_r:
@@ -425,6 +450,10 @@ class cvvdp(vq_metric):
         only covers those frames unless the caller all-reduces stats['Q_per_ch'] first."""
         H, W, F = vid_source.get_video_size()
         Q_per_ch, heatmap = self.compute_q_per_ch(vid_source, frame_range)
+        if isinstance(getattr(vid_source, "dm_photometry", None), vvdp_display_photo_eotf) and \
+                not hasattr(vid_source, "_frames_pulled_through_plugin"):
+            self.report_input_problems(vid_source, vid_source.get_batch_size() * H * W,
+                                       frame_range is None or frame_range[0] == 0)
         Q_jod = self.do_pooling_and_jods(Q_per_ch if frame_range is None else Q_per_ch[:, :, frame_range[0]:frame_range[1]])
         stats = self._make_stats(Q_per_ch, heatmap, vid_source, H, W, F)
         return (Q_jod.squeeze(), stats)

@@ -1,12 +1,17 @@
-"""Frame sharding across the GPUs of one box.
+"""Sharding a batch of clips across the GPUs of one box.
 
 Every Q_per_ch[b, c, f, band] depends only on frames f-(fl-1)..f of item b (causal FIR,
-cvvdp_metric.py:554-560), so rank r evaluates a contiguous frame range of every batch item (reading
-fl-1 halo frames before it) into a zero-initialised full-size Q_per_ch buffer.  ONE all-reduce (sum)
-of that small buffer -- each element is x + 0 + ... + 0, hence bit-exact -- gives every rank the
-whole tensor, and every rank runs the identical final pooling.  One process per GPU, launched with
-torchrun; `torch.distributed` (NCCL over NVLink on GPUs, gloo in the CPU tests) is the plumbing.
+cvvdp_metric.py:554-560), so the work is a flat sequence of (item, frame) units.  It is cut into one
+CONTIGUOUS run per rank (`work_shard`): with at least as many items as ranks a rank owns whole items and
+reads no temporal halo at all; a single clip degenerates to plain frame sharding, where a rank reads
+the fl-1 frames before its range as a halo through the front end only.  Every rank writes its units
+into a zero-initialised full-size Q_per_ch buffer; ONE all-reduce (sum) of that small buffer -- each
+element is x + 0 + ... + 0, hence bit-exact -- gives every rank the whole tensor, and every rank runs the
+identical final pooling.  One process per GPU, launched with torchrun; `torch.distributed` (NCCL over
+NVLink on GPUs, gloo in the CPU tests) is the plumbing.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -40,6 +45,87 @@ def predict_frame_sharded(metric, test_win, ref_win, first_frame, n_frames, fram
         dist.all_reduce(Q, op=dist.ReduceOp.SUM, group=group)
     jod = metric.do_pooling_and_jods(Q)
     return jod, Q
+
+
+def work_shard(batch, n_frames, rank, world_size):
+    """This rank's contiguous run of the flattened (item, frame) sequence as a list of pieces
+    (item, f_lo, f_hi).  batch >= world_size and divisible: whole items only (no temporal halo);
+    batch == 1: plain frame sharding."""
+    total = batch * n_frames
+    lo, hi = (rank * total) // world_size, ((rank + 1) * total) // world_size
+    pieces = []
+    b = lo // n_frames if n_frames else 0
+    while lo < hi:
+        f_lo = lo - b * n_frames
+        f_hi = min(hi - b * n_frames, n_frames)
+        pieces.append((b, f_lo, f_hi))
+        lo = b * n_frames + f_hi
+        b += 1
+    return pieces
+
+
+def predict_sharded(metric, pieces, batch, n_frames, frames_per_second, group=None):
+    """Evaluate this rank's pieces and combine across ranks.
+
+    pieces: list of (item, f_lo, f_hi, first_frame, test_win, ref_win); the window tensors are
+    [1,C,win,H,W] (host or device) holding clip frames [first_frame, first_frame + win) of that item --
+    at least `needed_window(...)` of [f_lo, f_hi).  Returns (JOD [batch] identical on every rank,
+    Q_per_ch [batch,C,F,L] on the metric's device)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    Q = None
+    for item, f_lo, f_hi, first_frame, test_win, ref_win in pieces:
+        Qi, _ = metric.q_per_ch_from_tensors(test_win, ref_win, n_frames, frames_per_second, (f_lo, f_hi), first_frame)
+        Qi = Qi.to(metric.device, non_blocking=True)
+        if Q is None:
+            Q = torch.zeros((batch,) + tuple(Qi.shape[1:]), dtype=torch.float32, device=metric.device)
+        Q[item] += Qi[0]  # pieces of one item cover disjoint frames; the rest of Qi is zero
+    if Q is None:
+        raise RuntimeError(f"no work for this rank ({batch} items x {n_frames} frames over {world} ranks)")
+    if world > 1:
+        dist.all_reduce(Q, op=dist.ReduceOp.SUM, group=group)
+    jod = metric.do_pooling_and_jods(Q)
+    # range / NaN warnings and the reference's failure on NaN input, from the front end's device counters
+    H, W = pieces[0][4].shape[3], pieces[0][4].shape[4]
+    n0 = sum(1 for p in pieces if p[1] == 0)
+    metric.report_input_problems(None, n0 * H * W, n0 > 0)
+    return jod, Q
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (CPU affinity + preferred memory node) to the NUMA node of its GPU, so that the pinned
+    host buffers it allocates afterwards are local to the GPU's PCIe root port: with one process per GPU on a
+    two-socket host, remote pinned memory makes every upload cross the socket interconnect.  Best effort --
+    returns a short description of what was done (for the bench line)."""
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bus}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpulist = open(f"{base}/local_cpulist").read().strip()
+    except Exception as e:  # no sysfs entry, attribute missing in this torch build, ...
+        return f"unbound ({type(e).__name__})"
+    cpus = set()
+    for part in cpulist.split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    allowed = os.sched_getaffinity(0)
+    cpus &= allowed
+    if not cpus or cpus == allowed and node < 0:
+        return f"unbound (node {node}, one NUMA domain)"
+    os.sched_setaffinity(0, cpus)
+    how = f"cpus {cpulist}"
+    if node >= 0:
+        try:  # set_mempolicy(MPOL_PREFERRED, {node}): x86-64 syscall 238
+            import ctypes
+            mask = ctypes.c_ulong(1 << node)
+            rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            how += f", memory node {node}" + ("" if rc == 0 else " (set_mempolicy refused)")
+        except Exception:
+            pass
+    return "bound to " + how
 
 
 def _overlap(a_lo, a_hi, b_lo, b_hi):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CVVDP_B200_ABI_VERSION 3
+#define CVVDP_B200_ABI_VERSION 4
 #define CVVDP_MAX_BANDS 16
 #define CVVDP_MAX_FILTER_LEN 129
 #define CVVDP_CSF_LUT_N 32
@@ -183,6 +183,21 @@ int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int bat
 int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, const cvvdp_b200_yuv *yuv, int batch,
                             int height, int width, int dtype, int frame, int colorspace, float *dst_dev, void *stream);
 
+/* Input validation of the fused path -- replaces the checks the reference makes frame by frame on the host:
+ * vvdp_display_photo_eotf.forward "Pixel outside the valid range 0-1" (display_model.py:335-337, only for EOTFs that
+ * clamp), video_source.check_if_valid NaN / Inf / first-frame mean (video_source.py:48-72).  The temporal kernels
+ * count, per warp that saw one, floating-point input values outside 0..1, NaN and Inf (integer clips cannot carry
+ * any), and accumulate the achromatic DKL channel of clip frame 0 of the TEST video over all batch items
+ * (first_frame_sum; divide by batch * height * width; only meaningful when a process call started at frame 0).
+ * cvvdp_b200_input_stats synchronises the device, reports the counters accumulated since the last reset and
+ * optionally resets them.  A NaN input makes the reference fail with "Must not be nan" (cvvdp_metric.py:906-907);
+ * the caller of this ABI is expected to do the same when nan != 0. */
+typedef struct {
+    int64_t out_of_range, nan, inf;
+    double first_frame_sum;
+} cvvdp_b200_input_report;
+int cvvdp_b200_input_stats(cvvdp_b200_ctx *ctx, cvvdp_b200_input_report *out, int reset);
+
 /* Per-kernel timing for bench.py's roofline: when enabled, every launch is bracketed by CUDA events on
  * its stream.  profile_read synchronises the device, aggregates by (kind, pyramid level) and resets.
  * algo_bytes is the ALGORITHMIC HBM traffic of those launches:
@@ -218,12 +233,9 @@ int cvvdp_b200_feature_layout(const cvvdp_b200_ctx *ctx, int band, int32_t *ph, 
                               int64_t *float_offset);
 int cvvdp_b200_set_feature_output(cvvdp_b200_ctx *ctx, float *features_dev);
 
-/* Column-strip width of the band kernel chosen for pyramid level `level` of the current plan (116: wide-strip
- * kernel, 52: narrow-strip kernel, 0: baseband or no plan).  Introspection for tests and profiling only. */
+/* Column-strip width of the band kernel for pyramid level `level` of the current plan (0: baseband or no plan).
+ * Introspection for tests and profiling only. */
 int cvvdp_b200_band_strip_width(const cvvdp_b200_ctx *ctx, int level);
-/* Which band kernel: 2 = k_band2 (default), 3 = k_band3<128> (CVVDP_B200_WIDE), 4 = k_band3<64>
- * (CVVDP_B200_BAND3_NARROW), 0 = baseband or no plan. */
-int cvvdp_b200_band_kernel_id(const cvvdp_b200_ctx *ctx, int level);
 
 #ifdef __cplusplus
 }

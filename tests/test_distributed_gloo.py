@@ -119,3 +119,57 @@ def test_halo_exchange_world4_gloo(tmp_path):
     for r in range(4):
         z = np.load(tmp_path / f"x{r}.npz")
         assert np.array_equal(z["Q"], full["Q"]) and np.array_equal(z["jod"], full["jod"])
+
+
+def _worker_runs(rank, world, port, out_dir):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import colorvideovdp_b200 as cv
+    from colorvideovdp_b200 import cvvdp_metric, distributed as D
+    import emu_util
+    import synth
+    cvvdp_metric._set_mock_library_for_tests(emu_util.emu_library())
+    B, F, fps = 3, 10, 30  # 30 units over 2 ranks: item 1 is split between them (halo on rank 1), items 0 and 2 are whole
+    clips = [synth.make_pair_u8(70 + b, F, 36, 48) for b in range(B)]
+    m = cv.cvvdp(display_name="standard_fhd")
+    pieces = []
+    for item, f_lo, f_hi in D.work_shard(B, F, rank, world):
+        wlo, whi = D.needed_window(m, F, fps, f_lo, f_hi)
+        tst, ref = clips[item]
+        pieces.append((item, f_lo, f_hi, wlo, torch.from_numpy(tst[:, :, wlo:whi].copy()), torch.from_numpy(ref[:, :, wlo:whi].copy())))
+    jod, Q = D.predict_sharded(m, pieces, B, F, fps)
+    np.savez(os.path.join(out_dir, f"w{rank}.npz"), jod=jod.numpy(), Q=Q.numpy(),
+             pieces=np.asarray([p[:3] for p in pieces]))
+    if rank == 0:
+        tb = np.concatenate([c[0] for c in clips], 0)
+        rb = np.concatenate([c[1] for c in clips], 0)
+        j_full, s_full = m.predict(tb, rb, frames_per_second=fps)
+        np.savez(os.path.join(out_dir, "wfull.npz"), jod=j_full.numpy(), Q=s_full["Q_per_ch"])
+    dist.destroy_process_group()
+
+
+def test_run_sharding_world2_gloo(tmp_path):
+    """Contiguous runs of the flattened (item, frame) sequence: whole items and a split item, bit-identical to
+    the single-process batch prediction."""
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_worker_runs, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    w0, w1, full = (np.load(tmp_path / n) for n in ("w0.npz", "w1.npz", "wfull.npz"))
+    assert w0["pieces"].tolist() == [[0, 0, 10], [1, 0, 5]] and w1["pieces"].tolist() == [[1, 5, 10], [2, 0, 10]]
+    assert np.array_equal(w0["Q"], w1["Q"]) and np.array_equal(w0["jod"], w1["jod"])
+    assert np.array_equal(w0["Q"], full["Q"]) and np.array_equal(w0["jod"], full["jod"])
+
+
+def test_work_shard_covers_every_unit_once():
+    from colorvideovdp_b200.distributed import work_shard
+    for B, F, world in ((8, 120, 8), (8, 120, 2), (1, 120, 8), (3, 10, 2), (2, 9, 4), (5, 7, 3), (1, 1, 1)):
+        seen = []
+        for r in range(world):
+            for item, lo, hi in work_shard(B, F, r, world):
+                assert 0 <= lo < hi <= F
+                seen += [(item, f) for f in range(lo, hi)]
+        assert seen == [(b, f) for b in range(B) for f in range(F)], (B, F, world)
+    assert work_shard(8, 120, 3, 8) == [(3, 0, 120)]  # as many items as ranks: whole items, no halo

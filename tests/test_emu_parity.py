@@ -42,22 +42,59 @@ def test_identical_pair_is_exactly_10(mock_device):
 
 
 @pytest.mark.parametrize("shape,fps,heatmap", [((1, 150, 360), 0, None), ((1, 131, 250), 0, "raw"), ((5, 64, 236), 30, None)])
-@pytest.mark.parametrize("variant", [0, 3, 5, 7, 11, 15])
-def test_band_kernel_variants_and_packed_temporal_kernel(shape, fps, heatmap, variant, mock_device, monkeypatch):
-    """The band kernel on levels several strips wide (several row segments, a ragged last strip, the heat-map
-    variant) in its A/B geometries (CVVDP_B200_BAND_VARIANT: bit 1 = 48-column strips, bit 0 = conflict-free
-    phase A; only honoured by builds with -DCVVDP_BAND_AB, otherwise every value runs the default); clips whose
-    planes are whole 64-pixel warp segments take the packed two-stage temporal kernel.  Checked against the oracle."""
+def test_band_kernel_strips_segments_and_packed_temporal_kernel(shape, fps, heatmap, mock_device):
+    """The band kernel on levels several 48-column strips wide (several row segments, a ragged last strip, phase C
+    trailing by 16 rows across the segment ends, the heat-map variant); clips whose planes are whole 64-pixel warp
+    segments take the packed two-stage temporal kernel.  Checked against the oracle."""
     F, H, W = shape
     tst, ref = synth.make_pair_u8(11, F, H, W)
-    monkeypatch.setenv("CVVDP_B200_BAND_VARIANT", str(variant))
     m = cv.cvvdp(display_name="standard_fhd", heatmap=heatmap)
     jod, stats = m.predict(tst, ref, frames_per_second=fps)
+    assert m._ctx.band_strip_width(0) == 48
     jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd", heatmap=heatmap)
     gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], str(shape))
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
     if heatmap:
         assert np.max(np.abs(stats["heatmap"].float().numpy() - stats_o["heatmap"].astype(np.float32))) <= gu.HEATMAP_ATOL
+
+
+@pytest.mark.parametrize("shape", [(6, 16, 64), (3, 20, 28)])  # two-stage temporal kernel / generic kernel
+def test_input_validation_on_the_fused_path(shape, mock_device, caplog):
+    """The reference's per-frame input checks (display_model.py:335-337, video_source.py:48-72,
+    cvvdp_metric.py:906-907) from the device counters of the fused front end: out-of-range values warn and are
+    clamped, a NaN warns and fails with the reference's assertion, nearly black content warns about the scale."""
+    import logging
+    F, H, W = shape
+    tst, ref = synth.make_pair_u8(21, F, H, W)
+    tf, rf = tst.astype(np.float32) / 255, ref.astype(np.float32) / 255
+    m = cv.cvvdp(display_name="standard_fhd")
+    with caplog.at_level(logging.WARNING):
+        j_clean, _ = m.predict(tf, rf, frames_per_second=30)
+    assert not caplog.records
+    hot = tf.copy()
+    hot[0, 1, 2, 5, 7] = 1.2
+    clamped = hot.copy()
+    clamped[0, 1, 2, 5, 7] = 1.0
+    with caplog.at_level(logging.WARNING):
+        j_hot, s_hot = m.predict(hot, rf, frames_per_second=30)
+    assert any("Pixel outside the valid range 0-1" in r.message for r in caplog.records)
+    j_cl, s_cl = m.predict(clamped, rf, frames_per_second=30)
+    assert np.array_equal(s_hot["Q_per_ch"], s_cl["Q_per_ch"])  # clamped, exactly like the reference
+    caplog.clear()
+    bad = tf.copy()
+    bad[0, 0, 1, 3, 3] = np.nan
+    with caplog.at_level(logging.WARNING):
+        with pytest.raises(AssertionError, match="Must not be nan"):
+            m.predict(bad, rf, frames_per_second=30)
+    assert any("NaN" in r.message for r in caplog.records)
+    caplog.clear()
+    with caplog.at_level(logging.WARNING):  # the counters were reset: a clean clip is clean again
+        j_again, _ = m.predict(tf, rf, frames_per_second=30)
+    assert not caplog.records and float(j_again) == float(j_clean)
+    dark = cv.cvvdp(display_name="standard_fhd", display_photometry=cv.vvdp_display_photo_eotf(0.5, contrast=1000, EOTF="sRGB", E_ambient=0))
+    with caplog.at_level(logging.WARNING):
+        dark.predict(tf, rf, frames_per_second=30)
+    assert any("mean color value is less than 1" in r.message for r in caplog.records)
 
 
 def test_frame_blocks_and_ranges_are_partition_independent(mock_device):

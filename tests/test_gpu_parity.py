@@ -216,13 +216,6 @@ def test_yuv_1080p_matches_oracle_and_rgb_path(tmp_path):
     assert abs(float(jod) - float(jod2)) <= 1e-4
 
 
-# Feature mode was written after the round's GPU budget was spent: green on the mock device (incl. under
-# AddressSanitizer) but never executed on a B200.  Non-strict xfail keeps an unexpected hardware-only
-# failure from masking the rest of the suite; an XPASS in the summary is the confirmation to drop the mark.
-_UNSEEN_ON_HARDWARE = pytest.mark.xfail(strict=False, reason="feature-mode kernels not yet run on a B200 (round 1)")
-
-
-@_UNSEEN_ON_HARDWARE
 @pytest.mark.parametrize("name", gu.feature_case_names())
 def test_features_against_reference_fixtures(name):
     """extract_features (band kernel in feature mode + k_feature_pool) against the tensors the
@@ -239,7 +232,6 @@ def test_features_against_reference_fixtures(name):
     assert np.array_equal(s0["Q_per_ch"], s1["Q_per_ch"]) and torch.equal(j0, j1)
 
 
-@_UNSEEN_ON_HARDWARE
 def test_features_1080p_against_oracle():
     """Feature mode at a BASELINE size (1080p, 38-pixel patches, ragged last patch row) against the oracle."""
     tst, ref = synth.make_pair_u8(41, 2, 1080, 1920)
@@ -253,3 +245,47 @@ def test_features_1080p_against_oracle():
         files = list(z)
 
     gu.assert_features_close([f.cpu().numpy() for f in feats], Z(z), "1080p")
+
+
+@pytest.mark.parametrize("fps", [8, 15, 24, 40, 48, 50, 120])
+def test_every_temporal_specialisation_on_hardware(fps):
+    """Filter lengths 3, 5, 7, 11, 13, 15 (two-stage kernel, one specialisation each) and 31 (generic kernel)
+    against the oracle; 9 and 17 taps are covered by the 30 / 60 fps cases above."""
+    F = 7 if fps < 60 else 21
+    tst, ref = synth.make_pair_u8(60 + fps, F, 32, 64)
+    m = cv.cvvdp(display_name="standard_fhd", temp_padding="symmetric", device=DEV)
+    jod, stats = m.predict(_t(tst), _t(ref), frames_per_second=fps)
+    jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd", "symmetric")
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"{fps} fps")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
+
+
+@pytest.mark.parametrize("shape", [(6, 16, 64), (3, 20, 28)])  # two-stage temporal kernel / generic kernel
+@pytest.mark.parametrize("resident", ["device", "host"])
+def test_input_validation_on_the_fused_path(shape, resident, caplog):
+    """1.2 -> 'Pixel outside the valid range 0-1' + clamp; NaN -> warning + AssertionError('Must not be nan')
+    (display_model.py:335-337, video_source.py:48-59, cvvdp_metric.py:906-907), through predict()."""
+    import logging
+    F, H, W = shape
+    tst, ref = synth.make_pair_u8(21, F, H, W)
+    tf, rf = tst.astype(np.float32) / 255, ref.astype(np.float32) / 255
+    put = (lambda a: a) if resident == "host" else _t
+    m = cv.cvvdp(display_name="standard_fhd", device=DEV)
+    with caplog.at_level(logging.WARNING):
+        m.predict(put(tf), put(rf), frames_per_second=30)
+    assert not caplog.records
+    hot = tf.copy()
+    hot[0, 1, 2, 5, 7] = 1.2
+    with caplog.at_level(logging.WARNING):
+        _, s_hot = m.predict(put(hot), put(rf), frames_per_second=30)
+    assert any("Pixel outside the valid range 0-1" in r.message for r in caplog.records)
+    hot[0, 1, 2, 5, 7] = 1.0
+    _, s_cl = m.predict(put(hot), put(rf), frames_per_second=30)
+    assert np.array_equal(s_hot["Q_per_ch"], s_cl["Q_per_ch"])
+    caplog.clear()
+    bad = tf.copy()
+    bad[0, 0, 1, 3, 3] = np.nan
+    with caplog.at_level(logging.WARNING):
+        with pytest.raises(AssertionError, match="Must not be nan"):
+            m.predict(put(bad), put(rf), frames_per_second=30)
+    assert any("NaN" in r.message for r in caplog.records)

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 timeout 120 python __graft_entry__.py --smoke >> gpurun_out/quick.txt 2>&1
 for envs in "$@"; do
   echo "=== env: [$envs]" >> gpurun_out/quick.txt
-  env $envs timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline >> gpurun_out/quick.txt 2>> gpurun_out/quick.err
+  env $envs timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline --no-extras >> gpurun_out/quick.txt 2>> gpurun_out/quick.err
 done
 python - <<'PY'
 import json
