@@ -16,7 +16,7 @@ CSF_LUT_N = 32
 DTYPE_U8, DTYPE_U16, DTYPE_F16, DTYPE_F32 = 0, 1, 2, 3
 EOTF_SRGB, EOTF_PQ, EOTF_LINEAR, EOTF_HLG, EOTF_GAMMA, EOTF_NONE = 0, 1, 2, 3, 4, 5
 PAD_REPLICATE, PAD_SYMMETRIC = 0, 1
-HEATMAP_NONE, HEATMAP_RAW = 0, 1
+HEATMAP_NONE, HEATMAP_RAW, HEATMAP_THRESHOLD, HEATMAP_SUPRATHRESHOLD = 0, 1, 2, 3
 CS_DKLD65, CS_RGB_LINEAR, CS_XYZ, CS_LMS2006 = 0, 1, 2, 3
 
 

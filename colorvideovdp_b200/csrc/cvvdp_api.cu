@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cvvdp_kernels.cuh"
@@ -73,6 +74,15 @@ struct cvvdp_b200_ctx {
     size_t q_dev_bytes = 0;
     void *hm_dev = nullptr;
     size_t hm_dev_bytes = 0;
+    // pinned bounce buffers for PAGEABLE host clips (see upload())
+    static const int kPinSlots = 3;
+    void *pin_buf[kPinSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pin_done[kPinSlots] = {nullptr, nullptr, nullptr};
+    size_t pin_bytes = 0;
+    int pin_next = 0;
+    unsigned *hm_tone_dev = nullptr;  // coloured heat maps: [0..1] min/max bits, [2..1025] histogram, then 2050 floats of tone curve
+    cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t hm_ready = nullptr, hm_copied = nullptr;
     int *flags_dev = nullptr;     // [0..2] input validation counters, [3] clip frame 0 seen; then one float: DKL-A sum of test frame 0
     long long launches = 0;
     bool prof = false;
@@ -400,7 +410,7 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
     const cvvdp_b200_params &P = ctx->P;
     const int n = f1 - f0, L = info.n_bands, B = job.batch;
     const int pairs = B * n;
-    const bool do_hm = job.heatmap == CVVDP_HEATMAP_RAW;
+    const bool do_hm = job.heatmap != CVVDP_HEATMAP_NONE;
     const bool do_feat = job.features != 0 && ctx->feat_out != nullptr;
     const float eps = 1e-5f;
 
@@ -668,16 +678,73 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, i, (double)n * 4.0 * (2.0 * npix + (double)ea.hc * ea.wc));
             CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), n), dim3(256), 0, st, ea);
         }
-        HeatmapOutArgs ha;
-        ha.img = ctx->lv[0].hm;
-        ha.out = (unsigned short *)hm_dev;
-        ha.npix = (long long)job.height * job.width;
-        ha.f_off = f0;
-        ha.jod_a = P.jod_a;
-        ha.jod_exp = P.jod_exp;
-        auto kfn = k_heatmap_out;
-        LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, -1, (double)n * 6.0 * ha.npix);
-        CVVDP_LAUNCH(kfn, dim3((unsigned)((ha.npix + 255) / 256), n), dim3(256), 0, st, ha);
+        const long long npix0 = (long long)job.height * job.width;
+        if (job.heatmap == CVVDP_HEATMAP_RAW) {
+            HeatmapOutArgs ha;
+            ha.img = ctx->lv[0].hm;
+            ha.out = (unsigned short *)hm_dev;
+            ha.npix = npix0;
+            ha.f_off = f0;
+            ha.jod_a = P.jod_a;
+            ha.jod_exp = P.jod_exp;
+            auto kfn = k_heatmap_out;
+            LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, -1, (double)n * 6.0 * ha.npix);
+            CVVDP_LAUNCH(kfn, dim3((unsigned)((ha.npix + 255) / 256), n), dim3(256), 0, st, ha);
+        } else {  // coloured map: tone curve of this block's context image, then colour (visualize_diff_map.py:23-106)
+            HmToneArgs ta;
+            ta.lv0 = ctx->lv[0].g;
+            ta.npix = npix0;
+            ta.n = n;
+            ta.minmax = ctx->hm_tone_dev;
+            ta.hist = reinterpret_cast<int *>(ctx->hm_tone_dev + 2);
+            ta.curve = reinterpret_cast<float *>(ctx->hm_tone_dev + 2 + CVVDP_HM_BINS);
+            ta.dr = 0.6f;
+            static const unsigned init[2] = {0x7f800000u, 0u};
+            CU_CHECK(ctx, cudaMemcpyAsync(ctx->hm_tone_dev, init, sizeof(init), cudaMemcpyHostToDevice, st));
+            CU_CHECK(ctx, cudaMemsetAsync(ctx->hm_tone_dev + 2, 0, CVVDP_HM_BINS * 4, st));
+            const unsigned gx = (unsigned)std::min<long long>((npix0 + 255) / 256, 4LL * ctx->num_sms);
+            {
+                LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, -2, (double)n * 16.0 * npix0);
+                auto k1 = k_hm_minmax;
+                CVVDP_LAUNCH(k1, dim3(gx, n), dim3(256), 0, st, ta);
+            }
+            {
+                LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, -3, (double)n * 16.0 * npix0);
+                auto k2 = k_hm_hist;
+                CVVDP_LAUNCH(k2, dim3(gx, n), dim3(256), 0, st, ta);
+            }
+            {
+                LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, -4, 0.0);
+                auto k3 = k_hm_curve;
+                CVVDP_LAUNCH(k3, dim3(1), dim3(CVVDP_HM_BINS), 0, st, ta);
+            }
+            HmColourArgs ca;
+            memset(&ca, 0, sizeof(ca));
+            ca.img = ctx->lv[0].hm;
+            ca.lv0 = ctx->lv[0].g;
+            ca.minmax = ta.minmax;
+            ca.curve = ta.curve;
+            ca.out = (unsigned short *)hm_dev;
+            ca.npix = npix0;
+            ca.f_off = f0;
+            ca.F_total = job.n_frames;
+            ca.jod_a = P.jod_a;
+            ca.jod_exp = P.jod_exp;
+            ca.dr = 0.6f;
+            static const float thr[5][3] = {{0.2f, 0.2f, 1.0f}, {0.2f, 1.0f, 1.0f}, {0.2f, 1.0f, 0.2f}, {1.0f, 1.0f, 0.2f}, {1.0f, 0.2f, 0.2f}};
+            static const float sup[3][3] = {{0.2f, 1.0f, 1.0f}, {1.0f, 1.0f, 1.0f}, {1.0f, 1.0f, 0.2f}};
+            const bool is_thr = job.heatmap == CVVDP_HEATMAP_THRESHOLD;
+            ca.n_map = is_thr ? 5 : 3;
+            for (int i = 0; i < ca.n_map; ++i) {
+                const float *c = is_thr ? thr[i] : sup[i];
+                ca.map_in[i] = is_thr ? (float)(0.25f * (float)i) * 0.1f : (float)(0.5f * (float)i) * 0.3f;  // l.67, 77
+                const float lum = c[0] * 0.212656f + c[1] * 0.715158f + c[2] * 0.072186f;                 // l.98
+                for (int k = 0; k < 3; ++k) ca.map_ch[i][k] = c[k] / (lum + 0.0001f);
+            }
+            LaunchScope ls(ctx, st, CVVDP_K_HEATMAP, -1, (double)n * (4.0 + 16.0 + 6.0) * npix0);
+            auto k4 = k_hm_colour;
+            CVVDP_LAUNCH(k4, dim3((unsigned)((npix0 + 255) / 256), n), dim3(256), 0, st, ca);
+        }
     }
     CU_CHECK(ctx, cudaGetLastError());
     return CVVDP_OK;
@@ -758,6 +825,13 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
         cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&s.consumed, cudaEventDisableTiming);
     }
+    if (cudaMalloc(&ctx->hm_tone_dev, (2 + CVVDP_HM_BINS + 2 * CVVDP_HM_BINS + 2) * 4) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->hm_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->hm_copied, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, CVVDP_ERR_NOMEM, "cannot allocate the heat-map tone buffers");
+    }
     if (cudaMalloc(&ctx->flags_dev, 32) != cudaSuccess || cudaMemset(ctx->flags_dev, 0, 32) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, CVVDP_ERR_NOMEM, "cannot allocate the validation flags");
@@ -779,6 +853,14 @@ void cvvdp_b200_destroy(cvvdp_b200_ctx *ctx) {
     if (ctx->q_dev) cudaFree(ctx->q_dev);
     if (ctx->hm_dev) cudaFree(ctx->hm_dev);
     if (ctx->flags_dev) cudaFree(ctx->flags_dev);
+    if (ctx->hm_tone_dev) cudaFree(ctx->hm_tone_dev);
+    for (int i = 0; i < cvvdp_b200_ctx::kPinSlots; ++i) {
+        if (ctx->pin_buf[i]) cudaFreeHost(ctx->pin_buf[i]);
+        if (ctx->pin_done[i]) cudaEventDestroy(ctx->pin_done[i]);
+    }
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+    if (ctx->hm_ready) cudaEventDestroy(ctx->hm_ready);
+    if (ctx->hm_copied) cudaEventDestroy(ctx->hm_copied);
     for (auto &s : ctx->stage) {
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.consumed) cudaEventDestroy(s.consumed);
@@ -811,6 +893,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     if (job->dtype < CVVDP_DTYPE_U8 || job->dtype > CVVDP_DTYPE_F32) return fail(ctx, CVVDP_ERR_INVALID, "unknown dtype %d", job->dtype);
     if (job->padding != CVVDP_PAD_REPLICATE && job->padding != CVVDP_PAD_SYMMETRIC)
         return fail(ctx, CVVDP_ERR_INVALID, "Unknown padding method");
+    if (job->heatmap < CVVDP_HEATMAP_NONE || job->heatmap > CVVDP_HEATMAP_SUPRATHRESHOLD)
+        return fail(ctx, CVVDP_ERR_INVALID, "unknown heat-map mode %d", job->heatmap);
     if (job->heatmap != CVVDP_HEATMAP_NONE && job->batch > 1)
         return fail(ctx, CVVDP_ERR_INVALID, "Heatmaps not supported when batches are used");  // cvvdp_metric.py:311-312
     if (ctx->disp.eotf == CVVDP_EOTF_HLG && job->in_channels != 3)
@@ -845,7 +929,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
 
     // workspace per frame of a block (all batch items)
     const size_t B = (size_t)job->batch;
-    const bool do_hm = job->heatmap == CVVDP_HEATMAP_RAW;
+    const bool do_hm = job->heatmap != CVVDP_HEATMAP_NONE;
     size_t per_frame = 0;
     for (int i = 0; i < L; ++i) {
         const size_t npix = (size_t)info.band_height[i] * info.band_width[i];
@@ -975,6 +1059,73 @@ int cvvdp_b200_process_device(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, 
 
 // ---- host-buffer path ---------------------------------------------------------------------------
 namespace {
+// ---- host -> device upload ------------------------------------------------------------------------
+// Pinned (or registered) host memory goes straight to the copy engine.  PAGEABLE memory -- what a caller who
+// just loaded a clip into a numpy array passes to predict() -- would make cudaMemcpyAsync fall back to the
+// driver's single-threaded staging (measured 11 GB/s on the bench box against 52 GB/s pinned); instead the
+// library bounces it through three pinned 32 MiB slots that several host threads fill while the previous slot
+// is on the wire.
+bool is_pageable(const void *p) {
+#ifdef CVVDP_EMU
+    (void)p;
+    return getenv("CVVDP_B200_FORCE_STAGING") != nullptr;  // test hook: exercise the bounce path on the mock device
+#else
+    if (getenv("CVVDP_B200_FORCE_STAGING")) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+#endif
+}
+
+void parallel_memcpy(char *dst, const char *src, size_t n, int threads) {
+    if (threads <= 1 || n < ((size_t)4 << 20)) {
+        memcpy(dst, src, n);
+        return;
+    }
+    const size_t part = ((n + threads - 1) / threads + 4095) / 4096 * 4096;
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+        const size_t o = (size_t)t * part;
+        if (o >= n) break;
+        pool.emplace_back([=]() { memcpy(dst + o, src + o, std::min(part, n - o)); });
+    }
+    memcpy(dst, src, std::min(part, n));
+    for (auto &th : pool) th.join();
+}
+
+int upload(cvvdp_b200_ctx *ctx, void *dst, const void *src, size_t bytes, bool pageable, cudaStream_t st) {
+    if (!pageable) {
+        CU_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return CVVDP_OK;
+    }
+    const size_t slot_bytes = (size_t)32 << 20;
+    if (ctx->pin_bytes < slot_bytes) {
+        for (int i = 0; i < cvvdp_b200_ctx::kPinSlots; ++i) {
+            if (cudaMallocHost(&ctx->pin_buf[i], slot_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(ctx, CVVDP_ERR_NOMEM, "cannot allocate the pinned bounce buffers");
+            }
+            CU_CHECK(ctx, cudaEventCreateWithFlags(&ctx->pin_done[i], cudaEventDisableTiming));
+            CU_CHECK(ctx, cudaEventRecord(ctx->pin_done[i], st));
+        }
+        ctx->pin_bytes = slot_bytes;
+    }
+    static const int threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    for (size_t off = 0; off < bytes; off += slot_bytes) {
+        const size_t len = std::min(slot_bytes, bytes - off);
+        const int slot = ctx->pin_next;
+        ctx->pin_next = (ctx->pin_next + 1) % cvvdp_b200_ctx::kPinSlots;
+        CU_CHECK(ctx, cudaEventSynchronize(ctx->pin_done[slot]));  // the copy that last used this slot has left it
+        parallel_memcpy((char *)ctx->pin_buf[slot], (const char *)src + off, len, threads);
+        CU_CHECK(ctx, cudaMemcpyAsync((char *)dst + off, ctx->pin_buf[slot], len, cudaMemcpyHostToDevice, st));
+        CU_CHECK(ctx, cudaEventRecord(ctx->pin_done[slot], st));
+    }
+    return CVVDP_OK;
+}
+
 struct HostLayout {
     // frames are copied per "outer index" (dims whose stride exceeds the frame stride) as contiguous spans
     int outer_dims[4];
@@ -1016,7 +1167,7 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         return fail(ctx, CVVDP_ERR_INVALID, "bad frame range [%d,%d)", frame_begin, frame_end);
     if (!q_per_ch_host) return fail(ctx, CVVDP_ERR_INVALID, "q_per_ch_host is null");
     const cvvdp_b200_job &job = ctx->job;
-    const bool do_hm = job.heatmap == CVVDP_HEATMAP_RAW;
+    const bool do_hm = job.heatmap != CVVDP_HEATMAP_NONE;
     if (do_hm && !heatmap_host) return fail(ctx, CVVDP_ERR_INVALID, "heatmap_host is null");
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     int lo, hi, rc;
@@ -1038,13 +1189,17 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         return fail(ctx, CVVDP_ERR_UNSUPPORTED,
                     "host clips must store each frame densely (dims with a stride below the frame stride must tile it)");
     const cvvdp_b200_clip *clips[2] = {test, ref};
+    const bool pageable[2] = {is_pageable(test->data), is_pageable(ref->data)};
     const size_t esz = dtype_size(job.dtype);
     // The upload is pipelined in chunks smaller than the device-resident block size so that compute
     // starts after the first few frames have arrived.  The staging area is a RING of frames (frame f at
     // slot f % ring): the fl-1 history frames of a chunk are simply still there, so every input byte
     // crosses PCIe exactly once and no device-to-device shuffling competes with the kernels.
     const int fl = ctx->info.filter_len;
-    const int nb = std::min(ctx->info.block_frames, std::max(16, fl - 1));
+    // coloured heat maps take their tone-curve statistics over a block of frames (like the reference): the
+    // chunks then are exactly the plan's blocks, the same partition as process_device
+    const bool hm_blocks = job.heatmap == CVVDP_HEATMAP_THRESHOLD || job.heatmap == CVVDP_HEATMAP_SUPRATHRESHOLD;
+    const int nb = hm_blocks ? ctx->info.block_frames : std::min(ctx->info.block_frames, std::max(16, fl - 1));
     const int ring = 2 * nb + 2 * fl;  // chunk k-1 (being computed) + chunk k (being uploaded) + history/look-ahead
 
     // staging ring: [outer index][ring][frame]
@@ -1079,7 +1234,8 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         ctx->q_dev_bytes = q_bytes;
     }
     CU_CHECK(ctx, cudaMemsetAsync(ctx->q_dev, 0, q_bytes, ctx->work_stream));
-    const size_t hm_bytes = do_hm ? (size_t)job.n_frames * job.height * job.width * 2 : 0;
+    const int hm_ch = job.heatmap == CVVDP_HEATMAP_RAW ? 1 : 3;
+    const size_t hm_bytes = do_hm ? (size_t)hm_ch * job.n_frames * job.height * job.width * 2 : 0;
     if (do_hm && ctx->hm_dev_bytes < hm_bytes) {
         if (ctx->hm_dev) cudaFree(ctx->hm_dev);
         CU_CHECK(ctx, cudaMalloc(&ctx->hm_dev, hm_bytes));
@@ -1122,7 +1278,7 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         // full chunks, then a tapered tail (8, 4, 4 frames) so that little compute is left once the last
         // byte has arrived
         const int rem = frame_end - f0;
-        f1 = f0 + (rem > nb ? nb : (rem > 4 ? (rem + 1) / 2 : rem));
+        f1 = f0 + (rem > nb || hm_blocks ? std::min(nb, rem) : (rem > 4 ? (rem + 1) / 2 : rem));
         Staging &sg = ctx->stage[blk & 1];  // events only; the data lives in the ring of stage[0]
         int wlo, whi;
         needed_frames(ctx, f0, f1, &wlo, &whi);
@@ -1145,9 +1301,10 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
                 for (int fa = new_lo; fa < whi;) {
                     const int slot = fa % ring;
                     const int run = std::min(whi - fa, ring - slot);
-                    CU_CHECK(ctx, cudaMemcpyAsync((char *)ctx->stage[0].buf[v] + (dbase + (long long)slot * sF) * esz,
-                                                  (const char *)c->data + (hbase + (long long)(fa - c->frame0) * sF) * esz,
-                                                  (size_t)run * sF * esz, cudaMemcpyHostToDevice, ctx->copy_stream));
+                    if ((rc = upload(ctx, (char *)ctx->stage[0].buf[v] + (dbase + (long long)slot * sF) * esz,
+                                     (const char *)c->data + (hbase + (long long)(fa - c->frame0) * sF) * esz,
+                                     (size_t)run * sF * esz, pageable[v], ctx->copy_stream)) != CVVDP_OK)
+                        return rc;
                     fa += run;
                 }
                 for (int k = 0; k < hl[v].n_outer; ++k) {
@@ -1167,15 +1324,21 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
             return rc;
         CU_CHECK(ctx, cudaEventRecord(sg.consumed, ctx->work_stream));
         tl_mark(ctx->work_stream);
+        if (do_hm && !skip_compute) {  // this block's heat-map frames go home on their own stream while the next block runs
+            const size_t fbytes = (size_t)job.height * job.width * 2;
+            CU_CHECK(ctx, cudaEventRecord(ctx->hm_ready, ctx->work_stream));
+            CU_CHECK(ctx, cudaStreamWaitEvent(ctx->d2h_stream, ctx->hm_ready, 0));
+            for (int c = 0; c < hm_ch; ++c) {
+                const size_t off = ((size_t)c * job.n_frames + f0) * fbytes;
+                CU_CHECK(ctx, cudaMemcpyAsync((char *)heatmap_host + off, (char *)ctx->hm_dev + off, (size_t)(f1 - f0) * fbytes,
+                                              cudaMemcpyDeviceToHost, ctx->d2h_stream));
+            }
+        }
     }
     CU_CHECK(ctx, cudaMemcpyAsync(q_per_ch_host, ctx->q_dev, q_bytes, cudaMemcpyDeviceToHost, ctx->work_stream));
-    if (do_hm) {
-        const size_t fbytes = (size_t)job.height * job.width * 2;
-        CU_CHECK(ctx, cudaMemcpyAsync((char *)heatmap_host + frame_begin * fbytes, (char *)ctx->hm_dev + frame_begin * fbytes,
-                                      (size_t)(frame_end - frame_begin) * fbytes, cudaMemcpyDeviceToHost, ctx->work_stream));
-    }
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->work_stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (do_hm) CU_CHECK(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     if (dbg_tl) {
         for (size_t i = 0; i + 3 < tl.size(); i += 4) {
             float t[4];

@@ -36,35 +36,44 @@ __device__ __forceinline__ float pq2lin(float V) {  // display_model.py:58-70
     return 10000.0f * f_pow(num / (c2 - c3 * im_t), (float)(1.0 / 0.1593017578125));
 }
 
-// v[0..n) display-encoded -> absolute linear (cd/m^2), in place.  n = 1 or 3.
-__device__ __forceinline__ void eotf_forward(float *v, int n, const DisplayDev &d) {
+// v[0..N) display-encoded -> absolute linear (cd/m^2), in place.  N = 1 or 3 is a compile-time count: with a
+// run-time one the small array is indexed dynamically and lands in local memory (measured in round 2: the fp32
+// input path of the temporal kernel ran 8x slower than the 8-bit table path because of it).
+template <int N>
+__device__ __forceinline__ void eotf_forward_n(float (&v)[3], const DisplayDev &d) {
     const float a = d.Ypeak - d.Yblack;
     if (d.eotf == CVVDP_EOTF_NONE) return;
     if (d.eotf != CVVDP_EOTF_LINEAR) {
-        for (int i = 0; i < n; ++i) v[i] = clamp01_keepnan(v[i]);  // display_model.py:335-337
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = clamp01_keepnan(v[i]);  // display_model.py:335-337
     }
     switch (d.eotf) {
         case CVVDP_EOTF_SRGB:
-            for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
                 float lin = srgb2lin(v[i]);
                 if (d.exposure != 1.f) lin = fminf(fmaxf(lin * d.exposure, 0.f), 1.f);
                 v[i] = a * lin + d.Yblack + d.Yrefl;
             }
             break;
         case CVVDP_EOTF_PQ:
-            for (int i = 0; i < n; ++i)
+#pragma unroll
+            for (int i = 0; i < N; ++i)
                 v[i] = fminf(fmaxf(pq2lin(v[i]) * d.exposure, 0.005f), d.Ypeak) + d.Yblack + d.Yrefl;
             break;
         case CVVDP_EOTF_LINEAR:
-            for (int i = 0; i < n; ++i) v[i] = fminf(fmaxf(v[i] * d.exposure, d.lin_lo), d.Ypeak) + d.Yrefl;
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i] * d.exposure, d.lin_lo), d.Ypeak) + d.Yrefl;
             break;
-        case CVVDP_EOTF_HLG: {  // display_model.py:89-108, 350-359 (needs all three channels)
+        case CVVDP_EOTF_HLG: {  // display_model.py:89-108, 350-359 (needs all three channels; the plan refuses N = 1)
             const float ha = 0.17883277f, hb = 1.f - 4.f * ha, hc = 0.5f - ha * logf(4.f * ha);
             float s[3];
+#pragma unroll
             for (int i = 0; i < 3; ++i)
                 s[i] = v[i] <= 0.5f ? v[i] * v[i] / 3.0f : (expf((v[i] - hc) / ha) + hb) / 12.0f;
             float Ys = 0.2627f * s[0] + 0.6780f * s[1] + 0.0593f * s[2];
             float gsc = powf(Ys, d.gamma - 1.f);
+#pragma unroll
             for (int i = 0; i < 3; ++i) {
                 float lin = gsc * s[i];
                 if (d.exposure != 1.f) lin = fminf(fmaxf(lin * d.exposure, 0.f), 1.f);
@@ -72,11 +81,16 @@ __device__ __forceinline__ void eotf_forward(float *v, int n, const DisplayDev &
             }
         } break;
         default:  // CVVDP_EOTF_GAMMA, display_model.py:360-362
-            for (int i = 0; i < n; ++i) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
                 float lin = fminf(fmaxf(f_pow(v[i], d.gamma) * d.exposure, 0.f), 1.f);
                 v[i] = a * lin + d.Yblack + d.Yrefl;
             }
     }
+}
+__device__ __forceinline__ void eotf_forward(float (&v)[3], int n, const DisplayDev &d) {
+    if (n == 3) eotf_forward_n<3>(v, d);
+    else eotf_forward_n<1>(v, d);
 }
 
 // Planar YUV pixel -> display-encoded RGB in 0..1 (video_source_yuv.py:153-233): limited-range unpack,
@@ -387,8 +401,8 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (USE_LUT) {
         for (int i = tid; i < 256; i += CVVDP_T2S_THREADS) {
-            float v[1] = {(float)i / 255.0f};
-            eotf_forward(v, 1, a.dd);
+            float v[3] = {(float)i / 255.0f, 0.f, 0.f};
+            eotf_forward_n<1>(v, a.dd);
             s_lut[i] = v[0];
         }
         __syncthreads();
@@ -1472,6 +1486,154 @@ __global__ void __launch_bounds__(256) k_heatmap_out(const HeatmapOutArgs a) {
     if (p >= a.npix) return;
     const float v = 1.f - met2jod_dev(a.img[f * a.npix + p], a.jod_a, a.jod_exp) / 10.f;
     a.out[(long long)(a.f_off + f) * a.npix + p] = float_to_half_bits(v);
+}
+
+
+// =================================================================================================
+// Coloured heat maps ('threshold' / 'supra-threshold'): visualize_diff_map + vis_tonemap
+// (visualize_diff_map.py:23-106) on top of the reconstructed difference map.  The context image is the TEST
+// sustained achromatic channel of the block, R[:,0] (cvvdp_metric.py:399-401) = the .x lane of the level-0 test
+// planes, tone-mapped with the statistics of the BLOCK of frames the reference visualises at once: minimum
+// positive value, maximum, a 1024-bin histogram of the log image -> cube-root histogram equalisation.
+// Four small kernels: min/max, histogram, curve (one CTA), colour.
+// =================================================================================================
+#define CVVDP_HM_BINS 1024
+struct HmToneArgs {
+    const float4 *lv0;     // level 0: [n][2][npix]; plane 2 f = test video of frame f (heat maps need a batch of one)
+    long long npix;
+    int n;
+    unsigned *minmax;      // [0] = bits of the smallest positive context value, [1] = bits of the largest
+    int *hist;             // [CVVDP_HM_BINS]
+    float *curve;          // [0..1023] tone curve v, [1024..2047] b_scale, [2048] b_min, [2049] b_max
+    float dr;              // 0.6
+};
+__global__ void __launch_bounds__(256) k_hm_minmax(const HmToneArgs a) {
+    const float4 *src = a.lv0 + (long long)blockIdx.y * 2 * a.npix;
+    unsigned mn = 0x7f800000u, mx = 0u;  // positive floats order like their bit patterns
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < a.npix; p += (long long)gridDim.x * 256) {
+        const float y = src[p].x;
+        if (y > 0.f) {
+#ifdef __CUDA_ARCH__
+            const unsigned b = __float_as_uint(y);
+#else
+            unsigned b;
+            memcpy(&b, &y, 4);
+#endif
+            mn = min(mn, b);
+            mx = max(mx, b);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&a.minmax[0], mn);
+        atomicMax(&a.minmax[1], mx);
+    }
+}
+__device__ __forceinline__ float hm_log_context(float y, float clampval) { return logf(fmaxf(y, clampval)); }
+__global__ void __launch_bounds__(256) k_hm_hist(const HmToneArgs a) {
+    __shared__ int sh[CVVDP_HM_BINS];
+    for (int i = threadIdx.x; i < CVVDP_HM_BINS; i += 256) sh[i] = 0;
+    __syncthreads();
+    const float clampval = bits_as_float(a.minmax[0]);
+    const float b_min = logf(clampval), b_max = logf(bits_as_float(a.minmax[1]));
+    const float4 *src = a.lv0 + (long long)blockIdx.y * 2 * a.npix;
+    for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < a.npix; p += (long long)gridDim.x * 256) {
+        const float b = hm_log_context(src[p].x, clampval);
+        // torch.histc (CUDA): bin = (int)((x - min) * bins / (max - min)), the maximum goes to the last bin
+        int bin = (int)((b - b_min) * (float)CVVDP_HM_BINS / (b_max - b_min));
+        bin = min(max(bin, 0), CVVDP_HM_BINS - 1);
+        atomicAdd(&sh[bin], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CVVDP_HM_BINS; i += 256)
+        if (sh[i]) atomicAdd(&a.hist[i], sh[i]);
+}
+// One CTA of 1024 threads: b_p = hist / sum; dy = b_p^(1/3) / sum(b_p^(1/3)); v = cumsum(dy) dr + (1 - dr) / 2;
+// b_scale = linspace(b_min, b_max, 1024)  (visualize_diff_map.py:34-43).
+__global__ void __launch_bounds__(CVVDP_HM_BINS) k_hm_curve(const HmToneArgs a) {
+    __shared__ float s_scan[CVVDP_HM_BINS];
+    __shared__ float s_red[32];
+    const int i = threadIdx.x;
+    const float clampval = bits_as_float(a.minmax[0]);
+    const float b_min = logf(clampval), b_max = logf(bits_as_float(a.minmax[1]));
+    const float total = (float)a.npix * (float)a.n;
+    const float bp = (float)a.hist[i] / total;
+    const float r = powf(bp, (float)(1.0 / 3.0));
+    // sum of r over the CTA
+    float t = r;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((i & 31) == 0) s_red[i >> 5] = t;
+    __syncthreads();
+    float sum = 0.f;
+    for (int w = 0; w < 32; ++w) sum += s_red[w];
+    // inclusive scan of dy (Hillis-Steele over shared memory; 1024 elements)
+    s_scan[i] = r / sum;
+    __syncthreads();
+    for (int o = 1; o < CVVDP_HM_BINS; o <<= 1) {
+        const float add = i >= o ? s_scan[i - o] : 0.f;
+        __syncthreads();
+        s_scan[i] += add;
+        __syncthreads();
+    }
+    a.curve[i] = s_scan[i] * a.dr + (1.0f - a.dr) / 2.0f;
+    // torch.linspace: start + i step for the first half, end - (steps - 1 - i) step for the second
+    const float step = (b_max - b_min) / (float)(CVVDP_HM_BINS - 1);
+    a.curve[CVVDP_HM_BINS + i] = i < CVVDP_HM_BINS / 2 ? b_min + step * (float)i : b_max - step * (float)(CVVDP_HM_BINS - 1 - i);
+    if (i == 0) {
+        a.curve[2 * CVVDP_HM_BINS] = b_min;
+        a.curve[2 * CVVDP_HM_BINS + 1] = b_max;
+    }
+}
+struct HmColourArgs {
+    const float *img;      // reconstructed difference map [n][npix]
+    const float4 *lv0;     // context, as in HmToneArgs
+    const unsigned *minmax;
+    const float *curve;
+    unsigned short *out;   // fp16 [3][F_total][npix]
+    long long npix;
+    int f_off, F_total;
+    float jod_a, jod_exp, dr;
+    int n_map;             // colour map entries (visualize_diff_map.py:57-84)
+    float map_in[5];
+    float map_ch[5][3];    // colour / (luminance + 1e-4)
+};
+// interp1 (interp.py:22-31, 81-89): imax = bucketize(x, xs) (first i with xs[i] >= x), clamped; imin = imax - 1
+__device__ __forceinline__ float hm_interp1(const float *xs, const float *vs, int stride, int n, float x) {
+    int lo = 0, hi = n;  // first index with xs[i] >= x
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (xs[mid] < x) lo = mid + 1;
+        else hi = mid;
+    }
+    const int imax = min(lo, n - 1), imin = max(imax - 1, 0);
+    float fr = (x - xs[imin]) / (xs[imax] - xs[imin] + 0.000001f);
+    if (imax == imin || fr < 0.f) fr = 0.f;
+    return vs[imin * stride] * (1.0f - fr) + vs[imax * stride] * fr;
+}
+__global__ void __launch_bounds__(256) k_hm_colour(const HmColourArgs a) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (p >= a.npix) return;
+    float d = 1.f - met2jod_dev(a.img[f * a.npix + p], a.jod_a, a.jod_exp) / 10.f;
+    d = fminf(fmaxf(d, 0.f), 1.f);
+    const float clampval = bits_as_float(a.minmax[0]);
+    const float b = hm_log_context(a.lv0[(long long)f * 2 * a.npix + p].x, clampval);
+    const float b_min = a.curve[2 * CVVDP_HM_BINS], b_max = a.curve[2 * CVVDP_HM_BINS + 1];
+    float tmo;
+    if (b_max - b_min < a.dr) tmo = (b - b_min) / (b_max - b_min + 1e-3f) * a.dr + (1.f - a.dr) / 2.f;  // l.30-32
+    else tmo = hm_interp1(a.curve + CVVDP_HM_BINS, a.curve, 1, CVVDP_HM_BINS, b);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        // the reference stores the colour in fp16 before it multiplies by the fp32 tone-mapped context (l.98-104)
+        const float col = half_bits_to_float(float_to_half_bits(hm_interp1(a.map_in, &a.map_ch[0][c], 3, a.n_map, d)));
+        const float v = fminf(fmaxf(col * tmo, 0.f), 1.f);
+        a.out[((long long)c * a.F_total + a.f_off + f) * a.npix + p] = float_to_half_bits(v);
+    }
 }
 
 }  // namespace cvvdp

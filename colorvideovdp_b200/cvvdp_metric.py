@@ -203,7 +203,8 @@ class cvvdp(vq_metric):
                                                                                            passthrough=True)
         else:
             disp = photo.native_display(self.pix_per_deg)
-        hm = N.HEATMAP_RAW if self.do_heatmap else N.HEATMAP_NONE
+        hm = {"raw": N.HEATMAP_RAW, "threshold": N.HEATMAP_THRESHOLD,
+              "supra-threshold": N.HEATMAP_SUPRATHRESHOLD}[self.heatmap] if self.do_heatmap else N.HEATMAP_NONE
         key = (B, H, W, F, float(fps), cin, dtype_id, self.temp_padding, hm, bytes(disp), self.gpu_mem,
                bytes(yuv) if yuv is not None else None, bool(features))
         if key != self._plan_key:
@@ -282,7 +283,7 @@ class cvvdp(vq_metric):
 
         pin = self.device.type == "cuda"
         Qh = torch.zeros((1, info.n_channels, F, info.n_bands), dtype=torch.float32, pin_memory=pin)
-        hmh = torch.zeros((1, 1, F, H, W), dtype=torch.float16, pin_memory=pin) if self.do_heatmap else None
+        hmh = torch.zeros((1, self._hm_channels(), F, H, W), dtype=torch.float16, pin_memory=pin) if self.do_heatmap else None
         self._ctx.process_host(clip_of(tt, tr), clip_of(rt, rr), f0, f1, Qh.data_ptr(),
                                hmh.data_ptr() if hmh is not None else None)
         return Qh, hmh
@@ -311,10 +312,16 @@ class cvvdp(vq_metric):
         if rep.nan:
             raise AssertionError("Must not be nan")
 
-    def _alloc_outputs(self, B, C, F, L, H, W):
+    def _alloc_outputs(self, B, C, F, L, H, W, whole=False):
         Q = torch.zeros((B, C, F, L), dtype=torch.float32, device=self.device)
-        hm = torch.zeros((1, 1, F, H, W), dtype=torch.float16, device=self.device) if self.do_heatmap else None
+        hm = None
+        if self.do_heatmap:  # every frame of the evaluated range is written by the kernels; zero only what is not
+            make = torch.empty if whole else torch.zeros
+            hm = make((1, self._hm_channels(), F, H, W), dtype=torch.float16, device=self.device)
         return Q, hm
+
+    def _hm_channels(self):
+        return 1 if self.heatmap == "raw" else 3  # cvvdp_metric.py:343
 
     def _run_arrays(self, vs, B, H, W, F, fps, f0, f1):
         """Fast path: raw clip tensors, display model fused into the CUDA front end."""
@@ -344,14 +351,17 @@ class cvvdp(vq_metric):
         resident = (test.device.type != "cpu" or ref.device.type != "cpu") if _resident is None else _resident
         if resident:  # (_resident is a test hook: on the mock device every tensor is a CPU tensor)
             test, ref = test.to(self.device), ref.to(self.device)
-            Q, hm = self._alloc_outputs(B, C, F, L, H, W)
+            Q, hm = self._alloc_outputs(B, C, F, L, H, W, whole=(f0 == 0 and f1 == F))
             self._ctx.process_device(_clip_of(test, B, first_frame), _clip_of(ref, B, first_frame), f0, f1,
                                      Q.data_ptr(), hm.data_ptr() if hm is not None else None, self._stream())
             return Q, hm
         # host clips: streamed upload overlapped with compute inside the native library
         pin = self.device.type == "cuda"
         Qh = torch.zeros((B, C, F, L), dtype=torch.float32, pin_memory=pin)
-        hmh = torch.zeros((1, 1, F, H, W), dtype=torch.float16, pin_memory=pin) if self.do_heatmap else None
+        hmh = None
+        if self.do_heatmap:
+            make = torch.empty if (f0 == 0 and f1 == F) else torch.zeros
+            hmh = make((1, self._hm_channels(), F, H, W), dtype=torch.float16, pin_memory=pin)
         try:
             self._ctx.process_host(_clip_of(test, B, first_frame), _clip_of(ref, B, first_frame), f0, f1,
                                    Qh.data_ptr(), hmh.data_ptr() if hmh is not None else None)
@@ -466,11 +476,13 @@ class cvvdp(vq_metric):
         stats["width"] = W
         stats["height"] = H
         stats["N_frames"] = F
-        if self.do_heatmap:
-            hm = heatmap.detach().cpu()
-            if self.heatmap != "raw":
-                from .visualize_diff_map import colorize_heatmap
-                hm = colorize_heatmap(hm, vid_source, self.heatmap, self.device)
+        if self.do_heatmap:  # raw [1,1,F,H,W] or coloured [1,3,F,H,W], fp16, from the native kernels, on the CPU
+            hm = heatmap.detach()
+            if hm.device.type == "cuda":  # through pinned memory: a pageable .cpu() of a 4K clip's map runs at a few GB/s
+                host = torch.empty(hm.shape, dtype=hm.dtype, pin_memory=True)
+                host.copy_(hm, non_blocking=True)
+                torch.cuda.current_stream(hm.device).synchronize()
+                hm = host
             stats["heatmap"] = hm
         return stats
 

@@ -43,8 +43,11 @@ enum { CVVDP_PAD_REPLICATE = 0, CVVDP_PAD_SYMMETRIC = 1 };
 /* Target colour spaces of cvvdp_b200_frontend (linear_2_target_colorspace, display_model.py:241-276). */
 enum { CVVDP_CS_DKLD65 = 0, CVVDP_CS_RGB_LINEAR = 1 /* forward() only */, CVVDP_CS_XYZ = 2, CVVDP_CS_LMS2006 = 3 };
 
-/* Heat map (cvvdp_metric.py:117,396-401).  Only the partition-independent raw map is produced natively. */
-enum { CVVDP_HEATMAP_NONE = 0, CVVDP_HEATMAP_RAW = 1 };
+/* Heat map (cvvdp_metric.py:117,396-401).  RAW: [1,1,F,H,W] fp16 difference map.  THRESHOLD / SUPRATHRESHOLD:
+ * [1,3,F,H,W] fp16 colour map of visualize_diff_map (visualize_diff_map.py:48-106): colour look-up table times the
+ * tone-mapped TEST sustained-achromatic context image (R[:,0], cvvdp_metric.py:399-401); like the reference, the
+ * tone-curve statistics are taken over the block of frames processed in one pass (plan_info.block_frames). */
+enum { CVVDP_HEATMAP_NONE = 0, CVVDP_HEATMAP_RAW = 1, CVVDP_HEATMAP_THRESHOLD = 2, CVVDP_HEATMAP_SUPRATHRESHOLD = 3 };
 
 /* cvvdp_parameters.json (cvvdp_metric.py:146-229).  Replaces cvvdp.load_config. */
 typedef struct {
@@ -152,7 +155,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
 /* The hot loop (cvvdp_metric.py:374-392 = read_block_of_frames 453-561 + process_block_of_frames
  * 660-751) for clip frames [frame_begin, frame_end) with test/reference views resident in HBM.
  * Writes Q_per_ch[b][c][f][band] for those frames into q_per_ch_dev (fp32, full [B,C,F,L] layout,
- * other frames untouched) and, when planned, the raw heat map [1,1,F,H,W] fp16 into heatmap_dev.
+ * other frames untouched) and, when planned, the heat map ([1,1,F,H,W] raw or [1,3,F,H,W] coloured, fp16) into heatmap_dev.
  * Asynchronous on `stream`. */
 int cvvdp_b200_process_device(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref,
                               int frame_begin, int frame_end, float *q_per_ch_dev, void *heatmap_dev,

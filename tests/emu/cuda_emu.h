@@ -207,6 +207,10 @@ template <typename T> inline T __shfl_down_sync(unsigned, T v, int d) {
 template <typename T> inline T __shfl_sync(unsigned, T v, int l) { return emu::shfl_generic(v, l); }
 template <typename T> inline T __ldg(const T *p) { return *p; }
 template <typename T> inline T atomicAdd(T *p, T v) { T o = *p; *p = o + v; return o; }
+template <typename T> inline T atomicMin(T *p, T v) { T o = *p; if (v < o) *p = v; return o; }
+template <typename T> inline T atomicMax(T *p, T v) { T o = *p; if (v > o) *p = v; return o; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
 
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }

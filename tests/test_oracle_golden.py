@@ -10,7 +10,7 @@ from oracle import cvvdp_oracle as O
 def test_oracle_matches_reference_fixture(name):
     z, meta = gu.load_case(name)
     jod, stats = O.predict(z["test"], z["ref"], meta["dim_order"], meta["fps"], meta["display"],
-                           meta["padding"], meta["heatmap"])
+                           meta["padding"], meta["heatmap"], hm_block=meta.get("hm_block") or None)
     gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
     assert np.allclose(stats["rho_band"], z["rho_band"])
     assert np.max(np.abs(np.asarray(jod, dtype=np.float64) - z["jod"])) <= gu.JOD_TOL
@@ -18,6 +18,10 @@ def test_oracle_matches_reference_fixture(name):
         hm, hm_ref = stats["heatmap"].astype(np.float32), z["heatmap"].astype(np.float32)
         assert hm.shape == hm_ref.shape
         assert np.max(np.abs(hm - hm_ref)) <= gu.HEATMAP_ATOL
+    elif meta["heatmap"] in ("threshold", "supra-threshold"):  # colour LUT x tone-mapped context, per block
+        hm, hm_ref = stats["heatmap"].astype(np.float32), z["heatmap"].astype(np.float32)
+        assert hm.shape == hm_ref.shape
+        assert np.max(np.abs(hm - hm_ref)) <= gu.COLOR_HEATMAP_ATOL
 
 
 @pytest.mark.parametrize("name", ["img_u8_70x121_4k", "vid_u8_10x64x100_fhd_rep"])
