@@ -82,6 +82,8 @@ struct cvvdp_b200_ctx {
     int pin_next = 0;
     unsigned *hm_tone_dev = nullptr;  // coloured heat maps: [0..1] min/max bits, [2..1025] histogram, then 2050 floats of tone curve
     cudaStream_t d2h_stream = nullptr;
+    cudaEvent_t dev_done = nullptr;   // end of the last process_device / pool_device on the caller's stream
+    bool dev_pending = false;
     cudaEvent_t hm_ready = nullptr, hm_copied = nullptr;
     int *flags_dev = nullptr;     // [0..2] input validation counters, [3] clip frame 0 seen; then one float: DKL-A sum of test frame 0
     long long launches = 0;
@@ -115,6 +117,22 @@ int fail(cvvdp_b200_ctx *ctx, int code, const char *fmt, ...) {
             return fail(ctx, CVVDP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
                         __FILE__, __LINE__);                                                        \
     } while (0)
+
+// Every ABI entry point runs on the context's device and leaves the caller's current device as it found it
+// (PyTorch reads the runtime's current device: a library that changes it behind torch's back redirects the caller's
+// next allocation).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) err = cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -798,7 +816,8 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
     ctx->device = device;
     ctx->P = *params;
     ctx->lut = *lut;
-    if (cudaSetDevice(device) != cudaSuccess) {
+    DeviceGuard dev_guard(device);
+    if (dev_guard.err != cudaSuccess) {
         delete ctx;
         return fail(nullptr, CVVDP_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     }
@@ -828,7 +847,8 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
     if (cudaMalloc(&ctx->hm_tone_dev, (2 + CVVDP_HM_BINS + 2 * CVVDP_HM_BINS + 2) * 4) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->hm_ready, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->hm_copied, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->hm_copied, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->dev_done, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, CVVDP_ERR_NOMEM, "cannot allocate the heat-map tone buffers");
     }
@@ -847,7 +867,7 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
 
 void cvvdp_b200_destroy(cvvdp_b200_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard dev_guard(ctx->device);
     cudaDeviceSynchronize();
     free_plan(ctx);
     if (ctx->q_dev) cudaFree(ctx->q_dev);
@@ -861,6 +881,7 @@ void cvvdp_b200_destroy(cvvdp_b200_ctx *ctx) {
     if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->hm_ready) cudaEventDestroy(ctx->hm_ready);
     if (ctx->hm_copied) cudaEventDestroy(ctx->hm_copied);
+    if (ctx->dev_done) cudaEventDestroy(ctx->dev_done);
     for (auto &s : ctx->stage) {
         if (s.copied) cudaEventDestroy(s.copied);
         if (s.consumed) cudaEventDestroy(s.consumed);
@@ -910,7 +931,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         if ((yv.chroma != 444 && (job->width & 1)) || (yv.chroma == 420 && (job->height & 1)))
             return fail(ctx, CVVDP_ERR_INVALID, "subsampled chroma needs even luma dimensions");
     }
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     CU_CHECK(ctx, cudaDeviceSynchronize());
     free_plan(ctx);
     ctx->job = *job;
@@ -1043,7 +1065,8 @@ int cvvdp_b200_process_device(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, 
         return fail(ctx, CVVDP_ERR_INVALID, "bad frame range [%d,%d)", frame_begin, frame_end);
     if (!q_per_ch_dev) return fail(ctx, CVVDP_ERR_INVALID, "q_per_ch_dev is null");
     if (ctx->job.heatmap != CVVDP_HEATMAP_NONE && !heatmap_dev) return fail(ctx, CVVDP_ERR_INVALID, "heatmap_dev is null");
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     int lo, hi;
     needed_frames(ctx, frame_begin, frame_end, &lo, &hi);
     int rc;
@@ -1054,6 +1077,9 @@ int cvvdp_b200_process_device(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, 
         const int f1 = std::min(f0 + nb, frame_end);
         if ((rc = run_block(ctx, test, ref, f0, f1, q_per_ch_dev, heatmap_dev, (cudaStream_t)stream)) != CVVDP_OK) return rc;
     }
+    // the workspace is still in use on the caller's stream: later calls on the context's own streams order after this
+    CU_CHECK(ctx, cudaEventRecord(ctx->dev_done, (cudaStream_t)stream));
+    ctx->dev_pending = true;
     return CVVDP_OK;
 }
 
@@ -1169,7 +1195,8 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
     const cvvdp_b200_job &job = ctx->job;
     const bool do_hm = job.heatmap != CVVDP_HEATMAP_NONE;
     if (do_hm && !heatmap_host) return fail(ctx, CVVDP_ERR_INVALID, "heatmap_host is null");
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     int lo, hi, rc;
     needed_frames(ctx, frame_begin, frame_end, &lo, &hi);
     if ((rc = check_clip(ctx, test, lo, hi, "test")) != CVVDP_OK) return rc;
@@ -1232,6 +1259,11 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         if (ctx->q_dev) cudaFree(ctx->q_dev);
         CU_CHECK(ctx, cudaMalloc(&ctx->q_dev, q_bytes));
         ctx->q_dev_bytes = q_bytes;
+    }
+    if (ctx->dev_pending) {  // an unsynchronised process_device call may still be using the workspace
+        CU_CHECK(ctx, cudaStreamWaitEvent(ctx->work_stream, ctx->dev_done, 0));
+        CU_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->dev_done, 0));
+        ctx->dev_pending = false;
     }
     CU_CHECK(ctx, cudaMemsetAsync(ctx->q_dev, 0, q_bytes, ctx->work_stream));
     const int hm_ch = job.heatmap == CVVDP_HEATMAP_RAW ? 1 : 3;
@@ -1353,7 +1385,8 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
 int cvvdp_b200_pool_device(cvvdp_b200_ctx *ctx, const float *q_dev, int B, int C, int F, int L, float *jod_dev, void *stream) {
     if (!ctx || !q_dev || !jod_dev) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
     if (B < 1 || C < 1 || C > 4 || F < 1 || L < 1) return fail(ctx, CVVDP_ERR_INVALID, "bad Q_per_ch shape");
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     PoolArgs pa;
     fill_pool_args(ctx, &pa, B, C, F, L);
     pa.Q = q_dev;
@@ -1370,7 +1403,8 @@ int cvvdp_b200_pool_device(cvvdp_b200_ctx *ctx, const float *q_dev, int B, int C
 int cvvdp_b200_pool(cvvdp_b200_ctx *ctx, const float *q_host, int B, int C, int F, int L, float *jod_host) {
     if (!ctx || !q_host || !jod_host) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
     if (B < 1 || C < 1 || C > 4 || F < 1 || L < 1) return fail(ctx, CVVDP_ERR_INVALID, "bad Q_per_ch shape");
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     const size_t qb = (size_t)B * C * F * L * sizeof(float);
     float *q_dev = nullptr, *j_dev = nullptr;
     CU_CHECK(ctx, cudaMalloc(&q_dev, qb + 256));
@@ -1398,7 +1432,8 @@ int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int bat
     if (frame < src->frame0 || frame >= src->frame0 + src->n_frames) return fail(ctx, CVVDP_ERR_INVALID, "frame %d outside the view", frame);
     if (ctx->disp.eotf == CVVDP_EOTF_HLG && in_channels != 3) return fail(ctx, CVVDP_ERR_UNSUPPORTED, "HLG needs three colour channels");
     if (colorspace < CVVDP_CS_DKLD65 || colorspace > CVVDP_CS_LMS2006) return fail(ctx, CVVDP_ERR_INVALID, "unknown colour space id %d", colorspace);
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     FrontendArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.clip = to_view(src);
@@ -1432,7 +1467,8 @@ int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, con
         return fail(ctx, CVVDP_ERR_INVALID, "subsampled chroma needs even luma dimensions");
     if (frame < src->frame0 || frame >= src->frame0 + src->n_frames) return fail(ctx, CVVDP_ERR_INVALID, "frame %d outside the view", frame);
     if (colorspace < CVVDP_CS_DKLD65 || colorspace > CVVDP_CS_LMS2006) return fail(ctx, CVVDP_ERR_INVALID, "unknown colour space id %d", colorspace);
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     FrontendArgs fa;
     memset(&fa, 0, sizeof(fa));
     fa.clip = to_view(src);
@@ -1459,7 +1495,8 @@ int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, con
 
 int cvvdp_b200_input_stats(cvvdp_b200_ctx *ctx, cvvdp_b200_input_report *out, int reset) {
     if (!ctx || !out) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     CU_CHECK(ctx, cudaDeviceSynchronize());  // the temporal kernels of every stream of this context have finished
     int h[8];
     CU_CHECK(ctx, cudaMemcpy(h, ctx->flags_dev, sizeof(h), cudaMemcpyDeviceToHost));
@@ -1524,7 +1561,8 @@ int cvvdp_b200_profile_enable(cvvdp_b200_ctx *ctx, int enable) {
 
 int cvvdp_b200_profile_read(cvvdp_b200_ctx *ctx, cvvdp_b200_kernel_stat *out, int max_entries, int *n_entries) {
     if (!ctx || !out || !n_entries) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
-    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
     CU_CHECK(ctx, cudaDeviceSynchronize());
     int n = 0;
     for (auto &r : ctx->prof_recs) {

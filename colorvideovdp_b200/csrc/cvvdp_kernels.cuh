@@ -66,13 +66,16 @@ __device__ __forceinline__ void eotf_forward_n(float (&v)[3], const DisplayDev &
             for (int i = 0; i < N; ++i) v[i] = fminf(fmaxf(v[i] * d.exposure, d.lin_lo), d.Ypeak) + d.Yrefl;
             break;
         case CVVDP_EOTF_HLG: {  // display_model.py:89-108, 350-359 (needs all three channels; the plan refuses N = 1)
-            const float ha = 0.17883277f, hb = 1.f - 4.f * ha, hc = 0.5f - ha * logf(4.f * ha);
+            // exp / pow through the MUFU pair like every other power on this path: the libm versions cost ~100
+            // instructions per call and, unrolled over pixels and frames, blew the float-input kernel up to 240 KB
+            const float ha = 0.17883277f, hb = 1.f - 4.f * ha, hc = 0.5f - ha * -0.33500979f;  // ln(4 ha) = -0.33500979
+            const float k_exp = 1.4426950408889634f / ha;
             float s[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                s[i] = v[i] <= 0.5f ? v[i] * v[i] / 3.0f : (expf((v[i] - hc) / ha) + hb) / 12.0f;
+                s[i] = v[i] <= 0.5f ? v[i] * v[i] / 3.0f : (f_ex2((v[i] - hc) * k_exp) + hb) / 12.0f;
             float Ys = 0.2627f * s[0] + 0.6780f * s[1] + 0.0593f * s[2];
-            float gsc = powf(Ys, d.gamma - 1.f);
+            float gsc = f_pow(Ys, d.gamma - 1.f);
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 float lin = gsc * s[i];
@@ -460,7 +463,9 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     float msum = 0.f;     // achromatic DKL sum of this thread's two pixels of clip frame 0 (test video)
     const int it_zero = v == 0 && a.mean0 != nullptr ? FL - 1 - a.f0 : -1;  // iteration that holds clip frame 0
     auto convert_chunk = [&](int it0) {
-#pragma unroll 3
+        // three frames in flight for the table variant (a dozen instructions per frame); the per-pixel EOTF of the
+        // float variant is long enough to hide its own latencies and must not be replicated
+#pragma unroll(USE_LUT ? 3 : 1)
         for (int g = 0; g < G; ++g) {
             const unsigned char *q = raw + g * frame_bytes;
             unsigned ba[3], bb[3];
@@ -1378,7 +1383,9 @@ __global__ void __launch_bounds__(256) k_pool(const PoolArgs a) {
     const float tot = block_sum_256(acc, red);
     if (tid == 0) {
         float Q;
-        if (a.F == 1) Q = q_img * a.image_int;  // l.636
+        // l.636: images (one frame, three channels -- a one-frame slice of a video keeps its transient channel
+        // and the temporal pooling formula)
+        if (a.F == 1 && a.C == 3) Q = q_img * a.image_int;
         else Q = spow_acc(tot / (float)a.F, 1.f / a.beta_t, a.eps);  // l.638
         a.jod[b] = met2jod_dev(Q, a.jod_a, a.jod_exp);
     }

@@ -102,6 +102,15 @@ def _band_frequencies(width, height, ppd):
     return freqs
 
 
+def _as_float32(t):
+    """video_source_array._get_frame's unpacking (video_source.py:324-342) for a whole clip."""
+    if t.dtype == torch.uint8:
+        return t.to(torch.float32) / 255
+    if t.dtype == torch.int16:
+        return (t.to(torch.int32) & 0xFFFF).to(torch.float32) / 65535
+    return t.to(torch.float32)
+
+
 def _clip_of(t, batch, frame0=0):
     c = N.Clip()
     c.data = t.data_ptr()
@@ -338,8 +347,8 @@ class cvvdp(vq_metric):
         photo = photometry if photometry is not None else self.display_photometry
         if not isinstance(photo, vvdp_display_photo_eotf):
             raise RuntimeError("the fused front end needs a vvdp_display_photo_eotf display model")
-        if test.dtype != ref.dtype:
-            raise RuntimeError("Test and reference must have the same dtype")
+        if test.dtype != ref.dtype:  # the reference unpacks frame by frame and accepts a mix (video_source.py:324-342)
+            test, ref = _as_float32(test), _as_float32(ref)
         B = max(test.shape[0], ref.shape[0])
         H, W, F = test.shape[3], test.shape[4], int(n_frames_total)
         if B > 1 and self.do_heatmap:

@@ -182,7 +182,7 @@ class vvdp_display_photo_eotf(vvdp_display_photometry):
         if V.dim() != 5:
             raise RuntimeError("expected a [B,C,1,H,W] frame")
         if not mock and not V.is_cuda:
-            V = V.to("cuda")
+            V = V.to(torch.device("cuda", torch.cuda.current_device()))  # host frames go to the caller's current device
         if V.dtype != torch.float32:
             V = V.to(torch.float32)
         B, Cc, F, H, W = V.shape

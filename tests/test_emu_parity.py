@@ -360,3 +360,18 @@ def test_pageable_host_clips_take_the_bounce_buffers(mock_device, monkeypatch):
     monkeypatch.setenv("CVVDP_B200_FORCE_STAGING", "1")
     _, staged = m.predict(tst, ref, frames_per_second=60)
     assert np.array_equal(direct["Q_per_ch"], staged["Q_per_ch"])
+
+
+def test_mixed_dtypes_and_single_frame_slices(mock_device):
+    """Test and reference of different dtypes are accepted like in the reference (it unpacks per frame); pooling a
+    one-frame slice of a video keeps the video formula (four channels, no image_int)."""
+    tst, ref = synth.make_pair_u8(97, 5, 24, 40)
+    m = cv.cvvdp(display_name="standard_fhd")
+    j_u8, s_u8 = m.predict(tst, ref, frames_per_second=30)
+    j_mix, s_mix = m.predict(tst, ref.astype(np.float32) / 255, frames_per_second=30)
+    gu.assert_q_close(s_mix["Q_per_ch"], s_u8["Q_per_ch"], "mixed dtypes")
+    assert abs(float(j_mix) - float(j_u8)) <= 1e-4
+    vs = cv.video_source_array(tst, ref, 30, display_photometry=m.display_photometry)
+    j1, s1 = m.predict_video_source(vs, frame_range=(2, 3))
+    j1_o = O.do_pooling_and_jods(s_u8["Q_per_ch"][:, :, 2:3], O.Params(), is_image=False)
+    assert abs(float(j1) - float(np.asarray(j1_o).ravel()[0])) <= 1e-4
