@@ -49,7 +49,7 @@ class Job(C.Structure):
     _fields_ = [("batch", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("n_frames", C.c_int32),
                 ("fps", C.c_float), ("in_channels", C.c_int32), ("dtype", C.c_int32), ("padding", C.c_int32),
                 ("heatmap", C.c_int32), ("max_block_frames", C.c_int32), ("workspace_limit_bytes", C.c_int64),
-                ("yuv", Yuv), ("features", C.c_int32)]
+                ("yuv", Yuv), ("features", C.c_int32), ("prefiltered", C.c_int32)]
 
 
 class PlanInfo(C.Structure):

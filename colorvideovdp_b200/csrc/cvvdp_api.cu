@@ -433,7 +433,22 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
     const float eps = 1e-5f;
 
     // ---- temporal stage ----
-    {
+    if (job.prefiltered) {  // cvvdp_metric.py:470-488: the source's four temporal channels are level 0
+        PackArgs pk;
+        pk.clip[0] = to_view(test);
+        pk.clip[1] = to_view(ref);
+        pk.clip[0].ring = pk.clip[1].ring = ring;
+        pk.B = B;
+        pk.H = job.height;
+        pk.W = job.width;
+        pk.f0 = f0;
+        pk.f1 = f1;
+        pk.out = ctx->lv[0].g;
+        const long long npix = (long long)job.height * job.width;
+        LaunchScope ls(ctx, st, CVVDP_K_TEMPORAL, 0, (double)npix * pairs * 2 * 32.0);
+        auto kfn = k_pack_level0;
+        CVVDP_LAUNCH(kfn, dim3((unsigned)((npix + 255) / 256), (unsigned)(pairs * 2)), dim3(256), 0, st, pk);
+    } else {
         TemporalArgs ta;
         memset(&ta, 0, sizeof(ta));
         ta.clip[0] = to_view(test);
@@ -907,7 +922,10 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     if (job->batch < 1 || job->height < 4 || job->width < 4 || job->n_frames < 1)
         return fail(ctx, CVVDP_ERR_INVALID, "bad job shape B=%d H=%d W=%d F=%d (H, W >= 4)", job->batch, job->height,
                     job->width, job->n_frames);
-    if (job->in_channels != 1 && job->in_channels != 3)
+    if (job->prefiltered) {
+        if (job->in_channels != 4 || job->dtype != CVVDP_DTYPE_F32 || job->n_frames < 2 || job->yuv.chroma != 0)
+            return fail(ctx, CVVDP_ERR_INVALID, "pre-filtered clips: fp32, four channels, a video");
+    } else if (job->in_channels != 1 && job->in_channels != 3)
         return fail(ctx, CVVDP_ERR_INVALID, "The content must have either 1 or 3 color channels.");
     if (job->n_frames > 1 && !(job->fps > 0.f))
         return fail(ctx, CVVDP_ERR_INVALID, "When passing video sequences, you must set frames_per_second parameter");
@@ -940,7 +958,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     memset(&info, 0, sizeof(info));
     const int L = band_setup(job->width, job->height, (double)ctx->disp.ppd, &info);
     info.n_channels = job->n_frames == 1 ? 3 : 4;
-    if (job->n_frames == 1) info.filter_len = 1;
+    if (job->n_frames == 1 || job->prefiltered) info.filter_len = 1;
     else {
         const int fl = temporal_filters(ctx->P, (double)job->fps, &info);
         if (fl < 0) return fail(ctx, CVVDP_ERR_UNSUPPORTED, "temporal filter longer than %d taps", CVVDP_MAX_FILTER_LEN);

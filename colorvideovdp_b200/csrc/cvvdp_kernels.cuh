@@ -321,6 +321,26 @@ __device__ __forceinline__ int temporal_source_frame(const TemporalArgs &a, int 
     return (a.padding == CVVDP_PAD_REPLICATE) ? 0 : symmetric_frame_index(t, a.F_total);
 }
 
+// Pre-filtered sources (cvvdp_metric.py:470-488): the video source already delivers the four temporal channels
+// (A-sust, RG, YV, A-trans: colour space 'DKLd65_trans'), so the FIR is bypassed and the stage only repacks the
+// planar fp32 [B,4,F,H,W] frames into the float4 pixels of level 0.
+struct PackArgs {
+    ClipView clip[2];
+    int B, H, W, f0, f1;
+    float4 *out;  // level 0: [B][n][2][H*W]
+};
+__global__ void __launch_bounds__(256) k_pack_level0(const PackArgs a) {
+    const long long npix = (long long)a.H * a.W;
+    const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (p >= npix) return;
+    const int n = a.f1 - a.f0;
+    const int v = blockIdx.y & 1, bf = blockIdx.y >> 1, b = bf / n, f = bf - b * n;
+    const ClipView &cv = a.clip[v];
+    const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
+    const float *src = (const float *)cv.data + b * cv.s[0] + (long long)frame_slot(cv, a.f0 + f) * cv.s[2] + y * cv.s[3] + x * cv.s[4];
+    a.out[((long long)(b * n + f) * 2 + v) * npix + p] = make_float4(src[0], src[cv.s[1]], src[2 * cv.s[1]], src[3 * cv.s[1]]);
+}
+
 // Two-stage packed temporal kernel.  A thread owns TWO pixels of its warp's 64-pixel segment (lane l: pixels
 // l and l+32, so both 128-bit stores of a warp cover 512 contiguous bytes) as the halves of fp32x2 registers;
 // the ring of the last FL frames lives in registers.  Unrolling the whole time loop by one ring period

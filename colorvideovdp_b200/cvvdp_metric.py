@@ -202,7 +202,7 @@ class cvvdp(vq_metric):
         return self.predict_video_source(test_vs)
 
     # ------------------------------------------------------------------------------------------
-    def _plan(self, B, H, W, F, fps, cin, dtype_id, photo, yuv=None, features=False):
+    def _plan(self, B, H, W, F, fps, cin, dtype_id, photo, yuv=None, features=False, prefiltered=False):
         """(Re)build the native plan when the job or the display changed.  photo=None: frames already
         are DKLd65 (plugin sources), the front end passes them through."""
         if self.temp_padding not in ("replicate", "symmetric"):
@@ -215,7 +215,7 @@ class cvvdp(vq_metric):
         hm = {"raw": N.HEATMAP_RAW, "threshold": N.HEATMAP_THRESHOLD,
               "supra-threshold": N.HEATMAP_SUPRATHRESHOLD}[self.heatmap] if self.do_heatmap else N.HEATMAP_NONE
         key = (B, H, W, F, float(fps), cin, dtype_id, self.temp_padding, hm, bytes(disp), self.gpu_mem,
-               bytes(yuv) if yuv is not None else None, bool(features))
+               bytes(yuv) if yuv is not None else None, bool(features), bool(prefiltered))
         if key != self._plan_key:
             self._ctx.set_display(disp)
             job = N.Job(batch=B, height=H, width=W, n_frames=F, fps=float(fps), in_channels=cin, dtype=dtype_id,
@@ -225,6 +225,7 @@ class cvvdp(vq_metric):
             if yuv is not None:
                 job.yuv = yuv
             job.features = 1 if features else 0
+            job.prefiltered = 1 if prefiltered else 0
             self._info = self._ctx.plan(job)
             self._plan_key = key
         return self._info
@@ -256,10 +257,10 @@ class cvvdp(vq_metric):
         B = vid_source.get_batch_size()
         if B > 1 and self.do_heatmap:
             raise vq_exception("Heatmaps not supported when batches are used")
-        if getattr(vid_source, "is_temporally_filtered", False):
-            raise NotImplementedError("pre-filtered video sources ('DKLd65_trans') are not supported")
         fps = vid_source.get_frames_per_second() if F > 1 else 0
         f0, f1 = (0, F) if frame_range is None else frame_range
+        if F > 1 and getattr(vid_source, "is_temporally_filtered", False):
+            return self._run_prefiltered(vid_source, B, H, W, F, fps, f0, f1)
         fast = type(vid_source) is video_source_array and type(vid_source.dm_photometry) is vvdp_display_photo_eotf
         if fast:
             return self._run_arrays(vid_source, B, H, W, F, fps, f0, f1)
@@ -421,6 +422,31 @@ class cvvdp(vq_metric):
             ph, pw, _, off = layout[bb]
             feats.append(buf[off:layout[bb + 1][3]].view(B, F, ph, pw, C, 6))
         return feats, None
+
+    def _run_prefiltered(self, vs, B, H, W, F, fps, f0, f1):
+        """Sources that deliver the four temporal channels themselves (cvvdp_metric.py:470-488, e.g. an
+        eye-motion model): frames come as 'DKLd65_trans' [B,4,1,H,W], reference before test, and enter the CUDA
+        path as level 0 -- the temporal filter is bypassed."""
+        vs._frames_pulled_through_plugin = True
+        info = self._plan(B, H, W, F, fps, 4, N.DTYPE_F32, None, prefiltered=True)
+        Q, hm = self._alloc_outputs(B, info.n_channels, F, info.n_bands, H, W, whole=(f0 == 0 and f1 == F))
+        nb = info.block_frames
+        for cur in range(f0, f1, nb):
+            end = min(cur + nb, f1)
+            fr_r, fr_t = [], []
+            for f in range(cur, end):
+                fr_r.append(vs.get_reference_frame(f, device=self.device, colorspace="DKLd65_trans").to(
+                    device=self.device, dtype=torch.float32))
+                fr_t.append(vs.get_test_frame(f, device=self.device, colorspace="DKLd65_trans").to(
+                    device=self.device, dtype=torch.float32))
+            win_t, win_r = torch.cat(fr_t, dim=2), torch.cat(fr_r, dim=2)
+            if win_t.shape[1] != 4 or win_r.shape[1] != 4:
+                raise RuntimeError("a temporally filtered source must deliver four channels ('DKLd65_trans')")
+            self._ctx.process_device(_clip_of(win_t, B, cur), _clip_of(win_r, B, cur), cur, end, Q.data_ptr(),
+                                     hm.data_ptr() if hm is not None else None, self._stream())
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()  # the windows are released below
+        return Q, hm
 
     def _run_plugin(self, vs, B, H, W, F, fps, f0, f1):
         """Any third-party video_source: frames are pulled through get_*_frame(..., 'DKLd65'), strictly in

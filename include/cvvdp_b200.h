@@ -110,6 +110,9 @@ typedef struct {
     int64_t workspace_limit_bytes; /* 0 = default */
     cvvdp_b200_yuv yuv;      /* yuv.chroma != 0: the clips hold planar YUV frames (dtype U8 or U16, in_channels 3) */
     int32_t features;        /* != 0: also produce the per-band patch statistics of the ML heads (see cvvdp_b200_feature_layout) */
+    int32_t prefiltered;     /* != 0: the clips hold the four temporal channels already ('DKLd65_trans' frames of a video
+                              * source with is_temporally_filtered, cvvdp_metric.py:470-488): fp32, in_channels 4, display
+                              * CVVDP_EOTF_NONE; the temporal filter is bypassed */
 } cvvdp_b200_job;
 
 typedef struct {

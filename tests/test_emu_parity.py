@@ -375,3 +375,33 @@ def test_mixed_dtypes_and_single_frame_slices(mock_device):
     j1, s1 = m.predict_video_source(vs, frame_range=(2, 3))
     j1_o = O.do_pooling_and_jods(s_u8["Q_per_ch"][:, :, 2:3], O.Params(), is_image=False)
     assert abs(float(j1) - float(np.asarray(j1_o).ravel()[0])) <= 1e-4
+
+
+def _prefiltered_source(z, fps):
+    class Prefiltered(cv.video_source):  # a third-party source that does its own temporal filtering
+        is_temporally_filtered = True
+
+        def get_video_size(self):
+            return (z["test4"].shape[3], z["test4"].shape[4], z["test4"].shape[2])
+
+        def get_frames_per_second(self):
+            return fps
+
+        def get_test_frame(self, frame, device, colorspace):
+            assert colorspace == "DKLd65_trans"
+            return torch.from_numpy(z["test4"][:, :, frame:frame + 1]).to(device)
+
+        def get_reference_frame(self, frame, device, colorspace):
+            assert colorspace == "DKLd65_trans"
+            return torch.from_numpy(z["ref4"][:, :, frame:frame + 1]).to(device)
+
+    return Prefiltered()
+
+
+def test_prefiltered_video_source(mock_device):
+    """is_temporally_filtered sources (cvvdp_metric.py:470-488): four-channel frames bypass the temporal filter."""
+    z, meta = gu.load_case("prefilt_vid_f32_7x48x80_fhd")
+    m = cv.cvvdp(display_name=meta["display"])
+    jod, stats = m.predict_video_source(_prefiltered_source(z, meta["fps"]))
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], "prefiltered")
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL

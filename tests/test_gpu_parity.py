@@ -304,3 +304,13 @@ def test_pageable_numpy_input_equals_pinned_input():
     _, pinned = m.predict(tp, rp, frames_per_second=30)
     _, dev = m.predict(_t(tst), _t(ref), frames_per_second=30)
     assert np.array_equal(pageable["Q_per_ch"], pinned["Q_per_ch"]) and np.array_equal(pinned["Q_per_ch"], dev["Q_per_ch"])
+
+
+def test_prefiltered_video_source_on_hardware():
+    """is_temporally_filtered sources (cvvdp_metric.py:470-488) against the reference-generated fixture."""
+    from test_emu_parity import _prefiltered_source
+    z, meta = gu.load_case("prefilt_vid_f32_7x48x80_fhd")
+    m = cv.cvvdp(display_name=meta["display"], device=DEV)
+    jod, stats = m.predict_video_source(_prefiltered_source(z, meta["fps"]))
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], "prefiltered")
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL

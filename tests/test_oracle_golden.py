@@ -134,3 +134,11 @@ def test_oracle_temporal_filters_match_reference():
         if key.startswith("fps_"):
             got = np.stack(O.temporal_filters(float(key[4:]), P))
             assert got.shape == z[key].shape and np.max(np.abs(got - z[key])) <= 2e-6, key
+
+
+def test_oracle_prefiltered_source_fixture():
+    """Pre-filtered video source (cvvdp_metric.py:470-488) against the reference-generated fixture."""
+    z, meta = gu.load_case("prefilt_vid_f32_7x48x80_fhd")
+    jod, stats = O.predict_prefiltered(z["test4"], z["ref4"], meta["fps"], meta["display"])
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], "prefiltered")
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
