@@ -137,7 +137,8 @@ struct DeviceGuard {
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Tiled tensor map over `planes` float4 planes of h x w pixels, viewed as fp32 [planes][h][4w].
-bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int planes, int box_px, int box_rows, int box_planes = 2) {
+bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int planes, int box_px, int box_rows, int box_planes = 2,
+                     int l2_promotion = 128) {
 #ifdef CVVDP_EMU
     m->base = (const float *)base;
     m->dim[0] = 4 * w;
@@ -149,6 +150,7 @@ bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int plane
     m->box[0] = 4 * box_px;
     m->box[1] = box_rows;
     m->box[2] = box_planes;
+    (void)l2_promotion;
     return true;
 #else
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -166,8 +168,12 @@ bool make_tensor_map(TensorMap3D *m, const float4 *base, int w, int h, int plane
     const cuuint64_t strides[2] = {(cuuint64_t)w * 16, (cuuint64_t)w * h * 16};  // bytes, dims 1 and 2
     const cuuint32_t box[3] = {(cuuint32_t)(4 * box_px), (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapL2promotion promo = l2_promotion == 0    ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                         : l2_promotion == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : l2_promotion == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                               : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
     return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                  CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 #endif
 }
 
@@ -1049,6 +1055,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     const double log2_10 = log2(10.0);
     const double sens = pow(10.0, (double)ctx->P.sensitivity_correction / 20.0);
     const double gain[4] = {1.0, 1.45, 1.0, 1.0};
+    // L2 promotion of the tensor maps: 64 / 128 / 256 bytes and none were timed on one box (round 2): within 1.5 %
+    const int reduce_promo = 128, band_promo = 128;
     for (int i = 0; i < L; ++i) {
         LevelBuf &lv = ctx->lv[i];
         char *base = (char *)ctx->arena;
@@ -1057,9 +1065,9 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.hm = do_hm ? (float *)(base + off_h[i]) : nullptr;
         lv.feat = job->features ? (float4 *)(base + off_f[i]) : nullptr;
         lv.lut = (float4 *)(base + off_l[i]);
-        lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_BAND_EW, CVVDP_B2_RB) &&
-                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_BAND_EW / 2 + 2, CVVDP_B2_CR) &&
-                   make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<8>::IH, 1);
+        lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_BAND_EW, CVVDP_B2_RB, 2, band_promo) &&
+                   make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_BAND_EW / 2 + 2, CVVDP_B2_CR, 2, band_promo) &&
+                   make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<8>::IH, 1, reduce_promo);
         float rows[4][CVVDP_CSF_LUT_N];
         for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
         float packed[CVVDP_CSF_LUT_N][4];

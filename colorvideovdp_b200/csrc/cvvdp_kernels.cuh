@@ -654,14 +654,19 @@ __global__ void __launch_bounds__(256) k_reduce(const ReduceArgs a) {
     }
 }
 
-// Persistent TMA version of the reduce: each CTA loops over output tiles of 30 x TY pixels; the 63 x (2 TY + 3)
-// input box of the NEXT tile is fetched by one cp.async.bulk.tensor while the current one is filtered
-// (two shared-memory buffers, one mbarrier each).  TMA's zero fill outside the image is exactly the
-// zero padding of the reference's strided conv2d; the edge fix-ups are the same as in k_reduce.
-// TY = 8 is the default; TY = 16 (63x35 input box, surplus halo traffic 1.25x -> 1.15x of the algorithmic bytes
-// when the L2 keeps none of it) is an opt-in A/B variant (CVVDP_B200_REDUCE_TY16), not yet measured.
+// Persistent TMA version of the reduce: each CTA owns a CONTIGUOUS range of output tiles of 30 x 8 pixels,
+// enumerated column-major inside a plane (ty fastest), so that consecutive tiles of a CTA are vertical neighbours:
+// the three halo rows a tile shares with its predecessor were fetched by the same SM microseconds earlier and
+// come from the L2 instead of DRAM (round 1 walked the tiles row-major with a grid stride and re-read every halo
+// row from DRAM: 1.19x the algorithmic bytes).  The 63 x 19 input box of the NEXT tile is fetched by one
+// cp.async.bulk.tensor while the current one is filtered (two shared-memory buffers, one mbarrier each).  TMA's
+// zero fill outside the image is exactly the zero padding of the reference's strided conv2d; the edge fix-ups
+// are the same as in k_reduce.  The vertical pass stores even and odd columns apart, so that the stride-2
+// column pass reads consecutive 128-bit words (no bank conflicts).
 #define CVVDP_R2_TX 30
 #define CVVDP_R2_IW (2 * CVVDP_R2_TX + 3)  // 63 pixels = 252 floats (TMA box limit 256)
+#define CVVDP_R2_EP 36                     // float4 pitch of the even-column half of a ya row (32 + 4: the odd half
+                                           // then starts 64 bytes off a 128-byte boundary)
 struct Reduce2Args {
     TensorMap3D tm_in;  // fp32 view [planes][h][4w], box {252, 2 TY + 3, 1}
     float4 *out;
@@ -669,10 +674,10 @@ struct Reduce2Args {
 };
 template <int TY>
 struct Reduce2Smem {
-    static constexpr int IH = 2 * TY + 3;                                    // 19 / 35 input rows
+    static constexpr int IH = 2 * TY + 3;                                    // 19 input rows
     static constexpr int BUF = (IH * CVVDP_R2_IW * 16 + 127) / 128 * 128 / 16;  // float4 per buffer, 128-byte multiple
     float4 in[2][BUF];
-    float4 ya[TY][CVVDP_R2_IW + 1];
+    float4 ya[TY][CVVDP_R2_EP + 32];  // [oy][0..31]: columns 0,2,4,...; [oy][36..67]: columns 1,3,5,...
     unsigned long long bar[2];
 };
 template <int TY>
@@ -684,6 +689,8 @@ __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2
     const int tid = threadIdx.x;
     const int ntx = (a.wc + CVVDP_R2_TX - 1) / CVVDP_R2_TX, nty = (a.hc + TY - 1) / TY;
     const long long total = (long long)ntx * nty * a.planes;
+    // this CTA's contiguous tile range; tile index t = (plane * ntx + tx) * nty + ty
+    const long long t_begin = total * blockIdx.x / gridDim.x, t_end = total * (blockIdx.x + 1) / gridDim.x;
     const bool rows_odd = (a.h & 1) != 0;
     if (tid == 0) {
         mbar_init(&sm.bar[0], 1);
@@ -692,21 +699,21 @@ __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2
     __syncthreads();
     auto issue = [&](long long t, int buf) {
         const int plane = (int)(t / (ntx * nty)), rem = (int)(t - (long long)plane * (ntx * nty));
-        const int ty = rem / ntx, tx = rem - ty * ntx;
+        const int tx = rem / nty, ty = rem - tx * nty;
         fence_proxy_async();
         mbar_expect_tx(&sm.bar[buf], IH * CVVDP_R2_IW * 16);
         tma_load_3d(&sm.in[buf][0], &a.tm_in, 4 * (2 * tx * CVVDP_R2_TX - 2), 2 * ty * TY - 2, plane, &sm.bar[buf]);
         mbar_emu_complete(&sm.bar[buf]);
     };
-    if (tid == 0 && (long long)blockIdx.x < total) issue(blockIdx.x, 0);
+    if (tid == 0 && t_begin < t_end) issue(t_begin, 0);
     int k = 0;
-    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++k) {
+    for (long long t = t_begin; t < t_end; ++t, ++k) {
         const int buf = k & 1;
-        if (tid == 0 && t + gridDim.x < total) issue(t + gridDim.x, buf ^ 1);
+        if (tid == 0 && t + 1 < t_end) issue(t + 1, buf ^ 1);
         mbar_wait(&sm.bar[buf], (unsigned)((k >> 1) & 1));
         const float4 *in = sm.in[buf];
         const int plane = (int)(t / (ntx * nty)), rem = (int)(t - (long long)plane * (ntx * nty));
-        const int ty = rem / ntx, tx = rem - ty * ntx;
+        const int tx = rem / nty, ty = rem - tx * nty;
         const int ox0 = tx * CVVDP_R2_TX, oy0 = ty * TY;
         const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
         for (int i = tid; i < TY * CVVDP_R2_IW; i += 256) {
@@ -733,29 +740,31 @@ __global__ void __launch_bounds__(256) k_reduce2(const __grid_constant__ Reduce2
                     }
                 }
             }
-            sm.ya[oy][c] = acc;
+            sm.ya[oy][(c & 1) * CVVDP_R2_EP + (c >> 1)] = acc;
         }
         __syncthreads();
-        for (int o = tid; o < CVVDP_R2_TX * TY; o += 256) {  // one pass for TY = 8 (240 outputs), two for TY = 16
+        // column c of the vertical pass lives at ya[oy][(c & 1) * EP + (c >> 1)]
+        auto ya_at = [&](int oy, int c) -> const float4 & { return sm.ya[oy][(c & 1) * CVVDP_R2_EP + (c >> 1)]; };
+        for (int o = tid; o < CVVDP_R2_TX * TY; o += 256) {  // one pass for TY = 8 (240 outputs)
             const int ox = o % CVVDP_R2_TX, oy = o / CVVDP_R2_TX;
             const int gox = ox0 + ox, goy = oy0 + oy;
             if (gox < a.wc && goy < a.hc) {
-                const int c = 2 * ox;
-                float4 acc = K0 * sm.ya[oy][c];
-                acc = fma4(K1, sm.ya[oy][c + 1], acc);
-                acc = fma4(K2, sm.ya[oy][c + 2], acc);
-                acc = fma4(K1, sm.ya[oy][c + 3], acc);
-                acc = fma4(K0, sm.ya[oy][c + 4], acc);
+                const float4 *ev = &sm.ya[oy][ox], *od = &sm.ya[oy][CVVDP_R2_EP + ox];  // columns 2 ox + {0,2,4} / {1,3}
+                float4 acc = K0 * ev[0];
+                acc = fma4(K1, od[0], acc);
+                acc = fma4(K2, ev[1], acc);
+                acc = fma4(K1, od[1], acc);
+                acc = fma4(K0, ev[2], acc);
                 if (gox == 0) {  // lpyr_dec.py:205
-                    acc = fma4(K1, sm.ya[oy][0 - ix0], acc);
-                    acc = fma4(K0, sm.ya[oy][min(1, a.w - 1) - ix0], acc);
+                    acc = fma4(K1, ya_at(oy, 0 - ix0), acc);
+                    acc = fma4(K0, ya_at(oy, min(1, a.w - 1) - ix0), acc);
                 }
                 if (gox == a.wc - 1) {  // lpyr_dec.py:206-209: the parity of the ROW count chooses the rule
                     if (rows_odd) {
-                        acc = fma4(K1, sm.ya[oy][a.w - 1 - ix0], acc);
-                        acc = fma4(K0, sm.ya[oy][max(a.w - 2, 0) - ix0], acc);
+                        acc = fma4(K1, ya_at(oy, a.w - 1 - ix0), acc);
+                        acc = fma4(K0, ya_at(oy, max(a.w - 2, 0) - ix0), acc);
                     } else {
-                        acc = fma4(K0, sm.ya[oy][a.w - 1 - ix0], acc);
+                        acc = fma4(K0, ya_at(oy, a.w - 1 - ix0), acc);
                     }
                 }
                 a.out[(long long)plane * a.hc * a.wc + (long long)goy * a.wc + gox] = acc;
