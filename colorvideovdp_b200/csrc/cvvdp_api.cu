@@ -39,6 +39,8 @@ struct LevelBuf {
     TensorMap3D tm;  // fp32 view [planes][h][4w] of g; box depends on the role (see make_tensor_map)
     TensorMap3D tm_as_coarse;
     TensorMap3D tm_reduce_in;  // box {63 px, 19 rows, 1 plane}
+    TensorMap3D tm_fa, tm_fb;  // fused band kernel: boxes {64 px, 11 rows, 2 planes} and {4 px, 11 rows, 2 planes}
+    bool fused = false;        // level i+1 is computed by this level's band kernel (k_band2f), no reduce launch
     bool tm_ok = false;
 };
 
@@ -546,8 +548,8 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
         }
     }
-    // ---- Gaussian pyramid ----
-    for (int i = 0; i + 1 < L; ++i) {
+    // ---- Gaussian pyramid: level i -> i+1, unless the band kernel of level i computes level i+1 itself ----
+    auto do_reduce = [&](int i) {
         ReduceArgs ra;
         ra.in = ctx->lv[i].g;
         ra.out = ctx->lv[i + 1].g;
@@ -575,12 +577,15 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             auto kfn = k_reduce;
             CVVDP_LAUNCH(kfn, grid, dim3(256), 0, st, ra);
         }
-    }
-    // ---- bands ----
+    };
+    // ---- bands (each preceded by the reduce that produces its coarse level, when that is a separate launch) ----
     const bool is_image = job.n_frames == 1;
     const float ch_w[4] = {1.f, P.ch_chrom_w, P.ch_chrom_w, is_image ? 0.f : P.ch_trans_w};
     const float t_int = is_image ? P.image_int : 1.f;
     for (int i = 0; i + 1 < L; ++i) {
+        static const bool no_tma = getenv("CVVDP_B200_NO_TMA") != nullptr;  // test hook: cp.async staging / plain reduce instead
+        const bool fused_now = ctx->lv[i].fused && !no_tma;
+        if (!fused_now) do_reduce(i);
         BandArgs ba;
         memset(&ba, 0, sizeof(ba));
         const LevelBuf &lv = ctx->lv[i];
@@ -620,7 +625,6 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         ba.hm_beta = P.beta_tch;
         ba.hm_scale = (i == 0) ? 1.f : 0.5f;
         ba.seg_rows = lv.seg_rows;
-        static const bool no_tma = getenv("CVVDP_B200_NO_TMA") != nullptr;  // A/B switch: cp.async staging instead
         ba.use_tma = (lv.tm_ok && ctx->lv[i + 1].tm_ok && !no_tma) ? 1 : 0;
         if (ba.use_tma) {
             ba.tm_fine = lv.tm;
@@ -631,6 +635,22 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
                        (double)pairs * 2 * 16.0 * ((double)ba.h * ba.w + (double)ba.hc * ba.wc) +
                            (do_hm ? (double)pairs * 4.0 * ba.h * ba.w : 0.0));
         const int variant = (ba.do_blur ? 4 : 0) | (ba.hm ? 2 : 0) | (ba.beta == 2.0f ? 1 : 0);
+        if (fused_now) {  // band + reduce in one kernel: writes level i+1
+            ba.coarse_out = ctx->lv[i + 1].g;
+            ba.tm_fine_a = lv.tm_fa;
+            ba.tm_fine_b = lv.tm_fb;
+            typedef void (*BandFn)(const BandArgs);
+            static const BandFn tf[4] = {k_band2f<false, false>, k_band2f<false, true>, k_band2f<true, false>, k_band2f<true, true>};
+            static bool attr_f[4] = {false, false, false, false};
+            const int vf = variant & 3;
+            if (!attr_f[vf]) {
+                cudaFuncSetAttribute(tf[vf], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BandFSmem));
+                attr_f[vf] = true;
+            }
+            BandFn kfn = tf[vf];
+            CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_B2_THREADS), sizeof(BandFSmem), st, ba);
+            continue;
+        }
         launch_band(ba, grid, st, variant, do_feat);
     }
     {
@@ -1057,6 +1077,7 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     const double gain[4] = {1.0, 1.45, 1.0, 1.0};
     // L2 promotion of the tensor maps: 64 / 128 / 256 bytes and none were timed on one box (round 2): within 1.5 %
     const int reduce_promo = 128, band_promo = 128;
+    const bool use_fused = getenv("CVVDP_B200_FUSED_REDUCE") != nullptr;  // A/B: band kernel computes the next level itself
     for (int i = 0; i < L; ++i) {
         LevelBuf &lv = ctx->lv[i];
         char *base = (char *)ctx->arena;
@@ -1068,6 +1089,11 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         lv.tm_ok = make_tensor_map(&lv.tm, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_BAND_EW, CVVDP_B2_RB, 2, band_promo) &&
                    make_tensor_map(&lv.tm_as_coarse, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_BAND_EW / 2 + 2, CVVDP_B2_CR, 2, band_promo) &&
                    make_tensor_map(&lv.tm_reduce_in, lv.g, lv.w, lv.h, (int)(B * nb * 2), CVVDP_R2_IW, Reduce2Smem<8>::IH, 1, reduce_promo);
+        lv.fused = false;
+        if (use_fused && i + 1 < L && lv.tm_ok && lv.do_blur && !job->features &&
+            make_tensor_map(&lv.tm_fa, lv.g, lv.w, lv.h, (int)(B * nb * 2), 64, CVVDP_BF_FR, 2, band_promo) &&
+            make_tensor_map(&lv.tm_fb, lv.g, lv.w, lv.h, (int)(B * nb * 2), 4, CVVDP_BF_FR, 2, band_promo))
+            lv.fused = true;
         float rows[4][CVVDP_CSF_LUT_N];
         for (int c = 0; c < 4; ++c) csf_row(ctx->lut, info.rho_band[i], c, rows[c]);
         float packed[CVVDP_CSF_LUT_N][4];

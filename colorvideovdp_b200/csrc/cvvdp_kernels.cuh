@@ -814,6 +814,10 @@ struct BandArgs {
     int use_tma;           // k_band2: stage the rows with TMA (else cp.async)
     TensorMap3D tm_fine;   // fp32 view [planes][h][4w] of level i,   box {4 EW, 8, 2}
     TensorMap3D tm_coarse; // fp32 view [planes][hc][4wc] of level i+1, box {4 CC, 6, 2}
+    // fused variant (k_band2f): level i+1 is COMPUTED here and written to coarse_out
+    float4 *coarse_out;    // level i+1 [pairs*2][hc*wc]
+    TensorMap3D tm_fine_a; // fp32 view of level i, box {256, 11, 2}: fine columns x0-10 .. x0+53
+    TensorMap3D tm_fine_b; // same view, box {16, 11, 2}: fine columns x0+54 .. x0+57
 };
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {  // torch 'reflect' padding
@@ -1221,6 +1225,330 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2(const __grid_cons
             }
         }
         dslot = dslot == 16 ? 0 : dslot + 8;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+        acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if ((tid & 31) == 0) {
+        sm.red[tid >> 5][0] = acc.x;
+        sm.red[tid >> 5][1] = acc.y;
+        sm.red[tid >> 5][2] = acc.z;
+        sm.red[tid >> 5][3] = acc.w;
+    }
+    __syncthreads();
+    if (tid < 4) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < CVVDP_B2_THREADS / 32; ++w) s += sm.red[w][tid];
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x, ntiles = gridDim.x * gridDim.y;
+        a.partials[((long long)pair * ntiles + tile) * 4 + tid] = s;
+    }
+}
+
+// =================================================================================================
+// Fused band kernel WITH the Gaussian-pyramid reduce ("one kernel per level", BASELINE north_star):
+// level i+1 is computed from the fine rows this kernel stages anyway, used for the expand / Laplacian of level i
+// straight from shared memory, and written to HBM once for the next level's kernel.  No reduce launches, and every
+// level is read from HBM once instead of twice.
+// Same strip-marching structure as k_band2 (EW = 60, conflict-free phase A, no lag), with per step:
+//   stage : ONE 11-row x 68-column box of fine rows [a0, a0+11) x [x0-10, x0+58) per video (two TMA boxes, 64 + 4
+//           columns wide): the 8 rows of the step plus the 3 rows below that the 5-tap reduce of coarse rows
+//           a0/2+1 .. a0/2+4 reaches; zero fill outside the image = the zero padding of the reference's conv2d
+//   R1    : vertical 5-tap pass, 4 coarse rows x 67 columns x 2 videos (even / odd columns stored apart)
+//   R2    : horizontal pass -> 4 x 32 coarse pixels x 2 videos into an 8-row ring; the pixels this CTA OWNS
+//           (coarse columns [24 bx, 24 bx + 24), coarse rows of its row segment) also go to HBM
+//   A,B,C : as k_band2; phase A reads the coarse ring with indices clamped to the coarse image (= replicate padding)
+// A prologue step (reduce only) at a0 = y_begin - 8 produces the two coarse rows above the first step.
+// =================================================================================================
+#define CVVDP_BF_EW 60
+#define CVVDP_BF_FW 68        // staged fine columns
+#define CVVDP_BF_FR 11        // staged fine rows
+#define CVVDP_BF_VP 36        // float4 pitch of the even-column half of a vertical-pass row (34 used + 2)
+#define CVVDP_BF_HBR 24       // ring of horizontally blurred rows (20 live)
+struct BandFSmem {
+    float4 lut[CVVDP_CSF_LUT_N];
+    float4 fine_a[2][CVVDP_BF_FR][64];                 // TMA box A (columns 0..63 of the staged frame)
+    float4 fine_b[2][CVVDP_BF_FR][4];                  // TMA box B (columns 64..67)
+    float4 crs[2][8][B2Geom<CVVDP_BF_EW>::CC];         // ring of coarse rows, slot = (cy - cbase) & 7
+    union {
+        float4 mm[CVVDP_B2_RB][CVVDP_BF_FW + 1];       // phase A -> B
+        float4 vp[2][4][2 * CVVDP_BF_VP];              // R1 -> R2: [video][coarse row][even half | odd half]
+    };
+    float4 hb[CVVDP_BF_HBR][B2Geom<CVVDP_BF_EW>::SW + 1];
+    float4 df[CVVDP_B2_DFR][B2Geom<CVVDP_BF_EW>::SW];
+    float red[CVVDP_B2_THREADS / 32][4];
+    unsigned long long bar;
+};
+#define CVVDP_BF_STAGE_BYTES ((unsigned)(sizeof(float4) * 2 * CVVDP_BF_FR * CVVDP_BF_FW))
+
+template <bool HM, bool BETA2>
+__global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2f(const __grid_constant__ BandArgs a) {
+    CVVDP_DYN_SMEM(smem_raw);
+    BandFSmem &sm = *reinterpret_cast<BandFSmem *>(smem_raw);
+    constexpr int EW = CVVDP_BF_EW, SW = B2Geom<EW>::SW, QW = B2Geom<EW>::QW, CC = B2Geom<EW>::CC;
+    constexpr int hal = CVVDP_BHALO;
+    const float K0 = 0.05f, K1 = 0.25f, K2 = 0.4f;
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.z;
+    const int x0 = blockIdx.x * SW, ex0 = x0 - hal, fx0 = x0 - 10;  // phase-A frame / staged frame
+    const int ys = blockIdx.y * a.seg_rows, ye = min(ys + a.seg_rows, a.h);
+    const int y_begin = max(ys - hal, 0);
+    const int a_end = min(ye + hal, a.h);
+    const long long npix = (long long)a.h * a.w, ncpix = (long long)a.hc * a.wc;
+    const bool x_edge = (ex0 < 0) || (x0 + SW + hal > a.w);
+    const int cx0 = ex0 / 2 - 1;              // coarse column of ring column 0 (= 24 bx - 4)
+    const int cbase = y_begin / 2 - 4;        // ring slot of coarse row cy: (cy - cbase) & 7
+    const int own_cy0 = ys / 2, own_cy1 = (ye == a.h) ? a.hc : ye / 2;  // coarse rows this segment writes
+    const bool rows_odd = (a.h & 1) != 0;
+    float4 *crs_out = a.coarse_out + (long long)pair * 2 * ncpix;
+
+    if (tid == 0) mbar_init(&sm.bar, 1);
+    if (tid < CVVDP_CSF_LUT_N) sm.lut[tid] = a.lut[tid];
+    __syncthreads();
+    unsigned tma_phase = 0;
+    auto stage = [&](int a0) {
+        if (tid == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&sm.bar, CVVDP_BF_STAGE_BYTES);
+            tma_load_3d(&sm.fine_a[0][0][0], &a.tm_fine_a, 4 * fx0, a0, 2 * pair, &sm.bar);
+            tma_load_3d(&sm.fine_b[0][0][0], &a.tm_fine_b, 4 * (fx0 + 64), a0, 2 * pair, &sm.bar);
+            mbar_emu_complete(&sm.bar);
+        }
+    };
+    stage(y_begin - CVVDP_B2_RB);  // prologue step: reduce only
+    float eps_q[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) eps_q[c] = f_pow(a.eps, a.q[c]);
+    const float eps_p = f_pow(a.eps, a.p);
+    const float eps_b = BETA2 ? 0.f : f_pow(a.eps, a.beta);
+    float4 acc = f4(0.f);
+    const int qy = tid / QW, qx = tid - qy * QW;
+    const int b_r = tid % CVVDP_B2_RB, b_xg = tid / CVVDP_B2_RB;
+    const int c_ix = tid % SW, c_rg = tid / SW;
+    const int a_gx = ex0 + 2 * qx;
+    const bool a_cols = a_gx + 1 >= 0 && a_gx < a.w && tid < B2Geom<EW>::A_THREADS;
+    const int sw_odd = (tid >> 2) & 1;
+    const float wA0 = sw_odd ? 0.f : 0.1f, wA1 = sw_odd ? 0.5f : 0.8f, wA2 = sw_odd ? 0.5f : 0.1f;
+    const float wB0 = sw_odd ? 0.1f : 0.f, wB1 = sw_odd ? 0.8f : 0.5f, wB2 = sw_odd ? 0.1f : 0.5f;
+    // staged fine pixel (video v, stage row r, staged column f)
+    auto fine_at = [&](int v, int r, int f) -> const float4 & { return f < 64 ? sm.fine_a[v][r][f] : sm.fine_b[v][r][f - 64]; };
+    // ---- R1: vertical 5-tap pass of the reduce for the coarse rows a0/2+1 .. a0/2+4 of the step whose fine rows
+    // [a0, a0+11) are in the stage (lpyr_dec.py:186-199).  (Running it one step ahead, in the barrier interval of
+    // phase C of the previous step, was tried: 25.4 instead of 23.9 ms at level 0.) ----
+    auto reduce_rows = [&](int a0) {
+        const int cyn = a0 / 2 + 1;  // a0 is even (negative in the prologue: exact division)
+        for (int t = tid; t < 2 * (CVVDP_BF_FW - 1); t += CVVDP_B2_THREADS) {
+            const int v = t / (CVVDP_BF_FW - 1), f = t - v * (CVVDP_BF_FW - 1);
+            const float4 *colp = f < 64 ? &sm.fine_a[v][0][f] : &sm.fine_b[v][0][f - 64];  // this column of the stage
+            const int pitch = f < 64 ? 64 : 4;
+            float4 x[CVVDP_BF_FR];
+#pragma unroll
+            for (int r = 0; r < CVVDP_BF_FR; ++r) x[r] = colp[r * pitch];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cy = cyn + i;
+                float4 s = K0 * x[2 * i];
+                s = fma4(K1, x[2 * i + 1], s);
+                s = fma4(K2, x[2 * i + 2], s);
+                s = fma4(K1, x[2 * i + 3], s);
+                s = fma4(K0, x[2 * i + 4], s);
+                if (cy == 0) {  // l.195: x~(-1) = x(0), x~(-2) = x(1); stage row of image row y is y - a0
+                    s = fma4(K1, fine_at(v, 0 - a0, f), s);
+                    s = fma4(K0, fine_at(v, min(1, a.h - 1) - a0, f), s);
+                }
+                if (cy == a.hc - 1) {  // l.196-199
+                    if (rows_odd) {
+                        s = fma4(K1, fine_at(v, a.h - 1 - a0, f), s);
+                        s = fma4(K0, fine_at(v, max(a.h - 2, 0) - a0, f), s);
+                    } else {
+                        s = fma4(K0, fine_at(v, a.h - 1 - a0, f), s);
+                    }
+                }
+                sm.vp[v][i][(f & 1) * CVVDP_BF_VP + (f >> 1)] = s;
+            }
+        }
+    };
+    int hslot0 = 0;  // hb ring slot of row a0 = (a0 - y_begin) mod 24, advanced per step
+
+    for (int a0 = y_begin - CVVDP_B2_RB; a0 - hal < ye; a0 += CVVDP_B2_RB) {
+        const bool have_a = a0 < a_end;             // fine rows of this step exist
+        const bool do_a = have_a && a0 >= y_begin;  // not the prologue
+        if (have_a) {
+            mbar_wait(&sm.bar, tma_phase);
+            tma_phase ^= 1u;
+        }
+        __syncthreads();  // the stage has landed; previous phase C is complete (mm / vp are free)
+        if (have_a) reduce_rows(a0);
+        __syncthreads();
+        if (have_a) {
+            const int cyn = a0 / 2 + 1;
+            // ---- R2: horizontal pass -> coarse ring (+ HBM for the pixels this CTA owns) (lpyr_dec.py:201-209) ----
+            for (int t = tid; t < 2 * 4 * CC; t += CVVDP_B2_THREADS) {
+                const int j = t % CC, vi = t / CC, v = vi >> 2, i = vi & 3;
+                const int cy = cyn + i, cx = cx0 + j;
+                const float4 *ev = &sm.vp[v][i][j], *od = &sm.vp[v][i][CVVDP_BF_VP + j];  // staged columns 2j+{0,2,4} / {1,3}
+                float4 s = K0 * ev[0];
+                s = fma4(K1, od[0], s);
+                s = fma4(K2, ev[1], s);
+                s = fma4(K1, od[1], s);
+                s = fma4(K0, ev[2], s);
+                auto vp_at = [&](int f) -> const float4 & { return sm.vp[v][i][(f & 1) * CVVDP_BF_VP + (f >> 1)]; };
+                if (cx == 0) {  // l.205
+                    s = fma4(K1, vp_at(0 - fx0), s);
+                    s = fma4(K0, vp_at(min(1, a.w - 1) - fx0), s);
+                }
+                if (cx == a.wc - 1) {  // l.206-209: the parity of the ROW count chooses the rule
+                    if (rows_odd) {
+                        s = fma4(K1, vp_at(a.w - 1 - fx0), s);
+                        s = fma4(K0, vp_at(max(a.w - 2, 0) - fx0), s);
+                    } else {
+                        s = fma4(K0, vp_at(a.w - 1 - fx0), s);
+                    }
+                }
+                sm.crs[v][(cy - cbase) & 7][j] = s;
+                if (j >= 4 && j < 4 + SW / 2 && cx < a.wc && cy >= own_cy0 && cy < own_cy1)
+                    crs_out[v * ncpix + (long long)cy * a.wc + cx] = s;
+            }
+        }
+        __syncthreads();  // coarse ring complete; vp (= mm) is free
+        // ---- phase A: one 2x2 quad per thread: expand, contrast, CSF -> mm, df ----
+        if (do_a) {
+            const int gy = a0 + 2 * qy;
+            if (gy < a_end && a_cols) {
+                float4 e[2][4];
+                // coarse rows a0/2-1+qy+{0,1,2}, columns cx0+qx+{0,1,2}, clamped to the coarse image (replicate padding)
+                int rs[3], cs[3];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) rs[r] = (min(max(a0 / 2 - 1 + qy + r, 0), a.hc - 1) - cbase) & 7;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) cs[c] = min(max(cx0 + qx + c, 0), a.wc - 1) - cx0;
+#pragma unroll
+                for (int v = 0; v < 2; ++v) {
+                    float4 ve[3], vo[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 c0 = sm.crs[v][rs[0]][cs[c]], c1 = sm.crs[v][rs[1]][cs[c]], c2 = sm.crs[v][rs[2]][cs[c]];
+                        ve[c] = fma4(0.1f, c2, fma4(0.8f, c1, 0.1f * c0));
+                        vo[c] = fma4(0.5f, c2, 0.5f * c1);
+                    }
+                    e[v][0] = fma4(wA2, ve[2], fma4(wA1, ve[1], wA0 * ve[0]));
+                    e[v][1] = fma4(wB2, ve[2], fma4(wB1, ve[1], wB0 * ve[0]));
+                    e[v][2] = fma4(wA2, vo[2], fma4(wA1, vo[1], wA0 * vo[0]));
+                    e[v][3] = fma4(wB2, vo[2], fma4(wB1, vo[1], wB0 * vo[0]));
+                }
+                float4 mm[4], df[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ry = 2 * qy + (k >> 1), rx = 2 * qx + ((k & 1) ^ sw_odd);
+                    band_pixel<false>(a, sm.lut, sm.fine_a[0][ry][rx + 4], sm.fine_a[1][ry][rx + 4], e[0][k], e[1][k], mm[k], df[k]);
+                }
+                const int ix = ex0 + 2 * qx - x0;
+                const bool in_strip = ix >= 0 && ix < SW;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int ry = 2 * qy + (k >> 1), cofs = (k & 1) ^ sw_odd, rx = 2 * qx + cofs;
+                    sm.mm[ry][rx] = mm[k];
+                    if (in_strip) sm.df[(a0 + ry) & (CVVDP_B2_DFR - 1)][ix + cofs] = df[k];
+                }
+            }
+        }
+        __syncthreads();
+        // ---- prefetch the next step's stage while phases B and C run ----
+        if (a0 + CVVDP_B2_RB < a_end) stage(a0 + CVVDP_B2_RB);
+        // ---- phase B: horizontal pass of the phase-uncertainty Gaussian for the new rows ----
+        if (do_a && tid < B2Geom<EW>::B_TASKS) {
+            const int gy = a0 + b_r, gxb = x0 + b_xg * 4;
+            if (gy < a_end && gxb < a.w) {
+                float4 win[2 * CVVDP_BHALO + 4];
+                if (x_edge) {
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                        int lx = reflect_idx(gxb + j - CVVDP_BHALO, a.w) - ex0;
+                        lx = min(max(lx, 0), EW - 1);
+                        win[j] = sm.mm[b_r][lx];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) win[j] = sm.mm[b_r][b_xg * 4 + j];
+                }
+                float4 *dst = &sm.hb[hslot0 + b_r][b_xg * 4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    float4 s = f4(0.f);
+#pragma unroll
+                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) s = fma4(a.kern[k], win[o + k], s);
+                    dst[o] = s;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase C: vertical pass, masking, clamp, pooling for rows [a0-6, a0+2) ----
+        if (a0 >= y_begin && tid < B2Geom<EW>::C_TASKS) {
+            const int gx = x0 + c_ix;
+            const int cyb = a0 - hal + c_rg * 4;
+            if (gx < a.w && cyb + 3 >= ys && cyb < ye) {
+                float4 win[2 * CVVDP_BHALO + 4];
+                const bool y_edge = (cyb - CVVDP_BHALO < 0) || (cyb + 3 + CVVDP_BHALO >= a.h);
+                if (y_edge) {
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                        int yy = reflect_idx(cyb + j - CVVDP_BHALO, a.h);
+                        yy = min(max(yy, y_begin), a.h - 1);
+                        win[j] = sm.hb[(yy - y_begin) % CVVDP_BF_HBR][c_ix];
+                    }
+                } else {  // row cyb-6 = a0-12+4 c_rg sits 12+4 c_rg slots after the slot of row a0 (mod 24)
+                    int s0 = hslot0 + 12 + 4 * c_rg;
+                    s0 -= s0 >= CVVDP_BF_HBR ? CVVDP_BF_HBR : 0;
+#pragma unroll
+                    for (int j = 0; j < 2 * CVVDP_BHALO + 4; ++j) {
+                        int sl = s0 + j;
+                        sl -= sl >= CVVDP_BF_HBR ? CVVDP_BF_HBR : 0;
+                        win[j] = sm.hb[sl][c_ix];
+                    }
+                }
+                float4 D[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int gy = cyb + o;
+                    float4 m = f4(0.f);
+#pragma unroll
+                    for (int k = 0; k < 2 * CVVDP_BHALO + 1; ++k) m = fma4(a.kern[k], win[o + k], m);
+                    D[o] = band_mask(a, m, sm.df[gy & (CVVDP_B2_DFR - 1)][c_ix], eps_q, eps_p);
+                }
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    const int gy = cyb + o;
+                    const bool live = gy >= ys && gy < ye;
+                    float4 t;
+                    if (BETA2) {
+                        const float e2 = 2.f * a.eps;
+                        t = make_float4(D[o].x * (D[o].x + e2), D[o].y * (D[o].y + e2), D[o].z * (D[o].z + e2), D[o].w * (D[o].w + e2));
+                    } else {
+                        t = make_float4(f_pow(D[o].x + a.eps, a.beta) - eps_b, f_pow(D[o].y + a.eps, a.beta) - eps_b,
+                                        f_pow(D[o].z + a.eps, a.beta) - eps_b, f_pow(D[o].w + a.eps, a.beta) - eps_b);
+                    }
+                    acc.x += live ? t.x : 0.f;
+                    acc.y += live ? t.y : 0.f;
+                    acc.z += live ? t.z : 0.f;
+                    acc.w += live ? t.w : 0.f;
+                    if (HM && live) {
+                        const float eb = f_pow(a.eps, a.hm_beta);
+                        float s = (f_pow(D[o].x * a.hm_w[0] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].y * a.hm_w[1] + a.eps, a.hm_beta) - eb) +
+                                  (f_pow(D[o].z * a.hm_w[2] + a.eps, a.hm_beta) - eb) + (f_pow(D[o].w * a.hm_w[3] + a.eps, a.hm_beta) - eb);
+                        const float ib = 1.f / a.hm_beta;
+                        a.hm[(long long)pair * npix + (long long)gy * a.w + gx] = (f_pow(s + a.eps, ib) - f_pow(a.eps, ib)) * a.hm_scale;
+                    }
+                }
+            }
+        }
+        if (a0 >= y_begin) {
+            hslot0 += CVVDP_B2_RB;
+            hslot0 -= hslot0 >= CVVDP_BF_HBR ? CVVDP_BF_HBR : 0;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
