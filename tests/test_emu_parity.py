@@ -405,3 +405,22 @@ def test_prefiltered_video_source(mock_device):
     jod, stats = m.predict_video_source(_prefiltered_source(z, meta["fps"]))
     gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], "prefiltered")
     assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+
+
+@pytest.mark.parametrize("shape,fps,heatmap", [((1, 150, 360), 0, "raw"), ((5, 64, 236), 30, None)])
+def test_unfused_reduce_and_band_kernels(shape, fps, heatmap, mock_device, monkeypatch):
+    """CVVDP_B200_UNFUSED=1: separate reduce launches + k_band2 (the pair the fused kernel replaces; still what tiny
+    levels, the feature mode and maps without TMA use) against the oracle and against the fused default."""
+    F, H, W = shape
+    tst, ref = synth.make_pair_u8(12, F, H, W)
+    _, fused = cv.cvvdp(display_name="standard_fhd", heatmap=heatmap).predict(tst, ref, frames_per_second=fps)
+    monkeypatch.setenv("CVVDP_B200_UNFUSED", "1")
+    m = cv.cvvdp(display_name="standard_fhd", heatmap=heatmap)
+    m._ctx.profile_enable(True)
+    jod, stats = m.predict(tst, ref, frames_per_second=fps)
+    assert sum(1 for p in m._ctx.profile_read() if p["kind"] == "reduce") == stats["Q_per_ch"].shape[3] - 1
+    jod_o, stats_o = O.predict(tst, ref, "BCFHW", fps, "standard_fhd", heatmap=heatmap)
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], str(shape))
+    gu.assert_q_close(stats["Q_per_ch"], fused["Q_per_ch"], "unfused vs fused")
+    if heatmap:
+        assert np.max(np.abs(stats["heatmap"].float().numpy() - stats_o["heatmap"].astype(np.float32))) <= gu.HEATMAP_ATOL

@@ -314,3 +314,12 @@ def test_prefiltered_video_source_on_hardware():
     jod, stats = m.predict_video_source(_prefiltered_source(z, meta["fps"]))
     gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], "prefiltered")
     assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+
+
+def test_unfused_kernels_on_hardware(monkeypatch):
+    """CVVDP_B200_UNFUSED=1 (separate reduce launches + k_band2) against the fused default at 1080p."""
+    tst, ref = synth.make_pair_u8(99, 6, 1080, 1920)
+    _, fused = cv.cvvdp(display_name="standard_fhd", device=DEV).predict(_t(tst), _t(ref), frames_per_second=30)
+    monkeypatch.setenv("CVVDP_B200_UNFUSED", "1")
+    _, unf = cv.cvvdp(display_name="standard_fhd", device=DEV).predict(_t(tst), _t(ref), frames_per_second=30)
+    gu.assert_q_close(unf["Q_per_ch"], fused["Q_per_ch"], "unfused vs fused")
