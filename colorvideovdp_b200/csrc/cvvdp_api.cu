@@ -1077,9 +1077,11 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
     const double gain[4] = {1.0, 1.45, 1.0, 1.0};
     // L2 promotion of the tensor maps: 64 / 128 / 256 bytes and none were timed on one box (round 2): within 1.5 %
     const int reduce_promo = 128, band_promo = 128;
-    // The band kernel of a level computes the next pyramid level itself (k_band2f: no reduce launch, the level is read
-    // from HBM once); CVVDP_B200_UNFUSED=1 keeps the separate reduce + k_band2 pair for A/B runs and tests.
-    const bool use_fused = getenv("CVVDP_B200_UNFUSED") == nullptr;
+    // CVVDP_B200_FUSED_REDUCE=1: the band kernel of a level computes the next pyramid level itself (k_band2f: no reduce
+    // launch, the level is read from HBM once -- the literal "one kernel per level" of the north star).  Parity-green
+    // on hardware, but between 2 % faster and 5 % slower than the separate reduce + k_band2 pair depending on the box
+    // (profiles/r02_ab_fused_*.txt), so the pair stays the default.
+    const bool use_fused = getenv("CVVDP_B200_FUSED_REDUCE") != nullptr;
     for (int i = 0; i < L; ++i) {
         LevelBuf &lv = ctx->lv[i];
         char *base = (char *)ctx->arena;

@@ -1336,40 +1336,52 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2f(const __grid_con
     const float wB0 = sw_odd ? 0.1f : 0.f, wB1 = sw_odd ? 0.8f : 0.5f, wB2 = sw_odd ? 0.1f : 0.5f;
     // staged fine pixel (video v, stage row r, staged column f)
     auto fine_at = [&](int v, int r, int f) -> const float4 & { return f < 64 ? sm.fine_a[v][r][f] : sm.fine_b[v][r][f - 64]; };
-    // ---- R1: vertical 5-tap pass of the reduce for the coarse rows a0/2+1 .. a0/2+4 of the step whose fine rows
-    // [a0, a0+11) are in the stage (lpyr_dec.py:186-199).  (Running it one step ahead, in the barrier interval of
+    // ---- reduce, vertical 5-tap pass (lpyr_dec.py:186-199) for the coarse rows a0/2+1 .. a0/2+4 of the step whose
+    // fine rows [a0, a0+11) are in the stage: one (video, column) task per thread, 2 x 64 columns of box A, then the
+    // 2 x 3 columns of box B on six threads.  EDGE: the step holds coarse row 0 or hc-1 (top / bottom fix-ups);
+    // everywhere else the pass is straight-line code.  (Running it one step ahead, in the barrier interval of
     // phase C of the previous step, was tried: 25.4 instead of 23.9 ms at level 0.) ----
-    auto reduce_rows = [&](int a0) {
-        const int cyn = a0 / 2 + 1;  // a0 is even (negative in the prologue: exact division)
-        for (int t = tid; t < 2 * (CVVDP_BF_FW - 1); t += CVVDP_B2_THREADS) {
-            const int v = t / (CVVDP_BF_FW - 1), f = t - v * (CVVDP_BF_FW - 1);
-            const float4 *colp = f < 64 ? &sm.fine_a[v][0][f] : &sm.fine_b[v][0][f - 64];  // this column of the stage
-            const int pitch = f < 64 ? 64 : 4;
-            float4 x[CVVDP_BF_FR];
+    auto reduce_column = [&](const float4 *colp, const int pitch, int v, int f, int a0, int cyn, bool edge) {
+        float4 x[CVVDP_BF_FR];
 #pragma unroll
-            for (int r = 0; r < CVVDP_BF_FR; ++r) x[r] = colp[r * pitch];
+        for (int r = 0; r < CVVDP_BF_FR; ++r) x[r] = colp[r * pitch];
+        float4 *dst = &sm.vp[v][0][(f & 1) * CVVDP_BF_VP + (f >> 1)];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < 4; ++i) {
+            float4 s = K0 * x[2 * i];
+            s = fma4(K1, x[2 * i + 1], s);
+            s = fma4(K2, x[2 * i + 2], s);
+            s = fma4(K1, x[2 * i + 3], s);
+            s = fma4(K0, x[2 * i + 4], s);
+            if (edge) {
                 const int cy = cyn + i;
-                float4 s = K0 * x[2 * i];
-                s = fma4(K1, x[2 * i + 1], s);
-                s = fma4(K2, x[2 * i + 2], s);
-                s = fma4(K1, x[2 * i + 3], s);
-                s = fma4(K0, x[2 * i + 4], s);
                 if (cy == 0) {  // l.195: x~(-1) = x(0), x~(-2) = x(1); stage row of image row y is y - a0
-                    s = fma4(K1, fine_at(v, 0 - a0, f), s);
-                    s = fma4(K0, fine_at(v, min(1, a.h - 1) - a0, f), s);
+                    s = fma4(K1, colp[(0 - a0) * pitch], s);
+                    s = fma4(K0, colp[(min(1, a.h - 1) - a0) * pitch], s);
                 }
                 if (cy == a.hc - 1) {  // l.196-199
                     if (rows_odd) {
-                        s = fma4(K1, fine_at(v, a.h - 1 - a0, f), s);
-                        s = fma4(K0, fine_at(v, max(a.h - 2, 0) - a0, f), s);
+                        s = fma4(K1, colp[(a.h - 1 - a0) * pitch], s);
+                        s = fma4(K0, colp[(max(a.h - 2, 0) - a0) * pitch], s);
                     } else {
-                        s = fma4(K0, fine_at(v, a.h - 1 - a0, f), s);
+                        s = fma4(K0, colp[(a.h - 1 - a0) * pitch], s);
                     }
                 }
-                sm.vp[v][i][(f & 1) * CVVDP_BF_VP + (f >> 1)] = s;
             }
+            dst[i * 2 * CVVDP_BF_VP] = s;
+        }
+    };
+    auto reduce_rows = [&](int a0) {
+        const int cyn = a0 / 2 + 1;  // a0 is even (negative in the prologue: exact division)
+        const bool edge = cyn <= 0 || cyn + 3 >= a.hc - 1;  // uniform
+        {
+            const int v = tid >> 6, f = tid & 63;
+            if (edge) reduce_column(&sm.fine_a[v][0][f], 64, v, f, a0, cyn, true);
+            else reduce_column(&sm.fine_a[v][0][f], 64, v, f, a0, cyn, false);
+        }
+        if (tid < 6) {  // staged columns 64..66
+            const int v = tid >= 3 ? 1 : 0, f = 64 + tid - 3 * v;
+            reduce_column(&sm.fine_b[v][0][f - 64], 4, v, f, a0, cyn, true);
         }
     };
     int hslot0 = 0;  // hb ring slot of row a0 = (a0 - y_begin) mod 24, advanced per step
@@ -1387,31 +1399,40 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2f(const __grid_con
         if (have_a) {
             const int cyn = a0 / 2 + 1;
             // ---- R2: horizontal pass -> coarse ring (+ HBM for the pixels this CTA owns) (lpyr_dec.py:201-209) ----
-            for (int t = tid; t < 2 * 4 * CC; t += CVVDP_B2_THREADS) {
-                const int j = t % CC, vi = t / CC, v = vi >> 2, i = vi & 3;
-                const int cy = cyn + i, cx = cx0 + j;
+            // 2 videos x 4 rows x 32 columns = two tasks per thread; EDGE (uniform): the ring holds coarse column 0 or wc-1
+            const bool edge_x = cx0 <= 0 || cx0 + CC - 1 >= a.wc - 1;
+            const int j = tid & (CC - 1);
+            const int j_own = min(4 + SW / 2, a.wc - cx0);  // owned ring columns: [4, j_own)
+            const bool own_j = j >= 4 && j < j_own;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int vi = (tid >> 5) + 4 * pass, v = vi >> 2, i = vi & 3;
+                const int cy = cyn + i;
                 const float4 *ev = &sm.vp[v][i][j], *od = &sm.vp[v][i][CVVDP_BF_VP + j];  // staged columns 2j+{0,2,4} / {1,3}
                 float4 s = K0 * ev[0];
                 s = fma4(K1, od[0], s);
                 s = fma4(K2, ev[1], s);
                 s = fma4(K1, od[1], s);
                 s = fma4(K0, ev[2], s);
-                auto vp_at = [&](int f) -> const float4 & { return sm.vp[v][i][(f & 1) * CVVDP_BF_VP + (f >> 1)]; };
-                if (cx == 0) {  // l.205
-                    s = fma4(K1, vp_at(0 - fx0), s);
-                    s = fma4(K0, vp_at(min(1, a.w - 1) - fx0), s);
-                }
-                if (cx == a.wc - 1) {  // l.206-209: the parity of the ROW count chooses the rule
-                    if (rows_odd) {
-                        s = fma4(K1, vp_at(a.w - 1 - fx0), s);
-                        s = fma4(K0, vp_at(max(a.w - 2, 0) - fx0), s);
-                    } else {
-                        s = fma4(K0, vp_at(a.w - 1 - fx0), s);
+                if (edge_x) {
+                    const int cx = cx0 + j;
+                    auto vp_at = [&](int f) -> const float4 & { return sm.vp[v][i][(f & 1) * CVVDP_BF_VP + (f >> 1)]; };
+                    if (cx == 0) {  // l.205
+                        s = fma4(K1, vp_at(0 - fx0), s);
+                        s = fma4(K0, vp_at(min(1, a.w - 1) - fx0), s);
+                    }
+                    if (cx == a.wc - 1) {  // l.206-209: the parity of the ROW count chooses the rule
+                        if (rows_odd) {
+                            s = fma4(K1, vp_at(a.w - 1 - fx0), s);
+                            s = fma4(K0, vp_at(max(a.w - 2, 0) - fx0), s);
+                        } else {
+                            s = fma4(K0, vp_at(a.w - 1 - fx0), s);
+                        }
                     }
                 }
                 sm.crs[v][(cy - cbase) & 7][j] = s;
-                if (j >= 4 && j < 4 + SW / 2 && cx < a.wc && cy >= own_cy0 && cy < own_cy1)
-                    crs_out[v * ncpix + (long long)cy * a.wc + cx] = s;
+                if (own_j && cy >= own_cy0 && cy < own_cy1)
+                    crs_out[(unsigned)(v * (int)ncpix + cy * a.wc + cx0 + j)] = s;
             }
         }
         __syncthreads();  // coarse ring complete; vp (= mm) is free
@@ -1422,10 +1443,17 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2f(const __grid_con
                 float4 e[2][4];
                 // coarse rows a0/2-1+qy+{0,1,2}, columns cx0+qx+{0,1,2}, clamped to the coarse image (replicate padding)
                 int rs[3], cs[3];
+                if (a0 / 2 - 1 < 0 || a0 / 2 + 4 > a.hc - 1 || cx0 < 0 || cx0 + CC - 1 > a.wc - 1) {  // uniform: at a border
 #pragma unroll
-                for (int r = 0; r < 3; ++r) rs[r] = (min(max(a0 / 2 - 1 + qy + r, 0), a.hc - 1) - cbase) & 7;
+                    for (int r = 0; r < 3; ++r) rs[r] = (min(max(a0 / 2 - 1 + qy + r, 0), a.hc - 1) - cbase) & 7;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) cs[c] = min(max(cx0 + qx + c, 0), a.wc - 1) - cx0;
+                    for (int c = 0; c < 3; ++c) cs[c] = min(max(cx0 + qx + c, 0), a.wc - 1) - cx0;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) rs[r] = (a0 / 2 - 1 + qy + r - cbase) & 7;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) cs[c] = qx + c;
+                }
 #pragma unroll
                 for (int v = 0; v < 2; ++v) {
                     float4 ve[3], vo[3];

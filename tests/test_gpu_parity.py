@@ -316,10 +316,15 @@ def test_prefiltered_video_source_on_hardware():
     assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
 
 
-def test_unfused_kernels_on_hardware(monkeypatch):
-    """CVVDP_B200_UNFUSED=1 (separate reduce launches + k_band2) against the fused default at 1080p."""
+def test_fused_band_and_reduce_kernel_on_hardware(monkeypatch):
+    """CVVDP_B200_FUSED_REDUCE=1 (band kernel computes the next level itself) against the default pair at 1080p and
+    against the oracle on an odd-sized clip."""
     tst, ref = synth.make_pair_u8(99, 6, 1080, 1920)
+    _, plain = cv.cvvdp(display_name="standard_fhd", device=DEV).predict(_t(tst), _t(ref), frames_per_second=30)
+    monkeypatch.setenv("CVVDP_B200_FUSED_REDUCE", "1")
     _, fused = cv.cvvdp(display_name="standard_fhd", device=DEV).predict(_t(tst), _t(ref), frames_per_second=30)
-    monkeypatch.setenv("CVVDP_B200_UNFUSED", "1")
-    _, unf = cv.cvvdp(display_name="standard_fhd", device=DEV).predict(_t(tst), _t(ref), frames_per_second=30)
-    gu.assert_q_close(unf["Q_per_ch"], fused["Q_per_ch"], "unfused vs fused")
+    gu.assert_q_close(fused["Q_per_ch"], plain["Q_per_ch"], "fused vs plain")
+    t2, r2 = synth.make_pair_u8(32, 12, 135, 240)
+    jod, stats = cv.cvvdp(display_name="standard_fhd", device=DEV).predict(_t(t2), _t(r2), frames_per_second=30)
+    jod_o, stats_o = O.predict(t2, r2, "BCFHW", 30, "standard_fhd")
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], "fused, odd size")

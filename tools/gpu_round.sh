@@ -11,7 +11,7 @@ fi
 if [ "$1" = "ncu" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-extras > gpurun_out/launches_bench.log 2>&1
-for k in k_band2f k_temporal_2s; do
+for k in k_band2 k_temporal_2s k_reduce2; do
   timeout 400 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o /tmp/prof_$k \
       python bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline --no-extras > gpurun_out/ncu_$k.txt 2>&1
   ncu -i /tmp/prof_$k.ncu-rep --page raw --csv > gpurun_out/raw_$k.csv 2>/dev/null
