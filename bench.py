@@ -325,6 +325,39 @@ def time_steps(fn, steps, warmup, dev):
 # ---------------------------------------------------------------------------------------------------
 # extra lines (rank 0, N = 1): the other BASELINE configurations and input types
 # ---------------------------------------------------------------------------------------------------
+def yuv_file_run(cv, dev, args, H, W, F, fps):
+    import shutil
+    import tempfile
+    tst, ref = make_clip(3, 0, F, H, W, "u8", dev)
+    root = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > 8 * F * H * W else None
+    td = tempfile.mkdtemp(prefix="cvvdp_b200_bench_", dir=root)
+    try:
+        props = {"width": W, "height": H, "fps": fps, "bit_depth": 8, "color_space": "709", "chroma_ss": "420"}
+        names = [os.path.join(td, cv.create_yuv_fname(n, props)) for n in ("test", "ref")]
+        for fn, clip in zip(names, (tst, ref)):
+            with open(fn, "wb") as fh:
+                for f in range(F):  # BT.709 forward matrix, limited range, 2x2 chroma average
+                    rgb = clip[0, :, f].float() / 255.0
+                    Y = 0.2126 * rgb[0] + 0.7152 * rgb[1] + 0.0722 * rgb[2]
+                    cb, cr = (rgb[2] - Y) / 1.8556, (rgb[0] - Y) / 1.5748
+                    planes = [(Y * 219 + 16).round().clamp(0, 255)]
+                    planes += [torch.nn.functional.avg_pool2d((c * 224 + 128)[None, None], 2)[0, 0].round().clamp(0, 255) for c in (cb, cr)]
+                    fh.write(torch.cat([p.reshape(-1) for p in planes]).to(torch.uint8).cpu().numpy().tobytes())
+        del tst, ref
+        m = cv.cvvdp(display_name=DISPLAY, device=dev)
+
+        def step():
+            vs = cv.video_source_yuv_file(names[0], names[1], display_photometry=DISPLAY)
+            return float(m.predict_video_source(vs)[0])
+
+        ms, jod = time_steps(step, 2, 1, dev)
+        return {"workload": f"{W}x{H}x{F}f @{fps:g}fps, {DISPLAY}, yuv420p 8-bit .yuv pair in {'/dev/shm' if root else 'tmp'}",
+                "e2e": {"value": round(F * H * W / 1e6 / (ms / 1e3), 2), "unit": "Mpix/s", "ms_per_step": round(ms, 3),
+                        "h2d_bytes_per_step": int(2 * F * H * W * 3 // 2)}, "jod": round(jod, 5)}
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+
+
 def extra_runs(args, dev, peak, ref_sample):
     import colorvideovdp_b200 as cv
     out = {}
@@ -389,6 +422,13 @@ def extra_runs(args, dev, peak, ref_sample):
                                              "ms_per_step": round(ms_p, 3), "jod": round(jod_p, 5),
                                              "h2d_bytes_per_step": int(tn.nbytes + rn.nbytes)}
     del m, tn, rn
+
+    # raw planar YUV files: predict_video_source(video_source_yuv_file) on an 8-bit 4:2:0 pair of the
+    # headline shape; the file mapping (page cache) is read by the library's upload threads, 1.5 bytes per pixel
+    try:
+        out["config3_yuv420p_files"] = yuv_file_run(cv, dev, args, H, W, F, fps)
+    except Exception as e:  # informational only
+        out["config3_yuv420p_files"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
     # the reference itself on this GPU (informational; tests/test_gpu_reference.py holds the parity checks)
     if ref_sample is not None:

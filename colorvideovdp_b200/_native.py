@@ -82,6 +82,8 @@ SYMBOLS = {
                                       C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_frontend_yuv": (C.c_int, [C.c_void_p, C.POINTER(Clip), C.POINTER(Yuv), C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cvvdp_b200_resize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p]),
     "cvvdp_b200_launch_count": (C.c_int64, [C.c_void_p]),
     "cvvdp_b200_band_strip_width": (C.c_int, [C.c_void_p, C.c_int]),
     "cvvdp_b200_input_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
@@ -100,7 +102,8 @@ class KernelStat(C.Structure):
     _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("launches", C.c_int32), ("total_ms", C.c_float),
                 ("algo_bytes", C.c_double)]
 
-ABI_VERSION = 4
+ABI_VERSION = 5
+RESIZE_MODES = {"nearest": 0, "bilinear": 1, "bicubic": 2, "area": 3}  # run_cvvdp.py:100
 
 
 class InputReport(C.Structure):
@@ -193,6 +196,13 @@ class Context:
     def frontend_yuv(self, src: Clip, yuv: Yuv, B, H, W, dtype, frame, colorspace, dst_ptr, stream):
         self._check(self._lib.cvvdp_b200_frontend_yuv(self._h, C.byref(src), C.byref(yuv), B, H, W, dtype, frame,
                                                       colorspace, dst_ptr, stream), "frontend_yuv")
+
+    def resize(self, src_ptr, dst_ptr, channels, H, W, out_h, out_w, mode, clip01, stream):
+        """`mode`: a key of RESIZE_MODES (the reference's --full-screen-resize choices)."""
+        if mode not in RESIZE_MODES:
+            raise NativeError(f"resize: unknown interpolation '{mode}'")
+        self._check(self._lib.cvvdp_b200_resize(self._h, src_ptr, dst_ptr, channels, H, W, out_h, out_w,
+                                                RESIZE_MODES[mode], 1 if clip01 else 0, stream), "resize")
 
     def launch_count(self):
         return int(self._lib.cvvdp_b200_launch_count(self._h))

@@ -1549,6 +1549,34 @@ int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, con
     return CVVDP_OK;
 }
 
+int cvvdp_b200_resize(cvvdp_b200_ctx *ctx, const float *src_dev, float *dst_dev, int channels, int height, int width,
+                      int out_height, int out_width, int mode, int clip01, void *stream) {
+    if (!ctx || !src_dev || !dst_dev) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
+    if (channels < 1 || height < 1 || width < 1 || out_height < 1 || out_width < 1)
+        return fail(ctx, CVVDP_ERR_INVALID, "resize: empty plane %dx%dx%d -> %dx%d", channels, height, width, out_height, out_width);
+    if (mode < CVVDP_RESIZE_NEAREST || mode > CVVDP_RESIZE_AREA) return fail(ctx, CVVDP_ERR_INVALID, "unknown resize mode %d", mode);
+    DeviceGuard dev_guard(ctx->device);
+    CU_CHECK(ctx, dev_guard.err);
+    ResizeArgs ra;
+    ra.src = src_dev;
+    ra.dst = dst_dev;
+    ra.C = channels;
+    ra.H = height;
+    ra.W = width;
+    ra.OH = out_height;
+    ra.OW = out_width;
+    ra.mode = mode;
+    ra.clip01 = clip01;
+    const long long onp = (long long)out_height * out_width;
+    auto kfn = k_resize;
+    {
+        LaunchScope ls(ctx, (cudaStream_t)stream, CVVDP_K_FRONTEND, 0, 4.0 * channels * ((double)height * width + (double)onp));
+        CVVDP_LAUNCH(kfn, dim3((unsigned)((onp + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, ra);
+    }
+    CU_CHECK(ctx, cudaGetLastError());
+    return CVVDP_OK;
+}
+
 int cvvdp_b200_input_stats(cvvdp_b200_ctx *ctx, cvvdp_b200_input_report *out, int reset) {
     if (!ctx || !out) return fail(ctx, CVVDP_ERR_INVALID, "null argument");
     DeviceGuard dev_guard(ctx->device);

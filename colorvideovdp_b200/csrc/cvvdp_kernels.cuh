@@ -231,6 +231,75 @@ __global__ void __launch_bounds__(256) k_frontend(const FrontendArgs a) {
 }
 
 // =================================================================================================
+// Full-screen resize of a decoded frame (run_cvvdp.py:100 `--full-screen-resize`; video_source_yuv.py:257-260,333-336,
+// video_source_file.py:280-285): torch.nn.functional.interpolate(size=..., mode=...) without align_corners or
+// antialiasing, followed by clip(0, 1).  The interpolation rules are torch's (third-party to the reference):
+//   nearest   src = min(floor(dst * in/out), in-1)
+//   bilinear  src = max((dst + 0.5) * in/out - 0.5, 0); the second tap stays on the last sample at the edge
+//   bicubic   src = (dst + 0.5) * in/out - 0.5, Keys kernel with A = -0.75, tap indices clamped to the plane
+//   area      adaptive average pool: mean over [floor(i in/out), ceil((i+1) in/out))
+// One thread per output pixel, all channels; the source planes are small enough to be served from L2.
+// =================================================================================================
+struct ResizeArgs {
+    const float *src;  // [C][H][W]
+    float *dst;        // [C][OH][OW]
+    int C, H, W, OH, OW, mode, clip01;
+};
+__device__ __forceinline__ float resize_cubic1(float x) { return ((1.25f * x - 2.25f) * x) * x + 1.f; }            // |x| <= 1, A=-0.75
+__device__ __forceinline__ float resize_cubic2(float x) { return ((-0.75f * x + 3.75f) * x - 6.f) * x + 3.f; }     // 1 < |x| < 2
+__device__ __forceinline__ void resize_cubic_taps(float t, float (&c)[4]) {
+    c[0] = resize_cubic2(t + 1.f);
+    c[1] = resize_cubic1(t);
+    c[2] = resize_cubic1(1.f - t);
+    c[3] = resize_cubic2((1.f - t) + 1.f);
+}
+__global__ void __launch_bounds__(256) k_resize(const ResizeArgs a) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long onp = (long long)a.OH * a.OW, inp = (long long)a.H * a.W;
+    if (p >= onp) return;
+    const int oy = (int)(p / a.OW), ox = (int)(p - (long long)oy * a.OW);
+    const float sy = (float)a.H / (float)a.OH, sx = (float)a.W / (float)a.OW;
+    for (int c = 0; c < a.C; ++c) {
+        const float *s = a.src + c * inp;
+        float v;
+        if (a.mode == CVVDP_RESIZE_NEAREST) {
+            const int y = min((int)floorf(oy * sy), a.H - 1), x = min((int)floorf(ox * sx), a.W - 1);
+            v = s[(long long)y * a.W + x];
+        } else if (a.mode == CVVDP_RESIZE_BILINEAR) {
+            const float ry = fmaxf(sy * (oy + 0.5f) - 0.5f, 0.f), rx = fmaxf(sx * (ox + 0.5f) - 0.5f, 0.f);
+            const int y0 = min((int)ry, a.H - 1), x0 = min((int)rx, a.W - 1);
+            const int y1 = y0 + (y0 < a.H - 1 ? 1 : 0), x1 = x0 + (x0 < a.W - 1 ? 1 : 0);
+            const float ly = ry - y0, lx = rx - x0;
+            const float top = (1.f - lx) * s[(long long)y0 * a.W + x0] + lx * s[(long long)y0 * a.W + x1];
+            const float bot = (1.f - lx) * s[(long long)y1 * a.W + x0] + lx * s[(long long)y1 * a.W + x1];
+            v = (1.f - ly) * top + ly * bot;
+        } else if (a.mode == CVVDP_RESIZE_BICUBIC) {
+            const float ry = sy * (oy + 0.5f) - 0.5f, rx = sx * (ox + 0.5f) - 0.5f;
+            const float fy = floorf(ry), fx = floorf(rx);
+            float cy[4], cx[4];
+            resize_cubic_taps(ry - fy, cy);
+            resize_cubic_taps(rx - fx, cx);
+            v = 0.f;
+            for (int i = 0; i < 4; ++i) {
+                const int y = max(min((int)fy - 1 + i, a.H - 1), 0);
+                float r = 0.f;
+                for (int j = 0; j < 4; ++j) r += s[(long long)y * a.W + max(min((int)fx - 1 + j, a.W - 1), 0)] * cx[j];
+                v += r * cy[i];
+            }
+        } else {  // area
+            const int y0 = (int)(((long long)oy * a.H) / a.OH), y1 = (int)((((long long)oy + 1) * a.H + a.OH - 1) / a.OH);
+            const int x0 = (int)(((long long)ox * a.W) / a.OW), x1 = (int)((((long long)ox + 1) * a.W + a.OW - 1) / a.OW);
+            float sum = 0.f;
+            for (int y = y0; y < y1; ++y)
+                for (int x = x0; x < x1; ++x) sum += s[(long long)y * a.W + x];
+            v = sum / (float)((y1 - y0) * (x1 - x0));
+        }
+        if (a.clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+        a.dst[c * onp + p] = v;
+    }
+}
+
+// =================================================================================================
 // Temporal stage: front end fused with the causal FIR  (cvvdp_metric.py:453-561)
 // Every input frame is read and EOTF-ed exactly once per block (+ fl-1 history frames at the start of
 // the block).  Two kernels; the host picks (cvvdp_api.cu, run_block):

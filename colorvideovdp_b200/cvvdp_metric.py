@@ -265,37 +265,51 @@ class cvvdp(vq_metric):
         if fast:
             return self._run_arrays(vid_source, B, H, W, F, fps, f0, f1)
         from .video_source_yuv import video_source_yuv_file
-        if type(vid_source) is video_source_yuv_file and type(vid_source.dm_photometry) is vvdp_display_photo_eotf:
-            tr, rr = vid_source.test_vidr, vid_source.reference_vidr
-            same = all(getattr(tr, k) == getattr(rr, k) for k in ("width", "height", "chroma_ss", "bit_depth", "color_space"))
-            if same and F <= min(tr.frames, rr.frames) - vid_source.offset:
-                return self._run_yuv(vid_source, H, W, F, fps, f0, f1)
+        from .video_source_file import video_source_video_file
+        if type(vid_source) in (video_source_yuv_file, video_source_video_file) and \
+                type(vid_source.dm_photometry) is vvdp_display_photo_eotf:
+            readers = vid_source.yuv_readers()
+            if readers is not None:
+                return self._run_yuv(vid_source, readers, H, W, F, fps, f0, f1)
         return self._run_plugin(vid_source, B, H, W, F, fps, f0, f1)
 
-    def _run_yuv(self, vs, H, W, F, fps, f0, f1):
-        """Raw planar YUV files: the memory-mapped frames go straight into the fused temporal kernel, which
-        unpacks, upsamples the chroma and applies the YCbCr matrix on the fly (video_source_yuv.py:146-233)."""
-        tr, rr = vs.test_vidr, vs.reference_vidr
+    yuv_chunk_bytes = 1 << 30  # host window (test + reference) handed to one process_host call of the YUV path
+
+    def _run_yuv(self, vs, readers, H, W, F, fps, f0, f1):
+        """Raw planar YUV frames (a memory-mapped .yuv file or an ffmpeg pipe) go straight into the fused temporal
+        kernel, which unpacks, upsamples the chroma and applies the YCbCr matrix on the fly
+        (video_source_yuv.py:146-233, video_source_file.py:261-324).  The clip is walked in windows of whole plan
+        blocks, in increasing frame order, so that a pipe is read once and host memory stays bounded."""
+        tr, rr, off = readers
         info = self._plan(1, H, W, F, fps, 3, tr.native_dtype(), vs.dm_photometry, tr.native_yuv())
         fl = info.filter_len
-        wlo, whi = self._needed_frames(f0, f1, fl, F)
-        tt = tr.frames_tensor(vs.offset + wlo, whi - wlo)
-        rt = rr.frames_tensor(vs.offset + wlo, whi - wlo)
-        if self.device.type == "cuda":
-            tt, rt = tt.pin_memory(), rt.pin_memory()
-
-        def clip_of(t, reader):
-            c = N.Clip()
-            c.data = t.data_ptr()
-            c.stride[0], c.stride[2] = 0, reader.frame_pixels
-            c.frame0, c.n_frames = wlo, whi - wlo
-            return c
-
+        nb = max(1, info.block_frames)
+        per = max(1, int(self.yuv_chunk_bytes // (2 * tr.frame_bytes * nb))) * nb
+        per = max(per, -(-fl // nb) * nb)
         pin = self.device.type == "cuda"
         Qh = torch.zeros((1, info.n_channels, F, info.n_bands), dtype=torch.float32, pin_memory=pin)
-        hmh = torch.zeros((1, self._hm_channels(), F, H, W), dtype=torch.float16, pin_memory=pin) if self.do_heatmap else None
-        self._ctx.process_host(clip_of(tt, tr), clip_of(rt, rr), f0, f1, Qh.data_ptr(),
-                               hmh.data_ptr() if hmh is not None else None)
+        hmh = None
+        if self.do_heatmap:
+            make = torch.empty if (f0 == 0 and f1 == F) else torch.zeros
+            hmh = make((1, self._hm_channels(), F, H, W), dtype=torch.float16, pin_memory=pin)
+        cur = f0
+        while cur < f1:
+            end = min(cur + per, f1)
+            wlo, whi = self._needed_frames(cur, end, fl, F)
+            windows = [r.frames_window(off + wlo, whi - wlo) for r in (tr, rr)]  # kept alive until the call returns
+            clips = []
+            for w in windows:
+                c = N.Clip()
+                c.data = w.ctypes.data
+                c.stride[0], c.stride[2] = 0, tr.frame_pixels
+                c.frame0, c.n_frames = wlo, whi - wlo
+                clips.append(c)
+            # process_host returns the whole [1,C,F,L] array, zero outside [cur, end): collect the windows
+            Qw = Qh if (cur == f0 and end == f1) else torch.empty_like(Qh)
+            self._ctx.process_host(clips[0], clips[1], cur, end, Qw.data_ptr(), hmh.data_ptr() if hmh is not None else None)
+            if Qw is not Qh:
+                Qh[:, :, cur:end] = Qw[:, :, cur:end]
+            cur = end
         return Qh, hmh
 
     def report_input_problems(self, vid_source, n_pixels, saw_frame0):

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CVVDP_B200_ABI_VERSION 4
+#define CVVDP_B200_ABI_VERSION 5
 #define CVVDP_MAX_BANDS 16
 #define CVVDP_MAX_FILTER_LEN 129
 #define CVVDP_CSF_LUT_N 32
@@ -48,6 +48,8 @@ enum { CVVDP_CS_DKLD65 = 0, CVVDP_CS_RGB_LINEAR = 1 /* forward() only */, CVVDP_
  * tone-mapped TEST sustained-achromatic context image (R[:,0], cvvdp_metric.py:399-401); like the reference, the
  * tone-curve statistics are taken over the block of frames processed in one pass (plan_info.block_frames). */
 enum { CVVDP_HEATMAP_NONE = 0, CVVDP_HEATMAP_RAW = 1, CVVDP_HEATMAP_THRESHOLD = 2, CVVDP_HEATMAP_SUPRATHRESHOLD = 3 };
+/* Interpolation of cvvdp_b200_resize: the `--full-screen-resize` choices of run_cvvdp.py:100. */
+enum { CVVDP_RESIZE_NEAREST = 0, CVVDP_RESIZE_BILINEAR = 1, CVVDP_RESIZE_BICUBIC = 2, CVVDP_RESIZE_AREA = 3 };
 
 /* cvvdp_parameters.json (cvvdp_metric.py:146-229).  Replaces cvvdp.load_config. */
 typedef struct {
@@ -166,7 +168,8 @@ int cvvdp_b200_process_device(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, 
 
 /* Same, with test/reference in HOST memory (pinned for full overlap): frames are uploaded in blocks
  * on a copy stream overlapped with compute, results are returned to host memory, and the call
- * returns after everything has completed.  q_per_ch_host: [B,C,F,L] fp32; heatmap_host: fp16 or NULL. */
+ * returns after everything has completed.  q_per_ch_host: [B,C,F,L] fp32, written whole (zero outside the frame
+ * range); heatmap_host: fp16 or NULL, only the frames of the range are written. */
 int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref,
                             int frame_begin, int frame_end, float *q_per_ch_host, void *heatmap_host);
 
@@ -188,6 +191,14 @@ int cvvdp_b200_frontend(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, int bat
  * CVVDP_CS_RGB_LINEAR the result is the display-encoded RGB of YUVReader.get_frame_rgb_tensor. */
 int cvvdp_b200_frontend_yuv(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *src, const cvvdp_b200_yuv *yuv, int batch,
                             int height, int width, int dtype, int frame, int colorspace, float *dst_dev, void *stream);
+
+/* Full-screen resize of one decoded frame: torch.nn.functional.interpolate(frame, size=(out_height, out_width),
+ * mode=...) followed by clip(0, 1) when clip01 != 0, as video_source_yuv.py:257-260,333-336 and
+ * video_source_file.py:280-287 apply it between the YCbCr matrix and the display model.  src_dev / dst_dev are
+ * dense fp32 planes [channels][height][width] / [channels][out_height][out_width] on the context's device;
+ * asynchronous on `stream`. */
+int cvvdp_b200_resize(cvvdp_b200_ctx *ctx, const float *src_dev, float *dst_dev, int channels, int height, int width,
+                      int out_height, int out_width, int mode, int clip01, void *stream);
 
 /* Input validation of the fused path -- replaces the checks the reference makes frame by frame on the host:
  * vvdp_display_photo_eotf.forward "Pixel outside the valid range 0-1" (display_model.py:335-337, only for EOTFs that

@@ -2,6 +2,8 @@
 checked against the reference-generated fixtures and the numpy oracle.  This is what keeps tile/halo
 indexing, padding rules and the host orchestration honest on a machine without a GPU; numerics of
 the real MUFU paths are covered by the -m gpu tests."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -268,6 +270,111 @@ def test_yuv_files_on_mock_device(name, tmp_path, mock_device):
 
     _, plug = m.predict_video_source(Wrapped())
     gu.assert_q_close(plug["Q_per_ch"], z["Q_per_ch"], name + " (plugin path)")
+
+
+def open_vfile_source(tf, rf, meta, **extra):
+    """The video source a vfile_* fixture was generated with."""
+    if meta["kind"] == "yuv":
+        return cv.video_source_yuv_file(tf, rf, display_photometry=meta["display"],
+                                        full_screen_resize=meta["full_screen_resize"],
+                                        resize_resolution=tuple(meta["resize_resolution"]),
+                                        retain_aspect_ratio=meta["retain_aspect_ratio"])
+    rr = meta["resize_resolution"]
+    return cv.video_source_video_file(tf, rf, display_photometry=meta["display"], full_screen_resize=meta["full_screen_resize"],
+                                      resize_resolution=None if rr is None else tuple(rr), ffmpeg_cc=meta["ffmpeg_cc"], **extra)
+
+
+@pytest.mark.parametrize("name", gu.vfile_case_names())
+def test_video_file_sources_on_mock_device(name, tmp_path, mock_device, monkeypatch):
+    """ffmpeg-pipe readers (planar YUV decoded on the device, --ffmpeg-cc packed RGB) and the full-screen resize against
+    fixtures generated with the reference's video_source_video_file / video_source_yuv_file."""
+    monkeypatch.setenv("PATH", gu.FAKE_FFMPEG_DIR + os.pathsep + os.environ["PATH"])
+    tf, rf, z, meta = gu.write_vfile_case(name, str(tmp_path))
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"])
+    vs = open_vfile_source(tf, rf, meta)
+    fused = []
+    run_yuv = m._run_yuv
+    monkeypatch.setattr(m, "_run_yuv", lambda *a, **k: (fused.append(1), run_yuv(*a, **k))[1])
+    jod, stats = m.predict_video_source(vs)
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+    # planar YUV without a resize goes through the fused temporal kernel; everything else frame by frame
+    expect_fused = meta["full_screen_resize"] is None and not meta.get("ffmpeg_cc", False)
+    assert bool(fused) == expect_fused
+    H, W, F = vs.get_video_size()
+    assert (stats["height"], stats["width"], stats["N_frames"]) == (H, W, F) == z["rgb_first_test_frame"].shape[:2] + (z["Q_per_ch"].shape[2],)
+    # the decoded (and resized) first frame, through the reader interface of the reference
+    if meta["kind"] == "yuv":
+        rd = cv.video_reader_yuv(tf, resize_fn=meta["full_screen_resize"], resize_height=H, resize_width=W)
+    else:
+        vs2 = open_vfile_source(tf, rf, meta)
+        vs2.init_readers()
+        rd = vs2.test_vidr
+    rgb = rd.unpack(rd.get_frame(), torch.device("cpu"))
+    assert tuple(rgb.shape) == z["rgb_first_test_frame"].shape
+    assert np.max(np.abs(rgb.numpy() - z["rgb_first_test_frame"])) <= 5e-6
+    rd.close()
+    if expect_fused:  # the frame-by-frame path of the same source gives the same answer
+        vs3 = open_vfile_source(tf, rf, meta)
+        monkeypatch.setattr(vs3, "yuv_readers", lambda: None)
+        _, plug = m.predict_video_source(vs3)
+        gu.assert_q_close(plug["Q_per_ch"], z["Q_per_ch"], name + " (frame by frame)")
+
+
+def test_yuv_path_walks_the_clip_in_bounded_windows(tmp_path, mock_device, monkeypatch):
+    """Host windows of the fused YUV path: a small window budget (one plan block per process call, pipes read
+    forward only) gives exactly the result of a single window."""
+    monkeypatch.setenv("PATH", gu.FAKE_FFMPEG_DIR + os.pathsep + os.environ["PATH"])
+    name = "vfile_pipe_444_12b_unknown_12x40x56_sym"
+    tf, rf, z, meta = gu.write_vfile_case(name, str(tmp_path))
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"], gpu_mem=1e-6)  # one frame per pass
+    _, whole = m.predict_video_source(open_vfile_source(tf, rf, meta))
+    calls = []
+    ph = m._ctx.process_host
+    monkeypatch.setattr(m._ctx, "process_host", lambda t, r, f0, f1, *a: (calls.append((f0, f1, t.frame0, t.n_frames)), ph(t, r, f0, f1, *a))[1])
+    monkeypatch.setattr(m, "yuv_chunk_bytes", 1)
+    _, parts = m.predict_video_source(open_vfile_source(tf, rf, meta))
+    assert len(calls) > 1 and calls[0][0] == 0 and calls[-1][1] == 12
+    assert all(c[2] <= c[0] for c in calls)
+    assert np.array_equal(parts["Q_per_ch"], whole["Q_per_ch"])
+    gu.assert_q_close(parts["Q_per_ch"], z["Q_per_ch"], name)
+
+
+def test_video_file_source_errors(tmp_path, mock_device, monkeypatch):
+    """Error behaviour of the file sources (video_source_file.py:76-88, 455-465)."""
+    with pytest.raises(cv.vq_exception, match="not found"):
+        cv.video_source_video_file(str(tmp_path / "a.mp4"), str(tmp_path / "b.mp4")).init_readers()
+    monkeypatch.setenv("PATH", gu.FAKE_FFMPEG_DIR + os.pathsep + os.environ["PATH"])
+    (tmp_path / "broken.mp4").write_bytes(b"xx")
+    with pytest.raises(cv.vq_exception, match="ffmpeg failed to open file"):
+        cv.video_reader(str(tmp_path / "broken.mp4"))
+    tf, rf, z, meta = gu.write_vfile_case("vfile_pipe_420_8b_bt709_5x48x64", str(tmp_path))
+    vs = open_vfile_source(tf, rf, meta)
+    vs.get_reference_frame(0, torch.device("cpu"), "DKLd65")
+    with pytest.raises(cv.vq_exception, match="frame-by-frame"):
+        vs.get_reference_frame(2, torch.device("cpu"), "DKLd65")
+    assert vs.yuv_readers() is None  # a source that was already read is not handed to the fused path
+    vs.reference_vidr.close(), vs.test_vidr.close()
+    short = open_vfile_source(tf, rf, meta, frames=3)
+    assert short.get_video_size() == (48, 64, 3)
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear", "bicubic", "area"])
+def test_resize_kernel_matches_torch_interpolate(mode, mock_device):
+    """k_resize against torch.nn.functional.interpolate (what the reference calls for --full-screen-resize)."""
+    from colorvideovdp_b200 import _native as N
+    from colorvideovdp_b200 import cvvdp_metric as cm
+    params, lut = cm._default_native_inputs()
+    ctx = N.Context(params, lut, 0, library=cm._mock_library)
+    g = torch.Generator().manual_seed(3)
+    for (H, W, OH, OW) in [(36, 52, 72, 104), (36, 52, 50, 77), (48, 64, 30, 41), (37, 53, 37, 80), (64, 96, 16, 24), (20, 30, 61, 45)]:
+        src = torch.rand((3, H, W), generator=g) * 1.2 - 0.1
+        dst = torch.empty((3, OH, OW))
+        ctx.resize(src.data_ptr(), dst.data_ptr(), 3, H, W, OH, OW, mode, True, None)
+        want = torch.nn.functional.interpolate(src[None], size=(OH, OW), mode=mode)[0].clip(0, 1)
+        assert float((dst - want).abs().max()) <= 5e-6, (mode, H, W, OH, OW)
+    with pytest.raises(N.NativeError):
+        ctx.resize(src.data_ptr(), dst.data_ptr(), 3, H, W, OH, OW, "lanczos", True, None)
 
 
 def test_yuv_filename_metadata():

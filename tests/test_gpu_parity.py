@@ -2,6 +2,8 @@
 reference-generated fixtures (tests/golden) and the numpy oracle on seeded inputs, plus
 size-independent properties at full BASELINE sizes.  Tolerances: |dJOD| <= 1e-3,
 |dQ_per_ch| <= 1e-3 |Q| + 1e-5, raw heat map (fp16, 0..1) <= 2e-3."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -199,6 +201,67 @@ def test_yuv_files(name, tmp_path):
     assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
     rgb = vs.test_vidr.get_frame_rgb_tensor(z["Q_per_ch"].shape[2] - 1, DEV)
     assert np.max(np.abs(rgb.cpu().numpy() - z["rgb_last_test_frame"])) <= 2e-6
+
+
+@pytest.mark.parametrize("name", gu.vfile_case_names())
+def test_video_file_sources(name, tmp_path, monkeypatch):
+    """ffmpeg-pipe readers and the full-screen resize on hardware, against the reference fixtures (the pipe is served by
+    tests/fake_ffmpeg: there is no ffmpeg in the image)."""
+    from test_emu_parity import open_vfile_source
+    monkeypatch.setenv("PATH", gu.FAKE_FFMPEG_DIR + os.pathsep + os.environ["PATH"])
+    tf, rf, z, meta = gu.write_vfile_case(name, str(tmp_path))
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"], device=DEV)
+    vs = open_vfile_source(tf, rf, meta)
+    jod, stats = m.predict_video_source(vs)
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+    H, W, F = vs.get_video_size()
+    if meta["kind"] == "yuv":
+        rd = cv.video_reader_yuv(tf, resize_fn=meta["full_screen_resize"], resize_height=H, resize_width=W)
+    else:
+        vs2 = open_vfile_source(tf, rf, meta)
+        vs2.init_readers()
+        rd = vs2.test_vidr
+    rgb = rd.unpack(rd.get_frame(), DEV)
+    assert np.max(np.abs(rgb.cpu().numpy() - z["rgb_first_test_frame"])) <= 5e-6
+    rd.close()
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear", "bicubic", "area"])
+def test_resize_kernel_matches_torch_interpolate(mode):
+    """k_resize on hardware against torch.nn.functional.interpolate on the same device, 1080p -> 4K and 4K -> 1080p."""
+    from colorvideovdp_b200 import _native as N
+    from colorvideovdp_b200 import cvvdp_metric as cm
+    params, lut = cm._default_native_inputs()
+    ctx = N.Context(params, lut, DEV.index or 0)
+    g = torch.Generator().manual_seed(3)
+    st = torch.cuda.current_stream(DEV).cuda_stream
+    for (H, W, OH, OW) in [(1080, 1920, 2160, 3840), (2160, 3840, 1080, 1920), (270, 480, 777, 1001)]:
+        src = (torch.rand((3, H, W), generator=g) * 1.2 - 0.1).to(DEV)
+        dst = torch.empty((3, OH, OW), device=DEV)
+        ctx.resize(src.data_ptr(), dst.data_ptr(), 3, H, W, OH, OW, mode, True, st)
+        want = torch.nn.functional.interpolate(src[None], size=(OH, OW), mode=mode)[0].clip(0, 1)
+        assert float((dst - want).abs().max()) <= 5e-6, (mode, H, W, OH, OW)
+
+
+def test_yuv_4k_file_streams_in_windows(tmp_path):
+    """A 4K 4:2:0 10-bit .yuv pair walked in several host windows (the mapping is read by the upload threads of the
+    library, no intermediate copy) == one window."""
+    from golden.make_golden_yuv_synth import synth_yuv
+    F, H, W = 12, 2160, 3840
+    t, r = synth_yuv(72, F, H, W, "420", 10)
+    props = {"width": W, "height": H, "fps": 30, "bit_depth": 10, "color_space": "2020", "chroma_ss": "420"}
+    tf, rf = str(tmp_path / cv.create_yuv_fname("t", props)), str(tmp_path / cv.create_yuv_fname("r", props))
+    t.tofile(tf), r.tofile(rf)
+    m = cv.cvvdp(display_name="standard_hdr_pq", device=DEV)
+    jod, whole = m.predict_video_source(cv.video_source_yuv_file(tf, rf, display_photometry="standard_hdr_pq"))
+    m.yuv_chunk_bytes = 1
+    jod2, parts = m.predict_video_source(cv.video_source_yuv_file(tf, rf, display_photometry="standard_hdr_pq"))
+    assert np.array_equal(parts["Q_per_ch"], whole["Q_per_ch"]) and float(jod) == float(jod2)
+    T, _ = O.read_yuv_rgb(tf, frames=F)
+    R, _ = O.read_yuv_rgb(rf, frames=F)
+    _, rgb_path = m.predict(torch.from_numpy(T).to(DEV), torch.from_numpy(R).to(DEV), frames_per_second=30)
+    gu.assert_q_close(whole["Q_per_ch"], rgb_path["Q_per_ch"], "4K yuv vs rgb path")
 
 
 def test_yuv_1080p_matches_oracle_and_rgb_path(tmp_path):

@@ -116,6 +116,41 @@ def test_oracle_yuv_ingestion(name, tmp_path):
     assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
 
 
+@pytest.mark.parametrize("name", gu.vfile_case_names())
+def test_oracle_video_file_sources(name, tmp_path):
+    """Frames decoded by ffmpeg (planar YUV with the ffmpeg-path matrix, packed RGB of --ffmpeg-cc) and the full-screen
+    resize, against fixtures generated with the reference's video_source_video_file /
+    video_source_yuv_file."""
+    tf, rf, z, meta = gu.write_vfile_case(name, str(tmp_path))
+    oh, ow = z["rgb_first_test_frame"].shape[:2]
+    rs = None if meta["full_screen_resize"] is None else (meta["full_screen_resize"], oh, ow)
+    if meta["kind"] == "yuv":
+        T, fps = O.read_yuv_rgb(tf, resize=rs)
+        R, _ = O.read_yuv_rgb(rf, resize=rs)
+    else:
+        st = next(s for s in meta["probe"]["streams"] if s["codec_type"] == "video")
+        T = O.read_ffmpeg_stream_rgb(tf, st, meta["ffmpeg_cc"], rs)
+        R = O.read_ffmpeg_stream_rgb(rf, st, meta["ffmpeg_cc"], rs)
+        fps = float(st["r_frame_rate"].split("/")[0])
+    assert np.max(np.abs(T[0, :, 0].transpose(1, 2, 0) - z["rgb_first_test_frame"])) <= 5e-6
+    jod, stats = O.predict(T, R, "BCFHW", fps, meta["display"], meta["padding"])
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear", "bicubic", "area"])
+def test_oracle_resize_matches_torch(mode):
+    import torch
+    """The resize restatement against torch.nn.functional.interpolate itself (the third-party routine the reference
+    calls), up- and down-scaling with non-integer factors."""
+    g = torch.Generator().manual_seed(5)
+    for (h, w, oh, ow) in [(36, 52, 72, 104), (36, 52, 50, 77), (48, 64, 30, 41), (37, 53, 37, 80), (20, 30, 61, 45)]:
+        x = torch.rand((h, w, 3), generator=g) * 1.2 - 0.1
+        want = torch.nn.functional.interpolate(x.permute(2, 0, 1)[None], size=(oh, ow), mode=mode)[0].permute(1, 2, 0).clip(0, 1)
+        got = O.resize_rgb(x.numpy(), oh, ow, mode)
+        assert np.max(np.abs(got - want.numpy())) <= 5e-6, (mode, h, w, oh, ow)
+
+
 @pytest.mark.parametrize("name", gu.feature_case_names())
 def test_oracle_features_match_reference(name):
     """per-band patch statistics of |T|S, |R|S, D (cvvdp_ml_metric.py:78-106, 302-352) against
