@@ -10,7 +10,8 @@ from .video_source import video_source, video_source_dm, video_source_array, res
 from .display_model import vvdp_display_photometry, vvdp_display_photo_eotf, vvdp_display_geometry
 from .cvvdp_metric import cvvdp
 from .video_source_yuv import video_source_yuv_file, YUVReader, video_reader_yuv, decode_video_props, create_yuv_fname
-from .video_source_file import video_source_video_file, video_reader, video_reader_yuv_pytorch
+from .video_source_file import (video_source_video_file, video_source_temp_resample_file, video_reader,
+                                video_reader_yuv_pytorch)
 from .utils import config_files
 
 __version__ = "0.1.0"

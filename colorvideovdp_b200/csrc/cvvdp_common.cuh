@@ -16,6 +16,8 @@
 
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/cvvdp_b200.h"
 
 namespace cvvdp {

@@ -95,6 +95,25 @@ __device__ __forceinline__ void eotf_forward(float (&v)[3], int n, const Display
     if (n == 3) eotf_forward_n<3>(v, d);
     else eotf_forward_n<1>(v, d);
 }
+// The same arithmetic for an EOTF known at compile time (sRGB, PQ or linear), three values: the temporal kernel picks
+// the body once per chunk of frames instead of branching per value (the run-time switch, taken twice per pixel pair
+// and frame, and the dtype switch next to it were a third of the float-input kernel's instructions).
+template <int E>
+__device__ __forceinline__ void eotf_forward_c(float (&v)[3], const DisplayDev &d) {
+    const float a = d.Ypeak - d.Yblack;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (E == CVVDP_EOTF_SRGB) {
+            float lin = srgb2lin(clamp01_keepnan(v[i]));
+            if (d.exposure != 1.f) lin = fminf(fmaxf(lin * d.exposure, 0.f), 1.f);
+            v[i] = a * lin + d.Yblack + d.Yrefl;
+        } else if (E == CVVDP_EOTF_PQ) {
+            v[i] = fminf(fmaxf(pq2lin(clamp01_keepnan(v[i])) * d.exposure, 0.005f), d.Ypeak) + d.Yblack + d.Yrefl;
+        } else {  // CVVDP_EOTF_LINEAR
+            v[i] = fminf(fmaxf(v[i] * d.exposure, d.lin_lo), d.Ypeak) + d.Yrefl;
+        }
+    }
+}
 
 // Planar YUV pixel -> display-encoded RGB in 0..1 (video_source_yuv.py:153-233): limited-range unpack,
 // bilinear chroma upsampling with torch's align_corners=False rule (src = (dst + .5)/2 - .5, clamped at
@@ -385,6 +404,16 @@ __device__ __forceinline__ float bits_as_float(unsigned b) {
 #endif
 }
 
+__device__ __forceinline__ unsigned float_as_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    unsigned b;
+    memcpy(&b, &f, 4);
+    return b;
+#endif
+}
+
 __device__ __forceinline__ int temporal_source_frame(const TemporalArgs &a, int t) {
     if (t >= 0) return t;
     return (a.padding == CVVDP_PAD_REPLICATE) ? 0 : symmetric_frame_index(t, a.F_total);
@@ -436,7 +465,7 @@ __device__ __forceinline__ unsigned lds_u8(const unsigned char *p) {
 }
 // Two pixels (a, b) -> DKL, as the halves of fp32x2 values.  Per lane the same operations in the same
 // order as bits_to_dkl (v1*M1, then fma with v0*M0, then fma with v2*M2), two lanes per instruction.
-template <bool USE_LUT>
+template <bool USE_LUT, int DT = -1, int E = -1>  // DT / E >= 0: dtype / EOTF fixed at compile time (three channels)
 __device__ __forceinline__ void bits_to_dkl2(const TemporalArgs &a, const float *lut, const unsigned ba[3], const unsigned bb[3],
                                              float2 &d0, float2 &d1, float2 &d2, unsigned &vbits) {
     float va[3], vb[3];
@@ -447,24 +476,42 @@ __device__ __forceinline__ void bits_to_dkl2(const TemporalArgs &a, const float 
             vb[i] = lut[bb[i]];
         }
     } else {
+        const int dtype = DT >= 0 ? DT : a.dtype;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            switch (a.dtype) {
+            switch (dtype) {
                 case CVVDP_DTYPE_U8: va[i] = (float)ba[i] / 255.0f; vb[i] = (float)bb[i] / 255.0f; break;
                 case CVVDP_DTYPE_U16: va[i] = (float)ba[i] * (1.0f / 65535.0f); vb[i] = (float)bb[i] * (1.0f / 65535.0f); break;
                 case CVVDP_DTYPE_F16: va[i] = half_bits_to_float((unsigned short)ba[i]); vb[i] = half_bits_to_float((unsigned short)bb[i]); break;
                 default: va[i] = bits_as_float(ba[i]); vb[i] = bits_as_float(bb[i]);
             }
         }
-        if (a.dtype >= CVVDP_DTYPE_F16) {  // integer code values cannot be out of range, NaN or Inf
-            const bool rng = a.dd.eotf != CVVDP_EOTF_LINEAR && a.dd.eotf != CVVDP_EOTF_NONE;
+        if (dtype >= CVVDP_DTYPE_F16) {  // integer code values cannot be out of range, NaN or Inf
+            const int eotf = E >= 0 ? E : a.dd.eotf;
+            const bool rng = eotf != CVVDP_EOTF_LINEAR && eotf != CVVDP_EOTF_NONE;
+            // As unsigned integers, the floats of [0, 1] are exactly the patterns <= 0x3f800000 (and -0); with the sign
+            // masked off, the finite ones are those <= 0x7f7fffff.  One integer max per value finds out whether this
+            // frame needs the exact classification at all.
+            unsigned worst = 0u;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) vbits |= input_bits(va[i], rng) | input_bits(vb[i], rng);
+            for (int i = 0; i < 3; ++i) {
+                const unsigned xa = float_as_bits(va[i]), xb = float_as_bits(vb[i]);
+                worst = max(worst, max(rng ? xa : (xa & 0x7fffffffu), rng ? xb : (xb & 0x7fffffffu)));
+            }
+            if (worst > (rng ? 0x3f800000u : 0x7f7fffffu)) {
+#pragma unroll
+                for (int i = 0; i < 3; ++i) vbits |= input_bits(va[i], rng) | input_bits(vb[i], rng);
+            }
         }
-        eotf_forward(va, a.cin, a.dd);
-        eotf_forward(vb, a.cin, a.dd);
+        if (E >= 0) {
+            eotf_forward_c<E>(va, a.dd);
+            eotf_forward_c<E>(vb, a.dd);
+        } else {
+            eotf_forward(va, a.cin, a.dd);
+            eotf_forward(vb, a.cin, a.dd);
+        }
     }
-    if (a.cin == 3) {
+    if (E >= 0 || a.cin == 3) {
         const float2 v0 = make_float2(va[0], vb[0]), v1 = make_float2(va[1], vb[1]), v2 = make_float2(va[2], vb[2]);
         d0 = fma2(v2, bc2(a.dd.M[2]), fma2(v0, bc2(a.dd.M[0]), mul2(v1, bc2(a.dd.M[1]))));
         d1 = fma2(v2, bc2(a.dd.M[5]), fma2(v0, bc2(a.dd.M[3]), mul2(v1, bc2(a.dd.M[4]))));
@@ -551,20 +598,25 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     unsigned vbits = 0u;  // input validity bits seen by this thread (floating-point clips only)
     float msum = 0.f;     // achromatic DKL sum of this thread's two pixels of clip frame 0 (test video)
     const int it_zero = v == 0 && a.mean0 != nullptr ? FL - 1 - a.f0 : -1;  // iteration that holds clip frame 0
-    auto convert_chunk = [&](int it0) {
-        // three frames in flight for the table variant (a dozen instructions per frame); the per-pixel EOTF of the
-        // float variant is long enough to hide its own latencies and must not be replicated
-#pragma unroll(USE_LUT ? 3 : 1)
+    // One body per (dtype, EOTF) pair that matters for throughput -- fp32 / fp16 / uint16 clips on an sRGB, PQ or linear
+    // display, three channels -- with both fixed at compile time; everything else (and the table variant, which has
+    // nothing left to specialise) takes the generic body with its run-time switches.
+    auto convert_body = [&](auto dt_c, auto eotf_c, auto esz_c, int it0) {
+        constexpr int DT = decltype(dt_c)::value, E = decltype(eotf_c)::value, ESZ = decltype(esz_c)::value;
+        const int eszv = ESZ > 0 ? ESZ : esz;
+        // three frames in flight for the table variant (a dozen instructions per frame), two for a specialised body; the
+        // generic per-pixel EOTF is long enough to hide its own latencies and must not be replicated
+#pragma unroll(USE_LUT ? 3 : (DT >= 0 ? 2 : 1))
         for (int g = 0; g < G; ++g) {
             const unsigned char *q = raw + g * frame_bytes;
             unsigned ba[3], bb[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const unsigned char *qc = q + (a.cin == 3 ? ch : 0) * row_bytes;
-                if (esz == 1) {
+                const unsigned char *qc = q + ((DT >= 0 || a.cin == 3) ? ch : 0) * row_bytes;
+                if (eszv == 1) {
                     ba[ch] = lds_u8(qc + lane);
                     bb[ch] = lds_u8(qc + lane + 32);
-                } else if (esz == 2) {
+                } else if (eszv == 2) {
                     ba[ch] = ((const unsigned short *)qc)[lane];
                     bb[ch] = ((const unsigned short *)qc)[lane + 32];
                 } else {
@@ -573,12 +625,43 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
                 }
             }
             float2 d0, d1, d2;
-            bits_to_dkl2<USE_LUT>(a, s_lut, ba, bb, d0, d1, d2, vbits);
+            bits_to_dkl2<USE_LUT, DT, E>(a, s_lut, ba, bb, d0, d1, d2, vbits);
             if (it0 + g == it_zero) msum = d0.x + d0.y;  // uniform
             dkl[(g * 3 + 0) * CVVDP_T2S_THREADS] = d0;
             dkl[(g * 3 + 1) * CVVDP_T2S_THREADS] = d1;
             dkl[(g * 3 + 2) * CVVDP_T2S_THREADS] = d2;
         }
+    };
+    // 0: generic; 1 + 3 * k + e: k = fp32, fp16, uint16 and e = sRGB, PQ, linear
+    int conv_mode = 0;
+    if (!USE_LUT && a.cin == 3) {
+        const int k = a.dtype == CVVDP_DTYPE_F32 ? 0 : (a.dtype == CVVDP_DTYPE_F16 ? 1 : (a.dtype == CVVDP_DTYPE_U16 ? 2 : -1));
+        const int e = a.dd.eotf == CVVDP_EOTF_SRGB ? 0 : (a.dd.eotf == CVVDP_EOTF_PQ ? 1 : (a.dd.eotf == CVVDP_EOTF_LINEAR ? 2 : -1));
+        if (k >= 0 && e >= 0) conv_mode = 1 + 3 * k + e;
+    }
+    auto convert_chunk = [&](int it0) {
+        using std::integral_constant;
+#define CVVDP_CONV_CASE(MODE, DTV, EV, ESZV)                                                                                    \
+    case MODE:                                                                                                                  \
+        convert_body(integral_constant<int, DTV>{}, integral_constant<int, EV>{}, integral_constant<int, ESZV>{}, it0);         \
+        break;
+        if (USE_LUT) {
+            convert_body(integral_constant<int, -1>{}, integral_constant<int, -1>{}, integral_constant<int, 1>{}, it0);
+            return;
+        }
+        switch (conv_mode) {  // uniform over the grid
+            CVVDP_CONV_CASE(1, CVVDP_DTYPE_F32, CVVDP_EOTF_SRGB, 4)
+            CVVDP_CONV_CASE(2, CVVDP_DTYPE_F32, CVVDP_EOTF_PQ, 4)
+            CVVDP_CONV_CASE(3, CVVDP_DTYPE_F32, CVVDP_EOTF_LINEAR, 4)
+            CVVDP_CONV_CASE(4, CVVDP_DTYPE_F16, CVVDP_EOTF_SRGB, 2)
+            CVVDP_CONV_CASE(5, CVVDP_DTYPE_F16, CVVDP_EOTF_PQ, 2)
+            CVVDP_CONV_CASE(6, CVVDP_DTYPE_F16, CVVDP_EOTF_LINEAR, 2)
+            CVVDP_CONV_CASE(7, CVVDP_DTYPE_U16, CVVDP_EOTF_SRGB, 2)
+            CVVDP_CONV_CASE(8, CVVDP_DTYPE_U16, CVVDP_EOTF_PQ, 2)
+            CVVDP_CONV_CASE(9, CVVDP_DTYPE_U16, CVVDP_EOTF_LINEAR, 2)
+            default: convert_body(integral_constant<int, -1>{}, integral_constant<int, -1>{}, integral_constant<int, 0>{}, it0);
+        }
+#undef CVVDP_CONV_CASE
     };
     issue_chunk(0);
     int it = 0;
@@ -1403,8 +1486,6 @@ __global__ void __launch_bounds__(CVVDP_B2_THREADS, 3) k_band2f(const __grid_con
     const int sw_odd = (tid >> 2) & 1;
     const float wA0 = sw_odd ? 0.f : 0.1f, wA1 = sw_odd ? 0.5f : 0.8f, wA2 = sw_odd ? 0.5f : 0.1f;
     const float wB0 = sw_odd ? 0.1f : 0.f, wB1 = sw_odd ? 0.8f : 0.5f, wB2 = sw_odd ? 0.1f : 0.5f;
-    // staged fine pixel (video v, stage row r, staged column f)
-    auto fine_at = [&](int v, int r, int f) -> const float4 & { return f < 64 ? sm.fine_a[v][r][f] : sm.fine_b[v][r][f - 64]; };
     // ---- reduce, vertical 5-tap pass (lpyr_dec.py:186-199) for the coarse rows a0/2+1 .. a0/2+4 of the step whose
     // fine rows [a0, a0+11) are in the stage: one (video, column) task per thread, 2 x 64 columns of box A, then the
     // 2 x 3 columns of box B on six threads.  EDGE: the step holds coarse row 0 or hc-1 (top / bottom fix-ups);

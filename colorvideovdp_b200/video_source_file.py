@@ -19,6 +19,7 @@ pyexr and are not part of this package: pass decoded images as arrays to `cvvdp.
 """
 import json
 import logging
+import math
 import os
 import re
 import shutil
@@ -316,3 +317,63 @@ class video_source_video_file(video_source_dm):
     def _prepare_frame(self, frame_np, device, unpack_fn, colorspace="Y"):
         frame_t = reshuffle_dims(unpack_fn(frame_np, device), in_dims="HWC", out_dims="BCFHW")
         return self.apply_dm_and_color_transform(frame_t, colorspace)
+
+
+def safe_floor(x):
+    """floor() that tolerates a value a rounding error below an integer (video_source_file.py:328-330)."""
+    x_f = math.floor(x)
+    return x_f if (x - x_f) < (1 - 1e-6) else x_f + 1
+
+
+class video_source_temp_resample_file(video_source_video_file):
+    """Test and reference with different (constant) frame rates: both are resampled in time, by frame repetition, to a
+    common rate (`--temp-resample`, video_source_file.py:478-541).  Frames are pulled one by one (plugin path)."""
+
+    max_fps = 166  # upsample to at most this rate
+
+    def __init__(self, test_fname, reference_fname, display_photometry="sdr_4k_30", config_paths=[], frames=-1,
+                 full_screen_resize=None, resize_resolution=None, ffmpeg_cc=False, verbose=False):
+        super().__init__(test_fname, reference_fname, display_photometry=display_photometry, config_paths=config_paths,
+                         frames=frames, full_screen_resize=full_screen_resize, resize_resolution=resize_resolution,
+                         ffmpeg_cc=ffmpeg_cc, verbose=verbose, ignore_framerate_mismatch=True)
+        super().init_readers()
+        test_fps, ref_fps = self.test_vidr.avg_fps, self.reference_vidr.avg_fps
+        cls = type(self)
+        if test_fps > cls.max_fps or ref_fps > cls.max_fps:
+            raise vq_exception(f"Maximum resample fps ({cls.max_fps}) is smaller than the fps of the test ({test_fps}) or "
+                               f"reference video ({ref_fps}). Increase maximum resample fps, e.g, by passing "
+                               f"`--temp-resample {max(test_fps, ref_fps)}`")
+        if test_fps % 1 == 0 and ref_fps % 1 == 0:  # an integer common multiple, if it is not too high
+            self.resample_fps = min(test_fps * ref_fps / math.gcd(int(test_fps), int(ref_fps)), cls.max_fps)
+        else:
+            self.resample_fps = cls.max_fps
+        test_rs = int(self.test_vidr.frames * self.resample_fps / test_fps)
+        ref_rs = int(self.reference_vidr.frames * self.resample_fps / ref_fps)
+        if self.test_vidr.frames == -1:
+            frames_rs = ref_rs
+        elif self.reference_vidr.frames == -1:
+            frames_rs = test_rs
+        else:
+            frames_rs = min(test_rs, ref_rs)
+        self.frames = frames_rs if frames < 0 else frames
+        logging.info(f"Test fps: {test_fps}; reference fps: {ref_fps}. Resampling videos to {self.resample_fps} frames per "
+                     f"second. {self.frames} frames will be processed.")
+        if test_rs != ref_rs:
+            logging.warning(f"Test and reference videos contain different number of frames after resampling ({test_rs} and "
+                            f"{ref_rs}). Comparing {self.frames} frames.")
+        self.cache_ind = [-1, -1]
+        self.cache_frame = [None, None]
+
+    def get_frames_per_second(self):
+        return self.resample_fps
+
+    def yuv_readers(self):
+        return None  # frames repeat: the clip is not a plain run of stream frames
+
+    def _get_frame(self, vid_reader, frame, device, colorspace):
+        frame_ind = int(safe_floor((frame + 0.5) * vid_reader.avg_fps / self.resample_fps))
+        ce = 0 if vid_reader is self.test_vidr else 1
+        if self.cache_ind[ce] != frame_ind:
+            self.cache_ind[ce] = frame_ind
+            self.cache_frame[ce] = super()._get_frame(vid_reader, frame_ind, device=device, colorspace=colorspace)
+        return self.cache_frame[ce]

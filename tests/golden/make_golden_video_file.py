@@ -161,7 +161,30 @@ def save_yuv_resized(name, seed, F, H, W, fps, chroma, bit_depth, color_space, d
     print(name, float(jod), Q.shape, rgb.shape)
 
 
+def save_resample(name, seed, F60, H, W, display, padding="replicate"):
+    """video_source_temp_resample_file: a 30 fps test stream against a 60 fps reference stream (8-bit 4:2:0)."""
+    t, r = synth_yuv(seed, F60, H, W, "420", 8)
+    fpix = H * W * 3 // 2
+    t30 = np.concatenate([t[f * fpix:(f + 1) * fpix] for f in range(0, F60, 2)])
+    probes = (probe_dict(W, H, 30, "yuv420p", "yuv420p", F60 // 2, "bt709"), probe_dict(W, H, 60, "yuv420p", "yuv420p", F60, "bt709"))
+    with tempfile.TemporaryDirectory() as td:
+        tf, rf = os.path.join(td, "test.mp4"), os.path.join(td, "ref.mp4")
+        for fn, a, pr in ((tf, t30, probes[0]), (rf, r, probes[1])):
+            a.tofile(fn)
+            with open(fn + ".probe.json", "w") as f:
+                json.dump(pr, f)
+        vs = ref_vsf.video_source_temp_resample_file(tf, rf, display_photometry=display)
+        fps, size = vs.get_frames_per_second(), [int(x) for x in vs.get_video_size()]
+        jod, Q = run_reference(vs, display, padding)
+    meta = {"kind": "resample", "display": display, "padding": padding, "probe_test": probes[0], "probe_ref": probes[1],
+            "resample_fps": float(fps), "video_size": size}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), test_bytes=t30, ref_bytes=r, meta=np.asarray(json.dumps(meta)),
+                        jod=jod, Q_per_ch=Q)
+    print(name, float(jod), Q.shape, fps, size)
+
+
 if __name__ == "__main__":
+    save_resample("vresample_30_vs_60fps_8x40x56", 89, 8, 40, 56, "standard_fhd")
     save_pipe("vfile_pipe_420_8b_bt709_5x48x64", 81, 5, 48, 64, 24, "420", 8, "bt709", "standard_fhd")
     save_pipe("vfile_pipe_422_10b_bt2020nc_4x36x52_pq_bilinear", 82, 4, 36, 52, 30, "422", 10, "bt2020nc", "standard_hdr_pq",
               resize="bilinear", resize_resolution=(78, 54), color_transfer="smpte2084")

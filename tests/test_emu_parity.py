@@ -340,6 +340,21 @@ def test_yuv_path_walks_the_clip_in_bounded_windows(tmp_path, mock_device, monke
     gu.assert_q_close(parts["Q_per_ch"], z["Q_per_ch"], name)
 
 
+def test_temporal_resampling_of_file_sources(tmp_path, mock_device, monkeypatch):
+    """video_source_temp_resample_file (--temp-resample): a 30 fps test against a 60 fps reference, frames repeated to
+    the common rate, against the reference's own class."""
+    monkeypatch.setenv("PATH", gu.FAKE_FFMPEG_DIR + os.pathsep + os.environ["PATH"])
+    tf, rf, z, meta = gu.write_vfile_case("vresample_30_vs_60fps_8x40x56", str(tmp_path))
+    with pytest.raises(cv.vq_exception, match="different frame rates"):
+        cv.video_source_video_file(tf, rf, display_photometry=meta["display"]).init_readers()
+    vs = cv.video_source_temp_resample_file(tf, rf, display_photometry=meta["display"])
+    assert vs.get_frames_per_second() == meta["resample_fps"] and list(vs.get_video_size()) == meta["video_size"]
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"])
+    jod, stats = m.predict_video_source(vs)
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], "temporal resampling")
+    assert abs(float(jod) - float(z["jod"])) <= gu.JOD_TOL
+
+
 def test_video_file_source_errors(tmp_path, mock_device, monkeypatch):
     """Error behaviour of the file sources (video_source_file.py:76-88, 455-465)."""
     with pytest.raises(cv.vq_exception, match="not found"):
