@@ -504,7 +504,10 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             if (cvw.s[4] != 1 || cvw.s[3] != job.width) dense = false;
             if (((uintptr_t)cvw.data) % 16 || (cvw.s[0] * es) % 16 || (cvw.s[1] * es) % 16 || (cvw.s[2] * es) % 16) dense = false;
         }
-        const int t_esz = use_lut ? 1 : (int)dtype_size(job.dtype);
+        // planar YUV: rows of whole 64-pixel segments (the two pixels of a thread share a row), frames anywhere
+        const bool yuv_2s = is_yuv && job.width % 64 == 0 && (job.dtype == CVVDP_DTYPE_U8 || job.dtype == CVVDP_DTYPE_U16);
+        if (yuv_2s) dense = true;
+        const int t_esz = is_yuv ? 0 : (use_lut ? 1 : (int)dtype_size(job.dtype));
         const size_t smem_2s = t2s_smem_bytes(info.filter_len, t_esz);
         bool taps_symmetric = true;  // exact: the two-stage kernel adds mirrored frames before multiplying
         for (int c = 0; c < 4; ++c)
@@ -517,11 +520,15 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
 #define CVVDP_TEMPORAL_CASE(FLV)                                                                  \
     case FLV: {                                                                                   \
         if (use_lut) {                                                                            \
-            auto kfn = k_temporal_2s<FLV, true>;                                                  \
+            auto kfn = k_temporal_2s<FLV, CVVDP_T2S_LUT>;                                         \
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2s); \
+            CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);                 \
+        } else if (is_yuv) {                                                                      \
+            auto kfn = k_temporal_2s<FLV, CVVDP_T2S_YUV>;                                         \
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2s); \
             CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);                 \
         } else {                                                                                  \
-            auto kfn = k_temporal_2s<FLV, false>;                                                 \
+            auto kfn = k_temporal_2s<FLV, CVVDP_T2S_ANY>;                                         \
             cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_2s); \
             CVVDP_LAUNCH(kfn, grid_2s, dim3(CVVDP_T2S_THREADS), smem_2s, st, ta);                 \
         }                                                                                         \

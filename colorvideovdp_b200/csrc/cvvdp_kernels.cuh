@@ -98,17 +98,17 @@ __device__ __forceinline__ void eotf_forward(float (&v)[3], int n, const Display
 // The same arithmetic for an EOTF known at compile time (sRGB, PQ or linear), three values: the temporal kernel picks
 // the body once per chunk of frames instead of branching per value (the run-time switch, taken twice per pixel pair
 // and frame, and the dtype switch next to it were a third of the float-input kernel's instructions).
-template <int E>
+template <int E, bool IN_RANGE = false>  // IN_RANGE: the values are known to lie in [0, 1] (decoded YUV): no clamp needed
 __device__ __forceinline__ void eotf_forward_c(float (&v)[3], const DisplayDev &d) {
     const float a = d.Ypeak - d.Yblack;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         if (E == CVVDP_EOTF_SRGB) {
-            float lin = srgb2lin(clamp01_keepnan(v[i]));
+            float lin = srgb2lin(IN_RANGE ? v[i] : clamp01_keepnan(v[i]));
             if (d.exposure != 1.f) lin = fminf(fmaxf(lin * d.exposure, 0.f), 1.f);
             v[i] = a * lin + d.Yblack + d.Yrefl;
         } else if (E == CVVDP_EOTF_PQ) {
-            v[i] = fminf(fmaxf(pq2lin(clamp01_keepnan(v[i])) * d.exposure, 0.005f), d.Ypeak) + d.Yblack + d.Yrefl;
+            v[i] = fminf(fmaxf(pq2lin(IN_RANGE ? v[i] : clamp01_keepnan(v[i])) * d.exposure, 0.005f), d.Ypeak) + d.Yblack + d.Yrefl;
         } else {  // CVVDP_EOTF_LINEAR
             v[i] = fminf(fmaxf(v[i] * d.exposure, d.lin_lo), d.Ypeak) + d.Yrefl;
         }
@@ -121,14 +121,13 @@ __device__ __forceinline__ void eotf_forward_c(float (&v)[3], const DisplayDev &
 __device__ __forceinline__ float yuv_sample(const void *data, long long off, int dtype) {
     return dtype == CVVDP_DTYPE_U8 ? (float)((const unsigned char *)data)[off] : (float)((const unsigned short *)data)[off];
 }
-__device__ __forceinline__ void yuv_fetch_rgb(const ClipView &cv, const YuvDev &yu, int dtype, long long fbase, int y, int x,
-                                              float rgb[3]) {
-    const long long ypix = (long long)yu.W * yu.H;
+// chroma samples (columns i0, i1, rows j0, j1) and weights of luma pixel (y, x)
+__device__ __forceinline__ void yuv_chroma_taps(const YuvDev &yu, int y, int x, int &i0, int &i1, int &j0, int &j1, float &lx,
+                                                float &ly) {
     const int cw = yu.chroma == 444 ? yu.W : yu.W / 2, ch = yu.chroma == 420 ? yu.H / 2 : yu.H;
-    const long long uvpix = (long long)cw * ch;
-    const float Y = fminf(fmaxf(yu.yw * yuv_sample(cv.data, fbase + (long long)y * yu.W + x, dtype) - yu.yo, 0.f), 1.f);
-    int i0 = x, i1 = x, j0 = y, j1 = y;
-    float lx = 0.f, ly = 0.f;
+    i0 = i1 = x;
+    j0 = j1 = y;
+    lx = ly = 0.f;
     if (yu.chroma != 444) {
         const float sx = fmaxf(((float)x + 0.5f) * 0.5f - 0.5f, 0.f);
         i0 = (int)sx;
@@ -141,6 +140,16 @@ __device__ __forceinline__ void yuv_fetch_rgb(const ClipView &cv, const YuvDev &
         ly = sy - (float)j0;
         j1 = min(j0 + 1, ch - 1);
     }
+}
+__device__ __forceinline__ void yuv_fetch_rgb(const ClipView &cv, const YuvDev &yu, int dtype, long long fbase, int y, int x,
+                                              float rgb[3]) {
+    const long long ypix = (long long)yu.W * yu.H;
+    const int cw = yu.chroma == 444 ? yu.W : yu.W / 2, ch = yu.chroma == 420 ? yu.H / 2 : yu.H;
+    const long long uvpix = (long long)cw * ch;
+    const float Y = fminf(fmaxf(yu.yw * yuv_sample(cv.data, fbase + (long long)y * yu.W + x, dtype) - yu.yo, 0.f), 1.f);
+    int i0, i1, j0, j1;
+    float lx, ly;
+    yuv_chroma_taps(yu, y, x, i0, i1, j0, j1, lx, ly);
     float uv[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
@@ -532,8 +541,15 @@ __host__ __device__ inline size_t t2s_smem_bytes(int fl, int esz) {
     const int G = (fl + 1) / 2;
     return (size_t)(CVVDP_T2S_THREADS / 32) * G * 3 * 64 * esz + (size_t)G * 3 * CVVDP_T2S_THREADS * 8;
 }
-template <int FL, bool USE_LUT>
+// SRC: where the frames come from -- 0: dense planes of any dtype (raw stage filled by cp.async), 1: 8-bit planes through
+// the 256-entry EOTF table, 2: planar YUV frames read straight from global memory (the chroma taps of neighbouring
+// pixels overlap, so L1 serves most of them; rows must be whole 64-pixel segments).
+#define CVVDP_T2S_ANY 0
+#define CVVDP_T2S_LUT 1
+#define CVVDP_T2S_YUV 2
+template <int FL, int SRC>
 __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __grid_constant__ TemporalArgs a) {
+    constexpr bool USE_LUT = SRC == CVVDP_T2S_LUT;
     constexpr int RP = T2SGeom<FL>::RP, G = T2SGeom<FL>::G;
     __shared__ float s_lut[256];
     CVVDP_DYN_SMEM(smem_raw);
@@ -551,18 +567,21 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
     if (wp >= npix) return;  // whole 64-pixel segments only (npix % 64 == 0); no block-level barrier below
     const ClipView &cv = a.clip[v];
-    const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
+    const int esz = USE_LUT ? 1 : (SRC == CVVDP_T2S_YUV ? 0 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2)));  // YUV: no raw stage
     const int row_bytes = 64 * esz;          // one (channel, frame) segment of this warp
     const int frame_bytes = 3 * row_bytes;   // slot of one frame in the raw stage (cin == 1 uses the first third)
     const int cpc = row_bytes / 16;          // 16-byte pieces per channel segment
-    const int ppf = a.cin * cpc;             // pieces per frame
+    const int ppf = SRC == CVVDP_T2S_YUV ? 1 : a.cin * cpc;  // pieces per frame
     unsigned char *raw = smem_raw + (size_t)warp * G * frame_bytes;
     float2 *dkl = reinterpret_cast<float2 *>(smem_raw + (size_t)(CVVDP_T2S_THREADS / 32) * G * frame_bytes) + tid;
     const long long fstride = cv.s[2] * esz, cstride = cv.s[1] * esz;
     const unsigned char *wsrc = (const unsigned char *)cv.data + (b * cv.s[0] + wp) * esz;
     const int n = a.f1 - a.f0;
     const int NI = (FL - 1) + n;  // iterations: FL-1 warm-up frames (temporal padding before frame 0), then the block
-    float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + wp + lane;
+    // the thread's two pixels: lane and lane + 32 of the segment, or -- planar YUV -- the horizontal neighbours 2 lane and
+    // 2 lane + 1, which share their chroma samples
+    constexpr int PB = SRC == CVVDP_T2S_YUV ? 1 : 32;
+    float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + wp + (SRC == CVVDP_T2S_YUV ? 2 * lane : lane);
     const long long ostep = 2 * npix;
     float2 r0[RP], r1[RP], r2[RP];
 #pragma unroll
@@ -575,6 +594,7 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     const int g_first = lane / ppf, rem_first = lane - g_first * ppf;
     const int cpc_shift = esz == 1 ? 2 : (esz == 2 ? 3 : 4);
     auto issue_chunk = [&](int c) {
+        if (SRC == CVVDP_T2S_YUV) return;  // no raw stage
         int g = g_first, rem = rem_first;
         const int it0 = c * G;
         while (g < G) {
@@ -632,6 +652,88 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
             dkl[(g * 3 + 2) * CVVDP_T2S_THREADS] = d2;
         }
     };
+    // Planar YUV (SRC == CVVDP_T2S_YUV, video_source_yuv.py:153-233): the thread's pixels (y, x) and (y, x + 1), x even, need
+    // the chroma columns L, M, R and rows j0, j1 of each plane -- six samples instead of eight: with subsampled chroma
+    // (k = x / 2) L = max(k-1, 0), M = k, R = min(k+1, cw-1), pixel x blends (L, M) with weight 0.75 (0 at k = 0, where
+    // torch clamps the source coordinate) and pixel x + 1 blends (M, R) with 0.25; 4:4:4 takes L = x, M = R = x + 1 with
+    // weights 0.  Rows as in yuv_chroma_taps.  The limited-range clip of a chroma sample is done as saturate(c + 0.5)
+    // and the 0.5 taken off after the blend (the weights add up to one).
+    int yuv_oL = 0, yuv_dM = 0, yuv_dR = 0, yuv_dj = 0, yuv_ypix = 0, yuv_uvpix = 0;  // (a frame has fewer than 2^31 samples)
+    float2 yuv_lx = make_float2(0.f, 0.f);
+    float yuv_ly = 0.f;
+    if (SRC == CVVDP_T2S_YUV) {
+        const int cwid = a.yuv.chroma == 444 ? a.W : a.W / 2, chei = a.yuv.chroma == 420 ? a.H / 2 : a.H;
+        yuv_ypix = (int)npix;
+        yuv_uvpix = cwid * chei;
+        const long long p0 = wp + 2 * lane;
+        const int y = (int)(p0 / a.W), x = (int)(p0 - (long long)y * a.W);
+        int i0, i1, j0, j1;
+        float lx_unused;
+        yuv_chroma_taps(a.yuv, y, x, i0, i1, j0, j1, lx_unused, yuv_ly);
+        yuv_dj = (j1 - j0) * cwid;
+        if (a.yuv.chroma == 444) {
+            yuv_oL = j0 * cwid + x;
+            yuv_dM = yuv_dR = 1;
+        } else {
+            const int k = x >> 1, cl = max(k - 1, 0);
+            yuv_oL = j0 * cwid + cl;
+            yuv_dM = k - cl;
+            yuv_dR = min(k + 1, cwid - 1) - cl;
+            yuv_lx = make_float2(k == 0 ? 0.f : 0.75f, 0.25f);
+        }
+    }
+    auto convert_yuv = [&](auto dt_c, auto eotf_c, int it0) {
+        constexpr int DT = decltype(dt_c)::value, E = decltype(eotf_c)::value;
+        typedef typename std::conditional<DT == CVVDP_DTYPE_U8, unsigned char, unsigned short>::type S;
+        const YuvDev &yu = a.yuv;
+        const float c_off = 0.5f - yu.co;
+        const float2 wx1 = yuv_lx, wx0 = make_float2(1.f - yuv_lx.x, 1.f - yuv_lx.y);
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            if (it0 + g >= NI) break;  // uniform
+            const int t = a.f0 - (FL - 1) + it0 + g;
+            const int slot = frame_slot(cv, t >= 0 ? t : temporal_source_frame(a, t));
+            const S *fy = (const S *)cv.data + b * cv.s[0] + (long long)slot * cv.s[2] + wp + 2 * lane;
+            const S *fc = fy - (wp + 2 * lane) + yuv_ypix + yuv_oL;
+            const float Ya = __saturatef(fmaf(yu.yw, (float)__ldg(fy), -yu.yo)), Yb = __saturatef(fmaf(yu.yw, (float)__ldg(fy + 1), -yu.yo));
+            float2 uv[2];
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+                const S *q = fc + pl * yuv_uvpix;
+                const float cL0 = __saturatef(fmaf(yu.cw, (float)__ldg(q), c_off));
+                const float cM0 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dM), c_off));
+                const float cR0 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dR), c_off));
+                const float cL1 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dj), c_off));
+                const float cM1 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dj + yuv_dM), c_off));
+                const float cR1 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dj + yuv_dR), c_off));
+                const float2 top = fma2(wx0, make_float2(cL0, cM0), mul2(wx1, make_float2(cM0, cR0)));
+                const float2 bot = fma2(wx0, make_float2(cL1, cM1), mul2(wx1, make_float2(cM1, cR1)));
+                uv[pl] = add2(fma2(bc2(1.f - yuv_ly), top, mul2(bc2(yuv_ly), bot)), bc2(-0.5f));
+            }
+            float ra[3], rb[3];
+            ra[0] = __saturatef(fmaf(yu.m_rv, uv[1].x, Ya));
+            ra[1] = __saturatef(fmaf(yu.m_gv, uv[1].x, fmaf(yu.m_gu, uv[0].x, Ya)));
+            ra[2] = __saturatef(fmaf(yu.m_bu, uv[0].x, Ya));
+            rb[0] = __saturatef(fmaf(yu.m_rv, uv[1].y, Yb));
+            rb[1] = __saturatef(fmaf(yu.m_gv, uv[1].y, fmaf(yu.m_gu, uv[0].y, Yb)));
+            rb[2] = __saturatef(fmaf(yu.m_bu, uv[0].y, Yb));
+            if (E >= 0) {
+                eotf_forward_c<E, true>(ra, a.dd);
+                eotf_forward_c<E, true>(rb, a.dd);
+            } else {
+                eotf_forward_n<3>(ra, a.dd);
+                eotf_forward_n<3>(rb, a.dd);
+            }
+            const float2 v0 = make_float2(ra[0], rb[0]), v1 = make_float2(ra[1], rb[1]), v2 = make_float2(ra[2], rb[2]);
+            const float2 d0 = fma2(v2, bc2(a.dd.M[2]), fma2(v0, bc2(a.dd.M[0]), mul2(v1, bc2(a.dd.M[1]))));
+            const float2 d1 = fma2(v2, bc2(a.dd.M[5]), fma2(v0, bc2(a.dd.M[3]), mul2(v1, bc2(a.dd.M[4]))));
+            const float2 d2 = fma2(v2, bc2(a.dd.M[8]), fma2(v0, bc2(a.dd.M[6]), mul2(v1, bc2(a.dd.M[7]))));
+            if (it0 + g == it_zero) msum = d0.x + d0.y;  // uniform
+            dkl[(g * 3 + 0) * CVVDP_T2S_THREADS] = d0;
+            dkl[(g * 3 + 1) * CVVDP_T2S_THREADS] = d1;
+            dkl[(g * 3 + 2) * CVVDP_T2S_THREADS] = d2;
+        }
+    };
     // 0: generic; 1 + 3 * k + e: k = fp32, fp16, uint16 and e = sRGB, PQ, linear
     int conv_mode = 0;
     if (!USE_LUT && a.cin == 3) {
@@ -649,7 +751,21 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
             convert_body(integral_constant<int, -1>{}, integral_constant<int, -1>{}, integral_constant<int, 1>{}, it0);
             return;
         }
-        switch (conv_mode) {  // uniform over the grid
+        if constexpr (SRC == CVVDP_T2S_YUV) {  // 8- or 16-bit samples x (sRGB, PQ, any other EOTF at run time)
+            const int e = a.dd.eotf;
+            if (a.dtype == CVVDP_DTYPE_U8) {
+                if (e == CVVDP_EOTF_SRGB) convert_yuv(integral_constant<int, CVVDP_DTYPE_U8>{}, integral_constant<int, CVVDP_EOTF_SRGB>{}, it0);
+                else if (e == CVVDP_EOTF_PQ) convert_yuv(integral_constant<int, CVVDP_DTYPE_U8>{}, integral_constant<int, CVVDP_EOTF_PQ>{}, it0);
+                else convert_yuv(integral_constant<int, CVVDP_DTYPE_U8>{}, integral_constant<int, -1>{}, it0);
+            } else {
+                if (e == CVVDP_EOTF_SRGB) convert_yuv(integral_constant<int, CVVDP_DTYPE_U16>{}, integral_constant<int, CVVDP_EOTF_SRGB>{}, it0);
+                else if (e == CVVDP_EOTF_PQ) convert_yuv(integral_constant<int, CVVDP_DTYPE_U16>{}, integral_constant<int, CVVDP_EOTF_PQ>{}, it0);
+                else convert_yuv(integral_constant<int, CVVDP_DTYPE_U16>{}, integral_constant<int, -1>{}, it0);
+            }
+            return;
+        }
+        if constexpr (SRC == CVVDP_T2S_ANY) {
+            switch (conv_mode) {  // uniform over the grid
             CVVDP_CONV_CASE(1, CVVDP_DTYPE_F32, CVVDP_EOTF_SRGB, 4)
             CVVDP_CONV_CASE(2, CVVDP_DTYPE_F32, CVVDP_EOTF_PQ, 4)
             CVVDP_CONV_CASE(3, CVVDP_DTYPE_F32, CVVDP_EOTF_LINEAR, 4)
@@ -660,6 +776,7 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
             CVVDP_CONV_CASE(8, CVVDP_DTYPE_U16, CVVDP_EOTF_PQ, 2)
             CVVDP_CONV_CASE(9, CVVDP_DTYPE_U16, CVVDP_EOTF_LINEAR, 2)
             default: convert_body(integral_constant<int, -1>{}, integral_constant<int, -1>{}, integral_constant<int, 0>{}, it0);
+            }
         }
 #undef CVVDP_CONV_CASE
     };
@@ -704,7 +821,7 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
                             o3 = fma2(bc2(a.taps[3][k]), r0[sl], o3);
                         }
                         outp[0] = make_float4(o0.x, o1.x, o2.x, o3.x);
-                        outp[32] = make_float4(o0.y, o1.y, o2.y, o3.y);
+                        outp[PB] = make_float4(o0.y, o1.y, o2.y, o3.y);
                         outp += ostep;
                     }
                 }

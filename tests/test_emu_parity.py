@@ -392,6 +392,28 @@ def test_resize_kernel_matches_torch_interpolate(mode, mock_device):
         ctx.resize(src.data_ptr(), dst.data_ptr(), 3, H, W, OH, OW, "lanczos", True, None)
 
 
+@pytest.mark.parametrize("chroma,bit_depth,color_space,display", [("420", 8, "709", "standard_fhd"), ("422", 10, "2020", "standard_hdr_pq"),
+                                                               ("444", 8, "709", "standard_hdr_hlg"), ("420", 10, "2020", "standard_hdr_pq")])
+def test_yuv_two_stage_front_end(chroma, bit_depth, color_space, display, tmp_path, mock_device, monkeypatch):
+    """Rows of whole 64-pixel segments take the packed two-stage temporal kernel with the planar-YUV front end (direct
+    chroma taps); it must agree with the oracle and with the frame-by-frame path (k_frontend + generic kernel)."""
+    from golden.make_golden_yuv_synth import synth_yuv
+    F, H, W = 6, 34, 128
+    t, r = synth_yuv(91, F, H, W, chroma, bit_depth)
+    props = {"width": W, "height": H, "fps": 30, "bit_depth": bit_depth, "color_space": color_space, "chroma_ss": chroma}
+    tf, rf = str(tmp_path / cv.create_yuv_fname("t", props)), str(tmp_path / cv.create_yuv_fname("r", props))
+    t.tofile(tf), r.tofile(rf)
+    m = cv.cvvdp(display_name=display)
+    jod, fast = m.predict_video_source(cv.video_source_yuv_file(tf, rf, display_photometry=display))
+    jod_o, want = O.predict_yuv(tf, rf, display)
+    gu.assert_q_close(fast["Q_per_ch"], want["Q_per_ch"], "two-stage YUV vs oracle")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
+    vs = cv.video_source_yuv_file(tf, rf, display_photometry=display)
+    monkeypatch.setattr(vs, "yuv_readers", lambda: None)
+    _, slow = m.predict_video_source(vs)
+    gu.assert_q_close(fast["Q_per_ch"], slow["Q_per_ch"], "two-stage YUV vs frame by frame")
+
+
 def test_yuv_filename_metadata():
     p = cv.decode_video_props("/x/clip_1280x720_10b_444_2020_59.94fps.yuv")
     assert (p["width"], p["height"], p["bit_depth"], p["chroma_ss"], p["color_space"], p["fps"]) == (1280, 720, 10, "444", "2020", 59.94)

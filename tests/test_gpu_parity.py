@@ -264,6 +264,28 @@ def test_yuv_4k_file_streams_in_windows(tmp_path):
     gu.assert_q_close(whole["Q_per_ch"], rgb_path["Q_per_ch"], "4K yuv vs rgb path")
 
 
+@pytest.mark.parametrize("chroma,bit_depth,color_space,display", [("420", 8, "709", "standard_fhd"), ("422", 10, "2020", "standard_hdr_pq"),
+                                                               ("444", 8, "709", "standard_hdr_hlg"), ("420", 10, "2020", "standard_hdr_pq")])
+def test_yuv_two_stage_front_end(chroma, bit_depth, color_space, display, tmp_path, monkeypatch):
+    """Planar-YUV front end of the packed two-stage temporal kernel (rows of whole 64-pixel segments) against the oracle
+    and the frame-by-frame path."""
+    from golden.make_golden_yuv_synth import synth_yuv
+    F, H, W = 6, 34, 128
+    t, r = synth_yuv(91, F, H, W, chroma, bit_depth)
+    props = {"width": W, "height": H, "fps": 30, "bit_depth": bit_depth, "color_space": color_space, "chroma_ss": chroma}
+    tf, rf = str(tmp_path / cv.create_yuv_fname("t", props)), str(tmp_path / cv.create_yuv_fname("r", props))
+    t.tofile(tf), r.tofile(rf)
+    m = cv.cvvdp(display_name=display, device=DEV)
+    jod, fast = m.predict_video_source(cv.video_source_yuv_file(tf, rf, display_photometry=display))
+    jod_o, want = O.predict_yuv(tf, rf, display)
+    gu.assert_q_close(fast["Q_per_ch"], want["Q_per_ch"], "two-stage YUV vs oracle")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
+    vs = cv.video_source_yuv_file(tf, rf, display_photometry=display)
+    monkeypatch.setattr(vs, "yuv_readers", lambda: None)
+    _, slow = m.predict_video_source(vs)
+    gu.assert_q_close(fast["Q_per_ch"], slow["Q_per_ch"], "two-stage YUV vs frame by frame")
+
+
 def test_yuv_1080p_matches_oracle_and_rgb_path(tmp_path):
     """1080p 4:2:0 8-bit clip: fused YUV path == (oracle RGB conversion -> fp32 RGB path)."""
     from golden.make_golden_yuv_synth import synth_yuv  # shared synthetic YUV generator
