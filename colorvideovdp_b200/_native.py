@@ -75,6 +75,8 @@ SYMBOLS = {
                                             C.c_void_p, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_process_host": (C.c_int, [C.c_void_p, C.POINTER(Clip), C.POINTER(Clip), C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p]),
+    "cvvdp_b200_process_files": (C.c_int, [C.c_void_p, C.POINTER(Clip), C.POINTER(Clip), C.c_int, C.c_int, C.c_int64,
+                                           C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "cvvdp_b200_pool": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cvvdp_b200_pool_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p]),
@@ -102,7 +104,7 @@ class KernelStat(C.Structure):
     _fields_ = [("kind", C.c_int32), ("level", C.c_int32), ("launches", C.c_int32), ("total_ms", C.c_float),
                 ("algo_bytes", C.c_double)]
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 RESIZE_MODES = {"nearest": 0, "bilinear": 1, "bicubic": 2, "area": 3}  # run_cvvdp.py:100
 
 
@@ -182,6 +184,10 @@ class Context:
     def process_host(self, test: Clip, ref: Clip, f0, f1, q_ptr, hm_ptr):
         self._check(self._lib.cvvdp_b200_process_host(self._h, C.byref(test), C.byref(ref), int(f0), int(f1),
                                                       q_ptr, hm_ptr), "process_host")
+
+    def process_files(self, test: Clip, ref: Clip, fd_test, fd_ref, off_test, off_ref, f0, f1, q_ptr, hm_ptr):
+        self._check(self._lib.cvvdp_b200_process_files(self._h, C.byref(test), C.byref(ref), fd_test, fd_ref, off_test,
+                                                       off_ref, f0, f1, q_ptr, hm_ptr), "process_files")
 
     def pool(self, q_ptr, B, Cc, F, L, jod_ptr):
         self._check(self._lib.cvvdp_b200_pool(self._h, q_ptr, B, Cc, F, L, jod_ptr), "pool")

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -385,8 +386,8 @@ void needed_frames(const cvvdp_b200_ctx *ctx, int f0, int f1, int *lo, int *hi) 
     *hi = mx + 1;
 }
 
-int check_clip(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *c, int lo, int hi, const char *name) {
-    if (!c || !c->data) return fail(ctx, CVVDP_ERR_INVALID, "%s clip is null", name);
+int check_clip(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *c, int lo, int hi, const char *name, bool from_file = false) {
+    if (!c || (!c->data && !from_file)) return fail(ctx, CVVDP_ERR_INVALID, "%s clip is null", name);
     if (lo < c->frame0 || hi > c->frame0 + c->n_frames)
         return fail(ctx, CVVDP_ERR_INVALID, "%s view holds frames [%d,%d) but frames [%d,%d) are needed", name,
                     c->frame0, c->frame0 + c->n_frames, lo, hi);
@@ -1169,25 +1170,43 @@ bool is_pageable(const void *p) {
 #endif
 }
 
-void parallel_memcpy(char *dst, const char *src, size_t n, int threads) {
-    if (threads <= 1 || n < ((size_t)4 << 20)) {
-        memcpy(dst, src, n);
-        return;
+// Where the host bytes of a clip live: memory (`ptr`) or a file (`fd` >= 0, `ptr` then is the byte offset).
+struct HostSrc {
+    const char *ptr;
+    int fd;
+};
+// One part of a copy into a pinned slot; false on a short read.
+bool copy_part(char *dst, const HostSrc &src, size_t off, size_t n) {
+    if (src.fd < 0) {
+        memcpy(dst, src.ptr + off, n);
+        return true;
     }
+    size_t done = 0;
+    while (done < n) {  // the page cache hands the bytes over without mapping the file (no page-table population, no unmap)
+        const ssize_t r = pread(src.fd, dst + done, n - done, (off_t)((uintptr_t)src.ptr + off + done));
+        if (r <= 0) return false;
+        done += (size_t)r;
+    }
+    return true;
+}
+bool parallel_copy(char *dst, const HostSrc &src, size_t n, int threads) {
+    if (threads <= 1 || n < ((size_t)4 << 20)) return copy_part(dst, src, 0, n);
     const size_t part = ((n + threads - 1) / threads + 4095) / 4096 * 4096;
     std::vector<std::thread> pool;
+    std::vector<char> ok((size_t)threads, 1);
     for (int t = 1; t < threads; ++t) {
         const size_t o = (size_t)t * part;
         if (o >= n) break;
-        pool.emplace_back([=]() { memcpy(dst + o, src + o, std::min(part, n - o)); });
+        pool.emplace_back([=, &ok]() { ok[(size_t)t] = copy_part(dst + o, src, o, std::min(part, n - o)) ? 1 : 0; });
     }
-    memcpy(dst, src, std::min(part, n));
+    ok[0] = copy_part(dst, src, 0, std::min(part, n)) ? 1 : 0;
     for (auto &th : pool) th.join();
+    return std::all_of(ok.begin(), ok.end(), [](char c) { return c != 0; });
 }
 
-int upload(cvvdp_b200_ctx *ctx, void *dst, const void *src, size_t bytes, bool pageable, cudaStream_t st) {
-    if (!pageable) {
-        CU_CHECK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+int upload(cvvdp_b200_ctx *ctx, void *dst, HostSrc src, size_t bytes, bool pageable, cudaStream_t st) {
+    if (!pageable && src.fd < 0) {
+        CU_CHECK(ctx, cudaMemcpyAsync(dst, src.ptr, bytes, cudaMemcpyHostToDevice, st));
         return CVVDP_OK;
     }
     const size_t slot_bytes = (size_t)32 << 20;
@@ -1208,7 +1227,10 @@ int upload(cvvdp_b200_ctx *ctx, void *dst, const void *src, size_t bytes, bool p
         const int slot = ctx->pin_next;
         ctx->pin_next = (ctx->pin_next + 1) % cvvdp_b200_ctx::kPinSlots;
         CU_CHECK(ctx, cudaEventSynchronize(ctx->pin_done[slot]));  // the copy that last used this slot has left it
-        parallel_memcpy((char *)ctx->pin_buf[slot], (const char *)src + off, len, threads);
+        HostSrc part = src;
+        part.ptr += off;
+        if (!parallel_copy((char *)ctx->pin_buf[slot], part, len, threads))
+            return fail(ctx, CVVDP_ERR_INVALID, "short read from the clip file (fd %d)", src.fd);
         CU_CHECK(ctx, cudaMemcpyAsync((char *)dst + off, ctx->pin_buf[slot], len, cudaMemcpyHostToDevice, st));
         CU_CHECK(ctx, cudaEventRecord(ctx->pin_done[slot], st));
     }
@@ -1248,8 +1270,28 @@ HostLayout analyse_layout(const cvvdp_b200_clip *c, const long long extent[5]) {
 }
 }  // namespace
 
+namespace {
+int process_host_impl(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref, const int fds[2],
+                      const long long file_off[2], int frame_begin, int frame_end, float *q_per_ch_host, void *heatmap_host);
+}
 int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref,
                             int frame_begin, int frame_end, float *q_per_ch_host, void *heatmap_host) {
+    const int fds[2] = {-1, -1};
+    const long long offs[2] = {0, 0};
+    return process_host_impl(ctx, test, ref, fds, offs, frame_begin, frame_end, q_per_ch_host, heatmap_host);
+}
+int cvvdp_b200_process_files(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref, int fd_test,
+                             int fd_ref, int64_t offset_test, int64_t offset_ref, int frame_begin, int frame_end,
+                             float *q_per_ch_host, void *heatmap_host) {
+    if (!ctx) return CVVDP_ERR_INVALID;
+    if (fd_test < 0 || fd_ref < 0 || offset_test < 0 || offset_ref < 0) return fail(ctx, CVVDP_ERR_INVALID, "bad file descriptor or offset");
+    const int fds[2] = {fd_test, fd_ref};
+    const long long offs[2] = {(long long)offset_test, (long long)offset_ref};
+    return process_host_impl(ctx, test, ref, fds, offs, frame_begin, frame_end, q_per_ch_host, heatmap_host);
+}
+namespace {
+int process_host_impl(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref, const int fds[2],
+                      const long long file_off[2], int frame_begin, int frame_end, float *q_per_ch_host, void *heatmap_host) {
     if (!ctx) return CVVDP_ERR_INVALID;
     if (!ctx->planned) return fail(ctx, CVVDP_ERR_STATE, "plan must be called before process");
     if (frame_begin < 0 || frame_end > ctx->job.n_frames || frame_begin >= frame_end)
@@ -1262,8 +1304,8 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
     CU_CHECK(ctx, dev_guard.err);
     int lo, hi, rc;
     needed_frames(ctx, frame_begin, frame_end, &lo, &hi);
-    if ((rc = check_clip(ctx, test, lo, hi, "test")) != CVVDP_OK) return rc;
-    if ((rc = check_clip(ctx, ref, lo, hi, "reference")) != CVVDP_OK) return rc;
+    if ((rc = check_clip(ctx, test, lo, hi, "test", fds[0] >= 0)) != CVVDP_OK) return rc;
+    if ((rc = check_clip(ctx, ref, lo, hi, "reference", fds[1] >= 0)) != CVVDP_OK) return rc;
 
     const long long ext_t[5] = {test->stride[0] ? job.batch : 1, job.in_channels, 0, job.height, job.width};
     const long long ext_r[5] = {ref->stride[0] ? job.batch : 1, job.in_channels, 0, job.height, job.width};
@@ -1279,7 +1321,7 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
         return fail(ctx, CVVDP_ERR_UNSUPPORTED,
                     "host clips must store each frame densely (dims with a stride below the frame stride must tile it)");
     const cvvdp_b200_clip *clips[2] = {test, ref};
-    const bool pageable[2] = {is_pageable(test->data), is_pageable(ref->data)};
+    const bool pageable[2] = {fds[0] >= 0 || is_pageable(test->data), fds[1] >= 0 || is_pageable(ref->data)};
     const size_t esz = dtype_size(job.dtype);
     // The upload is pipelined in chunks smaller than the device-resident block size so that compute
     // starts after the first few frames have arrived.  The staging area is a RING of frames (frame f at
@@ -1396,8 +1438,11 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
                 for (int fa = new_lo; fa < whi;) {
                     const int slot = fa % ring;
                     const int run = std::min(whi - fa, ring - slot);
-                    if ((rc = upload(ctx, (char *)ctx->stage[0].buf[v] + (dbase + (long long)slot * sF) * esz,
-                                     (const char *)c->data + (hbase + (long long)(fa - c->frame0) * sF) * esz,
+                    HostSrc hs;  // a memory address, or the byte offset in the file
+                    hs.fd = fds[v];
+                    hs.ptr = (fds[v] >= 0 ? (const char *)(uintptr_t)file_off[v] : (const char *)c->data) +
+                             (hbase + (long long)(fa - c->frame0) * sF) * esz;
+                    if ((rc = upload(ctx, (char *)ctx->stage[0].buf[v] + (dbase + (long long)slot * sF) * esz, hs,
                                      (size_t)run * sF * esz, pageable[v], ctx->copy_stream)) != CVVDP_OK)
                         return rc;
                     fa += run;
@@ -1444,6 +1489,7 @@ int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, co
     }
     return CVVDP_OK;
 }
+}  // namespace
 
 int cvvdp_b200_pool_device(cvvdp_b200_ctx *ctx, const float *q_dev, int B, int C, int F, int L, float *jod_dev, void *stream) {
     if (!ctx || !q_dev || !jod_dev) return fail(ctx, CVVDP_ERR_INVALID, "null argument");

@@ -296,17 +296,27 @@ class cvvdp(vq_metric):
         while cur < f1:
             end = min(cur + per, f1)
             wlo, whi = self._needed_frames(cur, end, fl, F)
-            windows = [r.frames_window(off + wlo, whi - wlo) for r in (tr, rr)]  # kept alive until the call returns
+            from_files = all(hasattr(r, "fileno") for r in (tr, rr))
+            # .yuv files: the library reads the window from the descriptors; pipes: from the readers' buffers
+            windows = [] if from_files else [r.frames_window(off + wlo, whi - wlo) for r in (tr, rr)]
             clips = []
-            for w in windows:
+            for k in range(2):
                 c = N.Clip()
-                c.data = w.ctypes.data
+                c.data = None if from_files else windows[k].ctypes.data
                 c.stride[0], c.stride[2] = 0, tr.frame_pixels
                 c.frame0, c.n_frames = wlo, whi - wlo
                 clips.append(c)
-            # process_host returns the whole [1,C,F,L] array, zero outside [cur, end): collect the windows
+            # process_host / process_files return the whole [1,C,F,L] array, zero outside [cur, end): collect the windows
             Qw = Qh if (cur == f0 and end == f1) else torch.empty_like(Qh)
-            self._ctx.process_host(clips[0], clips[1], cur, end, Qw.data_ptr(), hmh.data_ptr() if hmh is not None else None)
+            hm_ptr = hmh.data_ptr() if hmh is not None else None
+            if from_files:
+                for r in (tr, rr):
+                    if off + whi > r.frames:
+                        raise RuntimeError("The frame index is outside the range of available frames")
+                self._ctx.process_files(clips[0], clips[1], tr.fileno(), rr.fileno(), (off + wlo) * tr.frame_bytes,
+                                        (off + wlo) * rr.frame_bytes, cur, end, Qw.data_ptr(), hm_ptr)
+            else:
+                self._ctx.process_host(clips[0], clips[1], cur, end, Qw.data_ptr(), hm_ptr)
             if Qw is not Qh:
                 Qh[:, :, cur:end] = Qw[:, :, cur:end]
             cur = end

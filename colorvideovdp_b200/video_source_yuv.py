@@ -190,9 +190,24 @@ class YUVReader(yuv_frame_decoder):
         v = mm[o + self.y_pixels + self.uv_pixels:o + self.y_pixels + 2 * self.uv_pixels]
         return (np.reshape(Y, self.y_shape, "C"), np.reshape(u, self.uv_shape, "C"), np.reshape(v, self.uv_shape, "C"))
 
+    def fileno(self):
+        """A read-only descriptor of the file, for the library to pread() frame windows from (opened on first use)."""
+        if getattr(self, "_fd", None) is None:
+            self._fd = os.open(self.file_name, os.O_RDONLY)
+        return self._fd
+
+    def __del__(self):
+        fd = getattr(self, "_fd", None)
+        if fd is not None:
+            try:
+                os.close(fd)
+            except OSError:
+                pass
+            self._fd = None
+
     def frames_window(self, first, count):
         """Frames [first, first+count) as one contiguous host array [count * frame_pixels] -- a view of the file
-        mapping, no copy: the native upload path reads it with its own threads."""
+        mapping, no copy."""
         if first < 0 or first + count > self.frames:
             raise RuntimeError("The frame index is outside the range of available frames")
         return self._map()[first * self.frame_pixels:(first + count) * self.frame_pixels]

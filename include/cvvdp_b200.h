@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define CVVDP_B200_ABI_VERSION 5
+#define CVVDP_B200_ABI_VERSION 6
 #define CVVDP_MAX_BANDS 16
 #define CVVDP_MAX_FILTER_LEN 129
 #define CVVDP_CSF_LUT_N 32
@@ -172,6 +172,14 @@ int cvvdp_b200_process_device(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, 
  * range); heatmap_host: fp16 or NULL, only the frames of the range are written. */
 int cvvdp_b200_process_host(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref,
                             int frame_begin, int frame_end, float *q_per_ch_host, void *heatmap_host);
+
+/* Same, with the frames read straight from two open files (raw planar .yuv files, video_source_yuv.py:77-144, or any
+ * file of dense frames): `data` of the views is ignored; element i of the view of video v lives at byte
+ * offset_v + i * sizeof(dtype) of fd_v, addressed through the strides like memory.  The upload threads pread() into the
+ * pinned staging slots, so the file is neither mapped nor copied on the way.  The descriptors stay the caller's. */
+int cvvdp_b200_process_files(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200_clip *ref, int fd_test,
+                             int fd_ref, int64_t offset_test, int64_t offset_ref, int frame_begin, int frame_end,
+                             float *q_per_ch_host, void *heatmap_host);
 
 /* do_pooling_and_jods + met2jod (cvvdp_metric.py:610-658) on a host Q_per_ch [B,C,F,L]; jod_host: [B]. */
 int cvvdp_b200_pool(cvvdp_b200_ctx *ctx, const float *q_per_ch_host, int B, int C, int F, int L, float *jod_host);

@@ -414,6 +414,42 @@ def test_yuv_two_stage_front_end(chroma, bit_depth, color_space, display, tmp_pa
     gu.assert_q_close(fast["Q_per_ch"], slow["Q_per_ch"], "two-stage YUV vs frame by frame")
 
 
+def test_yuv_files_are_read_through_descriptors(tmp_path, mock_device, monkeypatch):
+    """.yuv pairs reach the library as file descriptors (cvvdp_b200_process_files: pread into the staging slots, no
+    mapping); several windows, an offset into the clip, and a file that ends early."""
+    from colorvideovdp_b200 import _native as N
+    name = "yuv_422_8b_709_12x40x48_sym"
+    tf, rf, z, meta = gu.write_yuv_case(name, str(tmp_path))
+    m = cv.cvvdp(display_name=meta["display"], temp_padding=meta["padding"], gpu_mem=1e-6)
+    calls = []
+    pf = m._ctx.process_files
+    monkeypatch.setattr(m._ctx, "process_files", lambda *a: (calls.append(a[2:8]), pf(*a))[1])
+    monkeypatch.setattr(m, "yuv_chunk_bytes", 1)
+    _, stats = m.predict_video_source(cv.video_source_yuv_file(tf, rf, display_photometry=meta["display"]))
+    gu.assert_q_close(stats["Q_per_ch"], z["Q_per_ch"], name)
+    assert len(calls) > 1 and calls[0][4:] == (0, calls[0][5]) and calls[-1][5] == 12
+    # frames 4.. of the clip as a clip of their own == the same frames cut out of the files
+    vs = cv.video_source_yuv_file(tf, rf, display_photometry=meta["display"])
+    vs.set_offset(4)
+    vs.set_num_frames(8)
+    _, tail = m.predict_video_source(vs)
+    fb = vs.test_vidr.frame_bytes
+    tf2, rf2 = str(tmp_path / "cut" / os.path.basename(tf)), str(tmp_path / "cut" / os.path.basename(rf))
+    os.makedirs(str(tmp_path / "cut"))
+    for src, dst in ((tf, tf2), (rf, rf2)):
+        with open(src, "rb") as f, open(dst, "wb") as g:
+            g.write(f.read()[4 * fb:])
+    _, cut = m.predict_video_source(cv.video_source_yuv_file(tf2, rf2, display_photometry=meta["display"]))
+    assert np.array_equal(tail["Q_per_ch"], cut["Q_per_ch"])
+    # a reference file that loses its last bytes after the reader counted its frames
+    vs = cv.video_source_yuv_file(tf, rf, display_photometry=meta["display"])
+    vs.reference_vidr.fileno()
+    with open(rf, "r+b") as f:
+        f.truncate(11 * fb + 5)
+    with pytest.raises(N.NativeError, match="short read"):
+        m.predict_video_source(vs)
+
+
 def test_yuv_filename_metadata():
     p = cv.decode_video_props("/x/clip_1280x720_10b_444_2020_59.94fps.yuv")
     assert (p["width"], p["height"], p["bit_depth"], p["chroma_ss"], p["color_space"], p["fps"]) == (1280, 720, 10, "444", "2020", 59.94)
