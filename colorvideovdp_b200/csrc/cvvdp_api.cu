@@ -8,6 +8,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -506,10 +509,15 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             if (((uintptr_t)cvw.data) % 16 || (cvw.s[0] * es) % 16 || (cvw.s[1] * es) % 16 || (cvw.s[2] * es) % 16) dense = false;
         }
         // planar YUV: rows of whole 64-pixel segments (the two pixels of a thread share a row), frames anywhere
-        const bool yuv_2s = is_yuv && job.width % 64 == 0 && (job.dtype == CVVDP_DTYPE_U8 || job.dtype == CVVDP_DTYPE_U16);
+        bool yuv_2s = is_yuv && job.width % 64 == 0 && (job.dtype == CVVDP_DTYPE_U8 || job.dtype == CVVDP_DTYPE_U16);
+        for (int v = 0; v < 2 && yuv_2s; ++v) {  // (the 16-byte pieces of the luma and chroma rows must be aligned)
+            const ClipView &cvw = ta.clip[v];
+            const long long es = (long long)dtype_size(job.dtype);
+            if (((uintptr_t)cvw.data) % 16 || (cvw.s[0] * es) % 16 || (cvw.s[2] * es) % 16) yuv_2s = false;
+        }
         if (yuv_2s) dense = true;
-        const int t_esz = is_yuv ? 0 : (use_lut ? 1 : (int)dtype_size(job.dtype));
-        const size_t smem_2s = t2s_smem_bytes(info.filter_len, t_esz);
+        const int t_esz = use_lut ? 1 : (int)dtype_size(job.dtype);
+        const size_t smem_2s = t2s_smem_bytes(info.filter_len, t_esz, is_yuv ? 5 : 3);
         bool taps_symmetric = true;  // exact: the two-stage kernel adds mirrored frames before multiplying
         for (int c = 0; c < 4; ++c)
             for (int k = 0; k < info.filter_len / 2; ++k)
@@ -1189,18 +1197,80 @@ bool copy_part(char *dst, const HostSrc &src, size_t off, size_t n) {
     }
     return true;
 }
-bool parallel_copy(char *dst, const HostSrc &src, size_t n, int threads) {
-    if (threads <= 1 || n < ((size_t)4 << 20)) return copy_part(dst, src, 0, n);
-    const size_t part = ((n + threads - 1) / threads + 4095) / 4096 * 4096;
-    std::vector<std::thread> pool;
-    std::vector<char> ok((size_t)threads, 1);
-    for (int t = 1; t < threads; ++t) {
-        const size_t o = (size_t)t * part;
-        if (o >= n) break;
-        pool.emplace_back([=, &ok]() { ok[(size_t)t] = copy_part(dst + o, src, o, std::min(part, n - o)) ? 1 : 0; });
+// Persistent helper threads for the staging copies (a slot is 32 MB, i.e. well under a millisecond of copying: creating
+// and joining threads per slot cost a fifth of that).  One pool per process; the caller works on the parts as well.
+class CopyPool {
+  public:
+    explicit CopyPool(int helpers) {
+        for (int i = 0; i < helpers; ++i) workers_.emplace_back([this]() { loop(); });
     }
-    ok[0] = copy_part(dst, src, 0, std::min(part, n)) ? 1 : 0;
-    for (auto &th : pool) th.join();
+    ~CopyPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_work_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void run(int parts, const std::function<void(int)> &fn) {
+        std::unique_lock<std::mutex> lk(m_);
+        fn_ = &fn;
+        parts_ = parts;
+        next_ = 0;
+        pending_ = parts;
+        ++gen_;
+        cv_work_.notify_all();
+        take_parts(lk);
+        cv_done_.wait(lk, [this]() { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void take_parts(std::unique_lock<std::mutex> &lk) {  // called with the lock held
+        while (fn_ != nullptr && next_ < parts_) {
+            const int i = next_++;
+            const std::function<void(int)> *fn = fn_;
+            lk.unlock();
+            (*fn)(i);
+            lk.lock();
+            if (--pending_ == 0) cv_done_.notify_all();
+        }
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(m_);
+        unsigned long long seen = 0;
+        for (;;) {
+            cv_work_.wait(lk, [&]() { return stop_ || gen_ != seen; });
+            if (stop_) return;
+            seen = gen_;
+            take_parts(lk);
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int parts_ = 0, next_ = 0, pending_ = 0;
+    unsigned long long gen_ = 0;
+    bool stop_ = false;
+};
+
+bool parallel_copy(char *dst, const HostSrc &src, size_t n, int threads) {
+    // CVVDP_B200_FORCE_STAGING=pool (test hook): tiny parts, so that small test clips go through the pool as well
+    const char *hook = getenv("CVVDP_B200_FORCE_STAGING");
+    const bool tiny = hook != nullptr && strcmp(hook, "pool") == 0;
+    const size_t part = tiny ? (size_t)16 << 10 : (size_t)1 << 20;  // 1 MB parts, handed out dynamically
+    if (threads <= 1 || n < 4 * part) return copy_part(dst, src, 0, n);
+    static CopyPool pool(threads - 1);
+    static std::mutex one_at_a_time;  // contexts of several threads share the pool
+    std::lock_guard<std::mutex> guard(one_at_a_time);
+    const int parts = (int)((n + part - 1) / part);
+    std::vector<char> ok((size_t)parts, 1);
+    const std::function<void(int)> fn = [&](int i) {
+        const size_t o = (size_t)i * part;
+        ok[(size_t)i] = copy_part(dst + o, src, o, std::min(part, n - o)) ? 1 : 0;
+    };
+    pool.run(parts, fn);
     return std::all_of(ok.begin(), ok.end(), [](char c) { return c != 0; });
 }
 
@@ -1221,7 +1291,7 @@ int upload(cvvdp_b200_ctx *ctx, void *dst, HostSrc src, size_t bytes, bool pagea
         }
         ctx->pin_bytes = slot_bytes;
     }
-    static const int threads = (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    static const int threads = (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
     for (size_t off = 0; off < bytes; off += slot_bytes) {
         const size_t len = std::min(slot_bytes, bytes - off);
         const int slot = ctx->pin_next;

@@ -536,10 +536,10 @@ struct T2SGeom {
     static constexpr int RP = FL + 1;   // ring period (even)
     static constexpr int G = RP / 2;    // frames per chunk
 };
-// dynamic shared memory: [warps][G][3][64*esz] raw bytes, then [G][3][threads] float2
-__host__ __device__ inline size_t t2s_smem_bytes(int fl, int esz) {
+// dynamic shared memory: [warps][G][3 (planar YUV: 5)][64*esz] raw bytes, then [G][3][threads] float2
+__host__ __device__ inline size_t t2s_smem_bytes(int fl, int esz, int rows = 3) {  // rows: 3 channels, or Y + 2 x 2 chroma rows
     const int G = (fl + 1) / 2;
-    return (size_t)(CVVDP_T2S_THREADS / 32) * G * 3 * 64 * esz + (size_t)G * 3 * CVVDP_T2S_THREADS * 8;
+    return (size_t)(CVVDP_T2S_THREADS / 32) * G * rows * 64 * esz + (size_t)G * 3 * CVVDP_T2S_THREADS * 8;
 }
 // SRC: where the frames come from -- 0: dense planes of any dtype (raw stage filled by cp.async), 1: 8-bit planes through
 // the 256-entry EOTF table, 2: planar YUV frames read straight from global memory (the chroma taps of neighbouring
@@ -567,11 +567,14 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
     if (wp >= npix) return;  // whole 64-pixel segments only (npix % 64 == 0); no block-level barrier below
     const ClipView &cv = a.clip[v];
-    const int esz = USE_LUT ? 1 : (SRC == CVVDP_T2S_YUV ? 0 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2)));  // YUV: no raw stage
+    constexpr bool YUV = SRC == CVVDP_T2S_YUV;
+    const int esz = USE_LUT ? 1 : (a.dtype == CVVDP_DTYPE_F32 ? 4 : (a.dtype == CVVDP_DTYPE_U8 ? 1 : 2));
     const int row_bytes = 64 * esz;          // one (channel, frame) segment of this warp
-    const int frame_bytes = 3 * row_bytes;   // slot of one frame in the raw stage (cin == 1 uses the first third)
-    const int cpc = row_bytes / 16;          // 16-byte pieces per channel segment
-    const int ppf = SRC == CVVDP_T2S_YUV ? 1 : a.cin * cpc;  // pieces per frame
+    // slot of one frame in the raw stage: three channel segments (cin == 1 uses the first), or -- planar YUV -- the luma
+    // segment and two rows of 64 samples of each chroma plane around it
+    const int frame_bytes = (YUV ? 5 : 3) * row_bytes;
+    const int cpc = row_bytes / 16;          // 16-byte pieces per segment
+    const int ppf = YUV ? 5 * cpc : a.cin * cpc;  // pieces per frame
     unsigned char *raw = smem_raw + (size_t)warp * G * frame_bytes;
     float2 *dkl = reinterpret_cast<float2 *>(smem_raw + (size_t)(CVVDP_T2S_THREADS / 32) * G * frame_bytes) + tid;
     const long long fstride = cv.s[2] * esz, cstride = cv.s[1] * esz;
@@ -593,8 +596,23 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     const int q32 = 32 / ppf, r32 = 32 - q32 * ppf;  // 32 = q32 * ppf + r32
     const int g_first = lane / ppf, rem_first = lane - g_first * ppf;
     const int cpc_shift = esz == 1 ? 2 : (esz == 2 ? 3 : 4);
+    // Planar YUV (video_source_yuv.py:153-233): the warp's 64 pixels lie in one row y (rows are whole segments).  Staged per
+    // frame: the 64 luma samples and, of each chroma plane, rows j0 and j1 (yuv_chroma_taps) from sample yuv_cs on --
+    // one 16-byte piece to the left of the segment's first chroma sample, so that the left neighbour is there and every
+    // piece stays 16-byte aligned; pieces that start outside the row are skipped (the taps clamp to the row).
+    int yuv_j0 = 0, yuv_j1 = 0, yuv_cs = 0, yuv_cw = 0, yuv_ypix = 0, yuv_uvpix = 0;  // (a frame has fewer than 2^31 samples)
+    float yuv_ly = 0.f;
+    if (YUV) {
+        yuv_cw = a.yuv.chroma == 444 ? a.W : a.W / 2;
+        yuv_ypix = (int)npix;
+        yuv_uvpix = yuv_cw * (a.yuv.chroma == 420 ? a.H / 2 : a.H);
+        const int y = (int)(wp / a.W), x0 = (int)(wp - (long long)y * a.W);
+        int i0, i1;
+        float lx_unused;
+        yuv_chroma_taps(a.yuv, y, x0, i0, i1, yuv_j0, yuv_j1, lx_unused, yuv_ly);
+        yuv_cs = a.yuv.chroma == 444 ? x0 : x0 / 2 - 16 / esz;
+    }
     auto issue_chunk = [&](int c) {
-        if (SRC == CVVDP_T2S_YUV) return;  // no raw stage
         int g = g_first, rem = rem_first;
         const int it0 = c * G;
         while (g < G) {
@@ -603,7 +621,15 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
                 const int t = a.f0 - (FL - 1) + it;
                 const int slot = frame_slot(cv, t >= 0 ? t : temporal_source_frame(a, t));
                 const int ch = rem >> cpc_shift, part = rem & (cpc - 1);
-                cp_async16(raw + g * frame_bytes + ch * row_bytes + part * 16, wsrc + (long long)slot * fstride + ch * cstride + part * 16);
+                if (!YUV || ch == 0) {
+                    cp_async16(raw + g * frame_bytes + ch * row_bytes + part * 16, wsrc + (long long)slot * fstride + ch * cstride + part * 16);
+                } else {  // segment 1 + 2 * plane + row
+                    const int ps = yuv_cs + part * (16 / esz);
+                    if (ps >= 0 && ps < yuv_cw) {
+                        const long long so = yuv_ypix + ((ch - 1) >> 1) * (long long)yuv_uvpix + (long long)(((ch - 1) & 1) ? yuv_j1 : yuv_j0) * yuv_cw + ps;
+                        cp_async16(raw + g * frame_bytes + ch * row_bytes + part * 16, wsrc + (long long)slot * fstride + (so - wp) * esz);
+                    }
+                }
             }
             g += q32;
             rem += r32;
@@ -652,33 +678,23 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
             dkl[(g * 3 + 2) * CVVDP_T2S_THREADS] = d2;
         }
     };
-    // Planar YUV (SRC == CVVDP_T2S_YUV, video_source_yuv.py:153-233): the thread's pixels (y, x) and (y, x + 1), x even, need
-    // the chroma columns L, M, R and rows j0, j1 of each plane -- six samples instead of eight: with subsampled chroma
-    // (k = x / 2) L = max(k-1, 0), M = k, R = min(k+1, cw-1), pixel x blends (L, M) with weight 0.75 (0 at k = 0, where
-    // torch clamps the source coordinate) and pixel x + 1 blends (M, R) with 0.25; 4:4:4 takes L = x, M = R = x + 1 with
-    // weights 0.  Rows as in yuv_chroma_taps.  The limited-range clip of a chroma sample is done as saturate(c + 0.5)
-    // and the 0.5 taken off after the blend (the weights add up to one).
-    int yuv_oL = 0, yuv_dM = 0, yuv_dR = 0, yuv_dj = 0, yuv_ypix = 0, yuv_uvpix = 0;  // (a frame has fewer than 2^31 samples)
+    // Planar YUV front end: the thread's pixels (y, x) and (y, x + 1), x even, need the chroma columns L, M, R of rows j0, j1
+    // of each plane -- six samples instead of eight: with subsampled chroma (k = x / 2) L = max(k-1, 0), M = k,
+    // R = min(k+1, cw-1), pixel x blends (L, M) with weight 0.75 (0 at k = 0, where torch clamps the source coordinate) and
+    // pixel x + 1 blends (M, R) with 0.25; 4:4:4 takes L = x, M = R = x + 1 with weights 0.  The limited-range clip of a
+    // chroma sample is done as saturate(c + 0.5) and the 0.5 taken off after the blend (the weights add up to one).
+    int yuv_iL = 0, yuv_iM = 0, yuv_iR = 0;  // sample indices in a staged chroma row
     float2 yuv_lx = make_float2(0.f, 0.f);
-    float yuv_ly = 0.f;
-    if (SRC == CVVDP_T2S_YUV) {
-        const int cwid = a.yuv.chroma == 444 ? a.W : a.W / 2, chei = a.yuv.chroma == 420 ? a.H / 2 : a.H;
-        yuv_ypix = (int)npix;
-        yuv_uvpix = cwid * chei;
-        const long long p0 = wp + 2 * lane;
-        const int y = (int)(p0 / a.W), x = (int)(p0 - (long long)y * a.W);
-        int i0, i1, j0, j1;
-        float lx_unused;
-        yuv_chroma_taps(a.yuv, y, x, i0, i1, j0, j1, lx_unused, yuv_ly);
-        yuv_dj = (j1 - j0) * cwid;
+    if (YUV) {
+        const int x = (int)(wp % a.W) + 2 * lane;
         if (a.yuv.chroma == 444) {
-            yuv_oL = j0 * cwid + x;
-            yuv_dM = yuv_dR = 1;
+            yuv_iL = x - yuv_cs;
+            yuv_iM = yuv_iR = x + 1 - yuv_cs;
         } else {
-            const int k = x >> 1, cl = max(k - 1, 0);
-            yuv_oL = j0 * cwid + cl;
-            yuv_dM = k - cl;
-            yuv_dR = min(k + 1, cwid - 1) - cl;
+            const int k = x >> 1;
+            yuv_iL = max(k - 1, 0) - yuv_cs;
+            yuv_iM = k - yuv_cs;
+            yuv_iR = min(k + 1, yuv_cw - 1) - yuv_cs;
             yuv_lx = make_float2(k == 0 ? 0.f : 0.75f, 0.25f);
         }
     }
@@ -688,24 +704,21 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
         const YuvDev &yu = a.yuv;
         const float c_off = 0.5f - yu.co;
         const float2 wx1 = yuv_lx, wx0 = make_float2(1.f - yuv_lx.x, 1.f - yuv_lx.y);
-#pragma unroll 1
+        const int row1 = yuv_j1 != yuv_j0 ? 64 : 0;  // samples from row j0 to row j1 in the stage
+#pragma unroll(FL >= 15 ? 1 : 2)  // (the 17-tap ring leaves no registers for a second frame in flight)
         for (int g = 0; g < G; ++g) {
-            if (it0 + g >= NI) break;  // uniform
-            const int t = a.f0 - (FL - 1) + it0 + g;
-            const int slot = frame_slot(cv, t >= 0 ? t : temporal_source_frame(a, t));
-            const S *fy = (const S *)cv.data + b * cv.s[0] + (long long)slot * cv.s[2] + wp + 2 * lane;
-            const S *fc = fy - (wp + 2 * lane) + yuv_ypix + yuv_oL;
-            const float Ya = __saturatef(fmaf(yu.yw, (float)__ldg(fy), -yu.yo)), Yb = __saturatef(fmaf(yu.yw, (float)__ldg(fy + 1), -yu.yo));
+            const S *q = (const S *)(raw + g * frame_bytes);
+            const float Ya = __saturatef(fmaf(yu.yw, (float)q[2 * lane], -yu.yo)), Yb = __saturatef(fmaf(yu.yw, (float)q[2 * lane + 1], -yu.yo));
             float2 uv[2];
 #pragma unroll
             for (int pl = 0; pl < 2; ++pl) {
-                const S *q = fc + pl * yuv_uvpix;
-                const float cL0 = __saturatef(fmaf(yu.cw, (float)__ldg(q), c_off));
-                const float cM0 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dM), c_off));
-                const float cR0 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dR), c_off));
-                const float cL1 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dj), c_off));
-                const float cM1 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dj + yuv_dM), c_off));
-                const float cR1 = __saturatef(fmaf(yu.cw, (float)__ldg(q + yuv_dj + yuv_dR), c_off));
+                const S *qc = q + 64 + 128 * pl;
+                const float cL0 = __saturatef(fmaf(yu.cw, (float)qc[yuv_iL], c_off));
+                const float cM0 = __saturatef(fmaf(yu.cw, (float)qc[yuv_iM], c_off));
+                const float cR0 = __saturatef(fmaf(yu.cw, (float)qc[yuv_iR], c_off));
+                const float cL1 = __saturatef(fmaf(yu.cw, (float)qc[row1 + yuv_iL], c_off));
+                const float cM1 = __saturatef(fmaf(yu.cw, (float)qc[row1 + yuv_iM], c_off));
+                const float cR1 = __saturatef(fmaf(yu.cw, (float)qc[row1 + yuv_iR], c_off));
                 const float2 top = fma2(wx0, make_float2(cL0, cM0), mul2(wx1, make_float2(cM0, cR0)));
                 const float2 bot = fma2(wx0, make_float2(cL1, cM1), mul2(wx1, make_float2(cM1, cR1)));
                 uv[pl] = add2(fma2(bc2(1.f - yuv_ly), top, mul2(bc2(yuv_ly), bot)), bc2(-0.5f));

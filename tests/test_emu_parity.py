@@ -537,9 +537,12 @@ def test_pageable_host_clips_take_the_bounce_buffers(mock_device, monkeypatch):
     tst, ref = synth.make_pair_u8(95, 24, 36, 64)
     m = cv.cvvdp(display_name="standard_fhd")
     _, direct = m.predict(tst, ref, frames_per_second=60)
-    monkeypatch.setenv("CVVDP_B200_FORCE_STAGING", "1")
+    monkeypatch.setenv("CVVDP_B200_FORCE_STAGING", "pool")  # (and parts small enough for the helper threads to share)
     _, staged = m.predict(tst, ref, frames_per_second=60)
     assert np.array_equal(direct["Q_per_ch"], staged["Q_per_ch"])
+    for _ in range(3):  # the pool is reused from call to call
+        _, again = m.predict(tst, ref, frames_per_second=60)
+        assert np.array_equal(direct["Q_per_ch"], again["Q_per_ch"])
 
 
 def test_mixed_dtypes_and_single_frame_slices(mock_device):
