@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Small end-to-end cases for compute-sanitizer (memcheck / racecheck / synccheck) on a B200: every kernel family
 runs at least once -- two-stage and generic temporal kernels, TMA reduce, band kernel with and without blur, with
-the heat map (raw and coloured) and in feature mode, baseband, finalize, pooling, host streaming path."""
+the heat map (raw and coloured) and in feature mode, baseband, finalize, pooling, host streaming path, the float /
+16-bit and planar-YUV front ends, file descriptors, resize."""
 import os
 import sys
 
@@ -33,5 +34,31 @@ feats, _ = m.extract_features(vs)
 out.append(float(feats[0].sum()))
 img_t, img_r = synth.make_pair_u8(10, 1, 40, 56)
 out.append(float(m.predict(t(img_t), t(img_r))[0]))   # image: three channels, tiny levels without blur
+# float / 16-bit front-end bodies of the two-stage kernel (fp32 sRGB, fp16 linear, uint16 PQ)
+tst, ref = synth.make_pair_u8(11, 5, 48, 128)
+m = cv.cvvdp(display_name="standard_fhd", device=dev)
+out.append(float(m.predict(t(tst).float() / 255, t(ref).float() / 255, frames_per_second=30)[0]))
+m = cv.cvvdp(display_name="standard_hdr_linear", device=dev)
+out.append(float(m.predict((t(tst).float() * 2).half(), (t(ref).float() * 2).half(), frames_per_second=30)[0]))
+m = cv.cvvdp(display_name="standard_hdr_pq", device=dev)
+out.append(float(m.predict((t(tst).to(torch.int32) * 200).to(torch.int16), (t(ref).to(torch.int32) * 200).to(torch.int16), frames_per_second=30)[0]))
+# planar YUV: cp.async-staged rows of the two-stage kernel (4:2:0 8 bit, 4:2:2 10 bit, 4:4:4), file descriptors, windows;
+# another width through the generic kernel; full-screen resize (all four filters) frame by frame
+import tempfile  # noqa: E402
+from golden.make_golden_yuv_synth import synth_yuv  # noqa: E402
+with tempfile.TemporaryDirectory() as td:
+    for chroma, bd, cs, disp, W in (("420", 8, "709", "standard_fhd", 128), ("422", 10, "2020", "standard_hdr_pq", 192),
+                                    ("444", 8, "709", "standard_fhd", 64), ("420", 8, "709", "standard_fhd", 100)):
+        F, H = 7, 36
+        ty, ry = synth_yuv(12, F, H, W, chroma, bd)
+        props = {"width": W, "height": H, "fps": 30, "bit_depth": bd, "color_space": cs, "chroma_ss": chroma}
+        tf, rf = os.path.join(td, cv.create_yuv_fname("t" + chroma + str(W), props)), os.path.join(td, cv.create_yuv_fname("r" + chroma + str(W), props))
+        ty.tofile(tf), ry.tofile(rf)
+        m = cv.cvvdp(display_name=disp, device=dev)
+        m.yuv_chunk_bytes = 1
+        out.append(float(m.predict_video_source(cv.video_source_yuv_file(tf, rf, display_photometry=disp))[0]))
+    for mode in ("nearest", "bilinear", "bicubic", "area"):
+        vs = cv.video_source_yuv_file(tf, rf, display_photometry="standard_fhd", frames=2, full_screen_resize=mode, resize_resolution=(150, 77))
+        out.append(float(m.predict_video_source(vs)[0]))
 torch.cuda.synchronize()
 print("sanitize cases OK:", ["%.5f" % v for v in out])
