@@ -412,11 +412,13 @@ ClipView to_view(const cvvdp_b200_clip *c) {
 template <int EW, bool CF, bool LAG, bool FEAT>
 void launch_band_v(const BandArgs &ba, dim3 grid, cudaStream_t st, int variant) {
     typedef void (*BandFn)(const BandArgs);
+    // (feature mode never comes with a heat map -- the plan refuses the pair, like the reference's ML metrics -- so those
+    // four instantiations do not exist)
     static const BandFn table[8] = {
         k_band2<EW, CF, LAG, false, false, false, FEAT>, k_band2<EW, CF, LAG, false, false, true, FEAT>,
-        k_band2<EW, CF, LAG, false, true, false, FEAT>,  k_band2<EW, CF, LAG, false, true, true, FEAT>,
+        FEAT ? nullptr : k_band2<EW, CF, LAG, false, !FEAT, false, false>, FEAT ? nullptr : k_band2<EW, CF, LAG, false, !FEAT, true, false>,
         k_band2<EW, CF, LAG, true, false, false, FEAT>,  k_band2<EW, CF, LAG, true, false, true, FEAT>,
-        k_band2<EW, CF, LAG, true, true, false, FEAT>,   k_band2<EW, CF, LAG, true, true, true, FEAT>};
+        FEAT ? nullptr : k_band2<EW, CF, LAG, true, !FEAT, false, false>,  FEAT ? nullptr : k_band2<EW, CF, LAG, true, !FEAT, true, false>};
     static bool attr_set[8] = {false, false, false, false, false, false, false, false};
     typedef Band2Smem<EW, B2Lag<LAG>::DFR> Smem;
     BandFn kfn = table[variant];
@@ -978,6 +980,8 @@ int cvvdp_b200_plan(cvvdp_b200_ctx *ctx, const cvvdp_b200_job *job, cvvdp_b200_p
         return fail(ctx, CVVDP_ERR_INVALID, "unknown heat-map mode %d", job->heatmap);
     if (job->heatmap != CVVDP_HEATMAP_NONE && job->batch > 1)
         return fail(ctx, CVVDP_ERR_INVALID, "Heatmaps not supported when batches are used");  // cvvdp_metric.py:311-312
+    if (job->heatmap != CVVDP_HEATMAP_NONE && job->features)
+        return fail(ctx, CVVDP_ERR_UNSUPPORTED, "Currently cvvdp-ml metrics do not produce heatmaps");  // cvvdp_ml_metric.py:120-121
     if (ctx->disp.eotf == CVVDP_EOTF_HLG && job->in_channels != 3)
         return fail(ctx, CVVDP_ERR_UNSUPPORTED, "HLG needs three colour channels");
     if (job->yuv.chroma != 0) {
