@@ -408,6 +408,15 @@ def extra_runs(args, dev, peak, ref_sample):
     # BASELINE configs[3]: 3840x2160 HDR (PQ), 60 frames, standard_hdr_pq, with the raw heat map (fp16, 1 GB D2H)
     run("config4_hdr_pq_heatmap", "standard_hdr_pq", 2160, 3840, 60, 60.0, "u16", heatmap="raw", hdr=True)
 
+    # BASELINE configs[0]: one 256x256 image pair (launch- and host-bound: 18 launches per call), and a 1080p image
+    for name, h, w in (("config1_image_256", 256, 256), ("image_1080p", 1080, 1920)):
+        m = cv.cvvdp(display_name="standard_fhd", device=dev)
+        ti, ri = make_clip(3, 0, 1, h, w, "u8", dev)
+        ms_i, jod_i = time_steps(lambda: float(m.predict(ti, ri, dim_order="BCFHW")[0]), 200, 20, dev)
+        out[name] = {"workload": f"{w}x{h} image pair, standard_fhd, u8, predict() on device tensors incl. the JOD read-back",
+                     "ms_per_call": round(ms_i, 4), "value": round(h * w / 1e6 / (ms_i / 1e3), 2), "unit": "Mpix/s", "jod": round(jod_i, 5)}
+        del m, ti, ri
+
     # predict() on PAGEABLE numpy arrays (what a user who just loaded a clip passes)
     m = cv.cvvdp(display_name=DISPLAY, device=dev)
     tst, ref = make_clip(3, 0, F, H, W, args.dtype, dev)

@@ -357,9 +357,11 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
     float *ring = reinterpret_cast<float *>(smem_raw);  // [fl][3][threads]
     const int tid = threadIdx.x;
     const long long npix = (long long)a.H * a.W;
-    const long long p = (long long)blockIdx.x * CVVDP_TEMPORAL_THREADS + tid;
+    const long long p_raw = (long long)blockIdx.x * CVVDP_TEMPORAL_THREADS + tid;
     const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
-    if (p >= npix) return;  // no block-level barriers in this kernel
+    // threads past the last pixel shadow it (no stores): every warp stays whole for the shuffles at the end
+    const bool valid = p_raw < npix;
+    const long long p = valid ? p_raw : npix - 1;
     const int y = (int)(p / a.W), x = (int)(p - (long long)y * a.W);
     const ClipView &cv = a.clip[v];
     const long long base = b * cv.s[0] + y * cv.s[3] + x * cv.s[4];
@@ -375,7 +377,19 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
             pixel_to_dkl(cv, base, frame_slot(cv, s), a.cin, a.dtype, a.dd, d0, d1, d2, &a.yuv, b, y, x, &vbits);
             last_s = s;
         }
-        if (t == 0 && v == 0 && a.mean0 != nullptr) atomicAdd(a.mean0, d0);  // rare path: images and odd layouts
+        if (t == 0 && v == 0 && a.mean0 != nullptr) {  // uniform; one atomic per CTA (per thread they serialise: 3 ms per 1080p image)
+            __shared__ float s_part[CVVDP_TEMPORAL_THREADS / 32];
+            float msum = valid ? d0 : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+            if ((tid & 31) == 0) s_part[tid >> 5] = msum;
+            __syncthreads();
+            if (tid == 0) {
+                float tot = 0.f;
+                for (int w = 0; w < CVVDP_TEMPORAL_THREADS / 32; ++w) tot += s_part[w];
+                atomicAdd(a.mean0, tot);
+            }
+        }
         ring[(slot * 3 + 0) * CVVDP_TEMPORAL_THREADS + tid] = d0;
         ring[(slot * 3 + 1) * CVVDP_TEMPORAL_THREADS + tid] = d1;
         ring[(slot * 3 + 2) * CVVDP_TEMPORAL_THREADS + tid] = d2;
@@ -392,15 +406,11 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
                 o3 = fmaf(a.taps[3][k], x0, o3);  // transient channel filters the achromatic plane (l.557)
                 ks = ks + 1 == fl ? 0 : ks + 1;
             }
-            out[(long long)(t - a.f0) * 2 * npix] = make_float4(o0, o1, o2, o3);
+            if (valid) out[(long long)(t - a.f0) * 2 * npix] = make_float4(o0, o1, o2, o3);
         }
         slot = slot + 1 == fl ? 0 : slot + 1;
     }
-    if (vbits != 0u && a.flags != nullptr) {  // per thread: this kernel has partial warps, and the case is an error path
-        if (vbits & 1u) atomicAdd(&a.flags[0], 1);
-        if (vbits & 2u) atomicAdd(&a.flags[1], 1);
-        if (vbits & 4u) atomicAdd(&a.flags[2], 1);
-    }
+    publish_input_bits(vbits, a.flags);
 }
 
 __device__ __forceinline__ float bits_as_float(unsigned b) {

@@ -90,8 +90,20 @@ def _default_native_inputs():
     return _default_cache
 
 
+_band_freq_cache = {}
+
+
 def _band_frequencies(width, height, ppd):
     """rho_band as the reference reports it in stats (lpyr_dec.py:18-52, cvvdp_metric.py:685-686)."""
+    key = (int(width), int(height), float(ppd))
+    if key not in _band_freq_cache:
+        if len(_band_freq_cache) > 64:
+            _band_freq_cache.clear()
+        _band_freq_cache[key] = _band_frequencies_uncached(width, height, ppd)
+    return _band_freq_cache[key].copy()
+
+
+def _band_frequencies_uncached(width, height, ppd):
     max_levels = int(np.floor(np.log2(min(height, width)))) - 1
     bands = np.concatenate([[1.0], np.power(2.0, -np.arange(0.0, 14.0)) * 0.3228], 0) * ppd / 2.0
     invalid = np.nonzero(bands <= 0.2)[0]
