@@ -916,10 +916,23 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
         return fail(nullptr, CVVDP_ERR_NOMEM, "cannot allocate the validation flags");
     }
     auto kr2 = k_reduce2<8>;
-    cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem<8>));
-    auto kt = k_temporal;
-    cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         std::min(ctx->max_smem_optin, 227 * 1024));
+    if (cudaFuncSetAttribute(kr2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Reduce2Smem<8>)) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        delete ctx;
+        return fail(nullptr, CVVDP_ERR_CUDA, "cannot raise the shared-memory limit of the reduce kernel: %s", cudaGetErrorString(e));
+    }
+    auto kt = k_temporal;  // its ring grows with the filter length: allow everything the SM has, minus its static part
+    {
+        cudaFuncAttributes fa;
+        int stat = 0;
+        if (cudaFuncGetAttributes(&fa, kt) == cudaSuccess) stat = (int)fa.sharedSizeBytes;
+        if (cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 std::min(ctx->max_smem_optin, 227 * 1024) - stat) != cudaSuccess) {
+            const cudaError_t e = cudaGetLastError();
+            delete ctx;
+            return fail(nullptr, CVVDP_ERR_CUDA, "cannot raise the shared-memory limit of the temporal kernel: %s", cudaGetErrorString(e));
+        }
+    }
     *out = ctx;
     return CVVDP_OK;
 }

@@ -259,6 +259,8 @@ static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = 0) { retur
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 template <typename T> static inline cudaError_t cudaFuncSetAttribute(T, cudaFuncAttribute, int) { return cudaSuccess; }
+struct cudaFuncAttributes { size_t sharedSizeBytes = 0; };
+template <typename T> static inline cudaError_t cudaFuncGetAttributes(cudaFuncAttributes *a, T) { *a = cudaFuncAttributes(); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) {
     *v = (a == cudaDevAttrMultiProcessorCount) ? 4 : 232448;
     return cudaSuccess;
