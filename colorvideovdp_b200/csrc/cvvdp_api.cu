@@ -561,7 +561,23 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             }
         }
 #undef CVVDP_TEMPORAL_CASE
-        if (!launched) {  // images, strided / permuted views, planar YUV, filters beyond 17 taps (> 64 fps)
+        // long filters (frame rates above 64 fps) on dense planes: the shared-memory ring kernel
+        const size_t smem_sr = tsr_smem_bytes(info.filter_len, use_lut);
+        if (!launched && dense && !is_yuv && taps_symmetric && !force_generic && info.filter_len >= 19 &&
+            smem_sr <= (size_t)std::min(ctx->max_smem_optin, 227 * 1024)) {
+            dim3 grid_sr((unsigned)((npix / 64 + CVVDP_TSR_THREADS / 32 - 1) / (CVVDP_TSR_THREADS / 32)), (unsigned)(B * 2));
+            if (use_lut) {
+                auto kfn = k_temporal_sr<true>;
+                cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sr);
+                CVVDP_LAUNCH(kfn, grid_sr, dim3(CVVDP_TSR_THREADS), smem_sr, st, ta);
+            } else {
+                auto kfn = k_temporal_sr<false>;
+                cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sr);
+                CVVDP_LAUNCH(kfn, grid_sr, dim3(CVVDP_TSR_THREADS), smem_sr, st, ta);
+            }
+            launched = true;
+        }
+        if (!launched) {  // images, strided / permuted views, planar YUV of other widths, filters beyond 73 taps
             auto kfn = k_temporal;
             CVVDP_LAUNCH(kfn, grid, dim3(CVVDP_TEMPORAL_THREADS), smem, st, ta);
         }

@@ -862,6 +862,200 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
 }
 
 // =================================================================================================
+// Temporal stage for long filters (19 taps and more: frame rates above 64 fps; 120 fps = 31 taps).  The register ring
+// of k_temporal_2s does not fit, so the ring lives in shared memory: [FL][3][threads] fp32x2, one slab per thread
+// (nobody else reads it: no barriers).  Same pixel ownership (lane, lane + 32 of a 64-pixel segment) and the same
+// symmetric-tap FIR (mirrored frames added first, A-sust and A-trans share the sums) as k_temporal_2s; the raw
+// samples of the next frame are loaded before the FIR of the current one runs.  Dense planes only (the host checks);
+// anything else stays with k_temporal.
+// dynamic shared memory: float4 taps[FL/2 + 1] | float lut[256] (table variant) | float2 ring[FL][3][threads]
+// =================================================================================================
+#define CVVDP_TSR_THREADS 128
+__host__ __device__ inline size_t tsr_smem_bytes(int fl, bool lut) {
+    return (size_t)(fl / 2 + 1) * 16 + (lut ? 1024 : 0) + (size_t)(fl + 1) * 3 * CVVDP_TSR_THREADS * 8;
+}
+template <bool USE_LUT>
+__global__ void __launch_bounds__(CVVDP_TSR_THREADS) k_temporal_sr(const __grid_constant__ TemporalArgs a) {
+    CVVDP_DYN_SMEM(smem_raw);
+    const int FL = a.fl, HP = FL / 2;  // HP mirrored pairs + the centre tap
+    const int RS = FL + 1;             // ring slots: the filter support of two consecutive output frames
+    float4 *s_taps = reinterpret_cast<float4 *>(smem_raw);
+    float *s_lut = reinterpret_cast<float *>(smem_raw + (size_t)(HP + 1) * 16);
+    float2 *ring = reinterpret_cast<float2 *>(smem_raw + (size_t)(HP + 1) * 16 + (USE_LUT ? 1024 : 0)) + threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int k = tid; k <= HP; k += CVVDP_TSR_THREADS) s_taps[k] = make_float4(a.taps[0][k], a.taps[1][k], a.taps[2][k], a.taps[3][k]);
+    if (USE_LUT) {
+        for (int i = tid; i < 256; i += CVVDP_TSR_THREADS) {
+            float v[3] = {(float)i / 255.0f, 0.f, 0.f};
+            eotf_forward_n<1>(v, a.dd);
+            s_lut[i] = v[0];
+        }
+    }
+    __syncthreads();
+    const long long npix = (long long)a.H * a.W;
+    const long long wp = ((long long)blockIdx.x * (CVVDP_TSR_THREADS / 32) + warp) * 64;
+    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
+    if (wp >= npix) return;  // whole segments only (npix % 64 == 0); no barrier below
+    const ClipView &cv = a.clip[v];
+    const int n = a.f1 - a.f0, NI = (FL - 1) + n;
+    float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + wp + lane;
+    const long long ostep = 2 * npix;
+    const long long pbase = b * cv.s[0] + wp + lane;  // element offset of the thread's first pixel in a frame
+    auto load_raw = [&](int it, unsigned (&ra)[3], unsigned (&rb)[3]) {
+        if (it >= NI) return;  // uniform
+        const int t = a.f0 - (FL - 1) + it;
+        const long long off = pbase + (long long)frame_slot(cv, t >= 0 ? t : temporal_source_frame(a, t)) * cv.s[2];
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) {
+            const long long o = off + (a.cin == 3 ? ch : 0) * cv.s[1];
+            if (USE_LUT || a.dtype == CVVDP_DTYPE_U8) {
+                ra[ch] = __ldg((const unsigned char *)cv.data + o);
+                rb[ch] = __ldg((const unsigned char *)cv.data + o + 32);
+            } else if (a.dtype == CVVDP_DTYPE_F32) {
+                ra[ch] = __ldg((const unsigned *)cv.data + o);
+                rb[ch] = __ldg((const unsigned *)cv.data + o + 32);
+            } else {
+                ra[ch] = __ldg((const unsigned short *)cv.data + o);
+                rb[ch] = __ldg((const unsigned short *)cv.data + o + 32);
+            }
+        }
+    };
+    unsigned vbits = 0u;
+    float msum = 0.f;
+    const int it_zero = v == 0 && a.mean0 != nullptr ? FL - 1 - a.f0 : -1;
+    auto convert = [&](int it, int slot, const unsigned (&ra)[3], const unsigned (&rb)[3]) {
+        float2 d0, d1, d2;
+        bits_to_dkl2<USE_LUT>(a, s_lut, ra, rb, d0, d1, d2, vbits);
+        if (it == it_zero) msum = d0.x + d0.y;  // uniform
+        ring[(slot * 3 + 0) * CVVDP_TSR_THREADS] = d0;
+        ring[(slot * 3 + 1) * CVVDP_TSR_THREADS] = d1;
+        ring[(slot * 3 + 2) * CVVDP_TSR_THREADS] = d2;
+    };
+    auto slot_add = [&](int s, int d) {  // (s + d) mod RS for 0 <= d <= 2
+        s += d;
+        return s >= RS ? s - RS : s;
+    };
+    auto ld3 = [&](int slot, float2 (&x)[3]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = ring[(slot * 3 + c) * CVVDP_TSR_THREADS];
+    };
+    // raw samples of frames it and it + 1, loaded ahead of their use
+    unsigned q0a[3] = {0u, 0u, 0u}, q0b[3] = {0u, 0u, 0u}, q1a[3] = {0u, 0u, 0u}, q1b[3] = {0u, 0u, 0u};
+    load_raw(0, q0a, q0b);
+    load_raw(1, q1a, q1b);
+    int rs = 0;  // ring slot of frame `it`
+    for (int it = 0; it < NI;) {
+        if (it >= FL - 1 && it + 1 < NI) {
+            // ---- two output frames t, t+1 per pass over the ring: every slot is read once for both ----
+            const int rs1 = slot_add(rs, 1);
+            unsigned ca[3] = {q0a[0], q0a[1], q0a[2]}, cb[3] = {q0b[0], q0b[1], q0b[2]};
+            unsigned ea[3] = {q1a[0], q1a[1], q1a[2]}, eb[3] = {q1b[0], q1b[1], q1b[2]};
+            load_raw(it + 2, q0a, q0b);
+            load_raw(it + 3, q1a, q1b);
+            convert(it, rs, ca, cb);
+            convert(it + 1, rs1, ea, eb);
+            // frame t-(FL-1)+k is A_k, frame t-k is B_k: out[t] pairs (A_k, B_k), out[t+1] pairs (A_{k+1}, B_{k-1})
+            int sa = slot_add(rs, 2), sb = rs;
+            float2 A[3], Bp[3];
+            ld3(sa, A);      // A_0
+            ld3(rs1, Bp);    // B_{-1} = frame t+1
+            float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0, u0 = o0, u1 = o0, u2 = o0, u3 = o0;
+#pragma unroll 2
+            for (int k = 0; k < HP; ++k) {
+                const float4 tp = s_taps[k];
+                sa = slot_add(sa, 1);
+                float2 An[3], Bc[3];
+                ld3(sa, An);  // A_{k+1}
+                ld3(sb, Bc);  // B_k
+                const float2 p0 = add2(A[0], Bc[0]), p1 = add2(A[1], Bc[1]), p2 = add2(A[2], Bc[2]);
+                const float2 r0 = add2(An[0], Bp[0]), r1 = add2(An[1], Bp[1]), r2 = add2(An[2], Bp[2]);
+                o0 = fma2(bc2(tp.x), p0, o0);
+                o1 = fma2(bc2(tp.y), p1, o1);
+                o2 = fma2(bc2(tp.z), p2, o2);
+                o3 = fma2(bc2(tp.w), p0, o3);
+                u0 = fma2(bc2(tp.x), r0, u0);
+                u1 = fma2(bc2(tp.y), r1, u1);
+                u2 = fma2(bc2(tp.z), r2, u2);
+                u3 = fma2(bc2(tp.w), r0, u3);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    A[c] = An[c];
+                    Bp[c] = Bc[c];
+                }
+                sb = sb == 0 ? RS - 1 : sb - 1;
+            }
+            {   // centre taps: A_HP for out[t], B_{HP-1} (= A_{HP+1}) for out[t+1]
+                const float4 tp = s_taps[HP];
+                o0 = fma2(bc2(tp.x), A[0], o0);
+                o1 = fma2(bc2(tp.y), A[1], o1);
+                o2 = fma2(bc2(tp.z), A[2], o2);
+                o3 = fma2(bc2(tp.w), A[0], o3);
+                u0 = fma2(bc2(tp.x), Bp[0], u0);
+                u1 = fma2(bc2(tp.y), Bp[1], u1);
+                u2 = fma2(bc2(tp.z), Bp[2], u2);
+                u3 = fma2(bc2(tp.w), Bp[0], u3);
+            }
+            outp[0] = make_float4(o0.x, o1.x, o2.x, o3.x);
+            outp[32] = make_float4(o0.y, o1.y, o2.y, o3.y);
+            outp += ostep;
+            outp[0] = make_float4(u0.x, u1.x, u2.x, u3.x);
+            outp[32] = make_float4(u0.y, u1.y, u2.y, u3.y);
+            outp += ostep;
+            it += 2;
+            rs = slot_add(rs, 2);
+        } else {
+            // ---- one frame: the warm-up frames before the first output, and an odd last output ----
+            unsigned ca[3] = {q0a[0], q0a[1], q0a[2]}, cb[3] = {q0b[0], q0b[1], q0b[2]};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                q0a[c] = q1a[c];
+                q0b[c] = q1b[c];
+            }
+            load_raw(it + 2, q1a, q1b);
+            convert(it, rs, ca, cb);
+            if (it >= FL - 1) {  // uniform: the ring holds frames t-(FL-1) .. t, the oldest two slots ahead of rs
+                float2 o0 = make_float2(0.f, 0.f), o1 = o0, o2 = o0, o3 = o0;
+                int sa = slot_add(rs, 2), sb = rs;
+#pragma unroll 2
+                for (int k = 0; k < HP; ++k) {  // tap k <-> frame t-(FL-1)+k, mirrored by frame t-k
+                    const float4 tp = s_taps[k];
+                    float2 x[3], y[3];
+                    ld3(sa, x);
+                    ld3(sb, y);
+                    const float2 p0 = add2(x[0], y[0]), p1 = add2(x[1], y[1]), p2 = add2(x[2], y[2]);
+                    o0 = fma2(bc2(tp.x), p0, o0);
+                    o1 = fma2(bc2(tp.y), p1, o1);
+                    o2 = fma2(bc2(tp.z), p2, o2);
+                    o3 = fma2(bc2(tp.w), p0, o3);
+                    sa = slot_add(sa, 1);
+                    sb = sb == 0 ? RS - 1 : sb - 1;
+                }
+                {
+                    const float4 tp = s_taps[HP];  // centre tap: sa has arrived at the middle frame
+                    float2 x[3];
+                    ld3(sa, x);
+                    o0 = fma2(bc2(tp.x), x[0], o0);
+                    o1 = fma2(bc2(tp.y), x[1], o1);
+                    o2 = fma2(bc2(tp.z), x[2], o2);
+                    o3 = fma2(bc2(tp.w), x[0], o3);
+                }
+                outp[0] = make_float4(o0.x, o1.x, o2.x, o3.x);
+                outp[32] = make_float4(o0.y, o1.y, o2.y, o3.y);
+                outp += ostep;
+            }
+            it += 1;
+            rs = slot_add(rs, 1);
+        }
+    }
+    if (!USE_LUT) publish_input_bits(vbits, a.flags);
+    if (it_zero >= 0 && it_zero < NI) {  // uniform per CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+        if (lane == 0) atomicAdd(a.mean0, msum);
+    }
+}
+
+// =================================================================================================
 // Gaussian pyramid reduce  (lpyr_dec.py:186-211): zero-padded 5-tap stride-2 passes (rows, then
 // columns) with the reference's edge fix-ups, including the parity quirk at line 206 (the ROW count
 // selects the right-edge rule of the column pass).

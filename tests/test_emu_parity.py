@@ -502,6 +502,44 @@ def test_every_temporal_specialisation_against_oracle(fps, mock_device):
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
 
 
+@pytest.mark.parametrize("fps,dtype,display,padding", [(72, "u8", "standard_fhd", "replicate"), (90, "f32", "standard_4k", "symmetric"),
+                                                       (120, "u8", "standard_4k", "symmetric"), (120, "f16", "standard_hdr_linear", "replicate"),
+                                                       (165, "u16", "standard_hdr_pq", "replicate")])
+def test_long_filters_take_the_shared_ring_kernel(fps, dtype, display, padding, mock_device):
+    """Frame rates above 64 fps (19, 25, 31, 43 taps): packed shared-memory-ring temporal kernel, table and float
+    variants, clips shorter and longer than the filter, against the oracle."""
+    F = 12 if fps == 90 else 50
+    tst, ref = synth.make_pair_u8(70 + fps, F, 16, 64)
+    if dtype == "u8":
+        tst_in, ref_in = tst, ref
+    elif dtype == "u16":
+        tst_in, ref_in = tst.astype(np.uint16) * 180, ref.astype(np.uint16) * 180
+    else:
+        scale = 3.0 if display == "standard_hdr_linear" else 1.0
+        tst_in, ref_in = (tst.astype(np.float32) / 255 * scale).astype(dtype.replace("f", "float")), (ref.astype(np.float32) / 255 * scale).astype(dtype.replace("f", "float"))
+    jod_o, stats_o = O.predict(tst_in, ref_in, "BCFHW", fps, display, padding)
+    if dtype == "u16":
+        tst_in, ref_in = tst_in.view(np.int16), ref_in.view(np.int16)
+    m = cv.cvvdp(display_name=display, temp_padding=padding)
+    jod, stats = m.predict(tst_in, ref_in, frames_per_second=fps)
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"{fps} fps {dtype}")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
+
+
+def test_shared_ring_kernel_is_independent_of_the_frame_partition(mock_device):
+    """The shared-ring kernel emits two frames per pass where it can; any split of the clip into frame ranges (odd and
+    even lengths, single frames) must give the bits of the whole clip."""
+    tst, ref = synth.make_pair_u8(77, 40, 16, 64)
+    m = cv.cvvdp(display_name="standard_fhd")
+    _, whole = m.predict(tst, ref, frames_per_second=120)
+    vs = cv.video_source_array(tst, ref, 120, display_photometry=m.display_photometry)
+    parts = np.zeros_like(whole["Q_per_ch"])
+    for lo, hi in ((0, 7), (7, 8), (8, 31), (31, 40)):
+        _, s = m.predict_video_source(vs, frame_range=(lo, hi))
+        parts[:, :, lo:hi] = s["Q_per_ch"][:, :, lo:hi]
+    assert np.array_equal(parts, whole["Q_per_ch"])
+
+
 @pytest.mark.parametrize("dtype,fps", [("f32", 60), ("f16", 30), ("f32", 24)])
 def test_two_stage_temporal_kernel_float_inputs(dtype, fps, mock_device):
     """fp32 / fp16 clips with whole 64-pixel warp segments: the non-table variant of the two-stage temporal

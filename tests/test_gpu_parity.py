@@ -347,6 +347,31 @@ def test_every_temporal_specialisation_on_hardware(fps):
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
 
 
+@pytest.mark.parametrize("fps,dtype,display,padding", [(72, "u8", "standard_fhd", "replicate"), (90, "f32", "standard_4k", "symmetric"),
+                                                       (120, "u8", "standard_4k", "symmetric"), (120, "f16", "standard_hdr_linear", "replicate"),
+                                                       (165, "u16", "standard_hdr_pq", "replicate")])
+def test_long_filters_take_the_shared_ring_kernel(fps, dtype, display, padding):
+    """Frame rates above 64 fps (19, 25, 31, 43 taps): packed shared-memory-ring temporal kernel, table and float
+    variants, clips shorter and longer than the filter, against the oracle."""
+    F = 12 if fps == 90 else 50
+    tst, ref = synth.make_pair_u8(70 + fps, F, 16, 64)
+    if dtype == "u8":
+        tst_in, ref_in = tst, ref
+    elif dtype == "u16":
+        tst_in, ref_in = tst.astype(np.uint16) * 180, ref.astype(np.uint16) * 180
+    else:
+        scale = 3.0 if display == "standard_hdr_linear" else 1.0
+        tst_in, ref_in = (tst.astype(np.float32) / 255 * scale).astype(dtype.replace("f", "float")), (ref.astype(np.float32) / 255 * scale).astype(dtype.replace("f", "float"))
+    jod_o, stats_o = O.predict(tst_in, ref_in, "BCFHW", fps, display, padding)
+    if dtype == "u16":
+        tst_in, ref_in = tst_in.view(np.int16), ref_in.view(np.int16)
+    tst_in, ref_in = _t(tst_in), _t(ref_in)
+    m = cv.cvvdp(display_name=display, temp_padding=padding, device=DEV)
+    jod, stats = m.predict(tst_in, ref_in, frames_per_second=fps)
+    gu.assert_q_close(stats["Q_per_ch"], stats_o["Q_per_ch"], f"{fps} fps {dtype}")
+    assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
+
+
 @pytest.mark.parametrize("shape", [(6, 16, 64), (3, 20, 28)])  # two-stage temporal kernel / generic kernel
 @pytest.mark.parametrize("resident", ["device", "host"])
 def test_input_validation_on_the_fused_path(shape, resident, caplog):

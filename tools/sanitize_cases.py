@@ -42,6 +42,11 @@ m = cv.cvvdp(display_name="standard_hdr_linear", device=dev)
 out.append(float(m.predict((t(tst).float() * 2).half(), (t(ref).float() * 2).half(), frames_per_second=30)[0]))
 m = cv.cvvdp(display_name="standard_hdr_pq", device=dev)
 out.append(float(m.predict((t(tst).to(torch.int32) * 200).to(torch.int16), (t(ref).to(torch.int32) * 200).to(torch.int16), frames_per_second=30)[0]))
+# long filters (120 and 90 fps: 31 and 25 taps): shared-memory-ring temporal kernel, table and float variants
+tst, ref = synth.make_pair_u8(13, 37, 32, 128)
+m = cv.cvvdp(display_name="standard_fhd", device=dev, temp_padding="symmetric")
+out.append(float(m.predict(t(tst), t(ref), frames_per_second=120)[0]))
+out.append(float(m.predict(t(tst).float() / 255, t(ref).float() / 255, frames_per_second=90)[0]))
 # planar YUV: cp.async-staged rows of the two-stage kernel (4:2:0 8 bit, 4:2:2 10 bit, 4:4:4), file descriptors, windows;
 # another width through the generic kernel; full-screen resize (all four filters) frame by frame
 import tempfile  # noqa: E402
