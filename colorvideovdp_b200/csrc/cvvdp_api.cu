@@ -503,12 +503,21 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         const bool use_lut = !is_yuv && job.dtype == CVVDP_DTYPE_U8 &&
                              (e == CVVDP_EOTF_SRGB || e == CVVDP_EOTF_PQ || e == CVVDP_EOTF_LINEAR || e == CVVDP_EOTF_GAMMA);
         // two-stage packed kernel: dense, 16-byte aligned planes made of whole 64-pixel warp segments
+        // ... either planar (pixel stride 1) or channel-interleaved (HWC frames: pixel stride 3, channel stride 1), both videos alike
         bool dense = !is_yuv && npix % 64 == 0 && job.in_channels <= 3;
+        const bool inter = dense && job.in_channels == 3 && ta.clip[0].s[4] == 3 && ta.clip[1].s[4] == 3;
+        ta.inter = inter ? 1 : 0;
         for (int v = 0; v < 2 && dense; ++v) {
             const ClipView &cvw = ta.clip[v];
             const long long es = (long long)dtype_size(job.dtype);
-            if (cvw.s[4] != 1 || cvw.s[3] != job.width) dense = false;
-            if (((uintptr_t)cvw.data) % 16 || (cvw.s[0] * es) % 16 || (cvw.s[1] * es) % 16 || (cvw.s[2] * es) % 16) dense = false;
+            const long long sb = B > 1 ? cvw.s[0] : 0;  // (the stride of a singleton batch dimension is arbitrary)
+            if (inter) {
+                if (cvw.s[1] != 1 || cvw.s[3] != 3LL * job.width) dense = false;
+                if (((uintptr_t)cvw.data) % 16 || (sb * es) % 16 || (cvw.s[2] * es) % 16) dense = false;
+            } else {
+                if (cvw.s[4] != 1 || cvw.s[3] != job.width) dense = false;
+                if (((uintptr_t)cvw.data) % 16 || (sb * es) % 16 || (cvw.s[1] * es) % 16 || (cvw.s[2] * es) % 16) dense = false;
+            }
         }
         // planar YUV: rows of whole 64-pixel segments (the two pixels of a thread share a row), frames anywhere
         bool yuv_2s = is_yuv && job.width % 64 == 0 && (job.dtype == CVVDP_DTYPE_U8 || job.dtype == CVVDP_DTYPE_U16);

@@ -347,6 +347,7 @@ struct TemporalArgs {
     YuvDev yuv;
     float4 *out;  // level 0: [B][n][2][H*W]
     int *flags;   // [0..2]: warps that saw out-of-range / NaN / Inf input values (null: no validation)
+    int inter;    // two-stage / shared-ring kernels: 1 = channel-interleaved pixels (HWC frames: pixel stride 3, channel stride 1)
     float *mean0; // sum over the pixels of clip frame 0 of the TEST video of its achromatic DKL channel (video_source.py:64-71)
     float taps[4][CVVDP_MAX_FILTER_LEN];  // taps[c][k] multiplies frame f-(fl-1)+k (= F_c flipped, l.556)
 };
@@ -587,8 +588,12 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     const int ppf = YUV ? 5 * cpc : a.cin * cpc;  // pieces per frame
     unsigned char *raw = smem_raw + (size_t)warp * G * frame_bytes;
     float2 *dkl = reinterpret_cast<float2 *>(smem_raw + (size_t)(CVVDP_T2S_THREADS / 32) * G * frame_bytes) + tid;
-    const long long fstride = cv.s[2] * esz, cstride = cv.s[1] * esz;
-    const unsigned char *wsrc = (const unsigned char *)cv.data + (b * cv.s[0] + wp) * esz;
+    // Channel-interleaved frames (HWC): the warp's 64 pixels are 3 * 64 consecutive elements -- for the copies that is
+    // three "channel segments" 64 elements apart; only the element a lane picks out of the stage differs (below).
+    const bool inter = !YUV && a.inter != 0;
+    const long long fstride = cv.s[2] * esz, cstride = inter ? row_bytes : cv.s[1] * esz;
+    const unsigned char *wsrc = (const unsigned char *)cv.data + (b * cv.s[0] + (inter ? 3 * wp : wp)) * esz;
+    const int el_a = inter ? 3 * lane : lane, el_b = inter ? 3 * (lane + 32) : lane + 32, el_c = inter ? 1 : 64;  // stage elements
     const int n = a.f1 - a.f0;
     const int NI = (FL - 1) + n;  // iterations: FL-1 warm-up frames (temporal padding before frame 0), then the block
     // the thread's two pixels: lane and lane + 32 of the segment, or -- planar YUV -- the horizontal neighbours 2 lane and
@@ -668,16 +673,16 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
             unsigned ba[3], bb[3];
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-                const unsigned char *qc = q + ((DT >= 0 || a.cin == 3) ? ch : 0) * row_bytes;
+                const int ec = ((DT >= 0 || a.cin == 3) ? ch : 0) * el_c;
                 if (eszv == 1) {
-                    ba[ch] = lds_u8(qc + lane);
-                    bb[ch] = lds_u8(qc + lane + 32);
+                    ba[ch] = lds_u8(q + el_a + ec);
+                    bb[ch] = lds_u8(q + el_b + ec);
                 } else if (eszv == 2) {
-                    ba[ch] = ((const unsigned short *)qc)[lane];
-                    bb[ch] = ((const unsigned short *)qc)[lane + 32];
+                    ba[ch] = ((const unsigned short *)q)[el_a + ec];
+                    bb[ch] = ((const unsigned short *)q)[el_b + ec];
                 } else {
-                    ba[ch] = ((const unsigned *)qc)[lane];
-                    bb[ch] = ((const unsigned *)qc)[lane + 32];
+                    ba[ch] = ((const unsigned *)q)[el_a + ec];
+                    bb[ch] = ((const unsigned *)q)[el_b + ec];
                 }
             }
             float2 d0, d1, d2;
@@ -900,7 +905,8 @@ __global__ void __launch_bounds__(CVVDP_TSR_THREADS) k_temporal_sr(const __grid_
     const int n = a.f1 - a.f0, NI = (FL - 1) + n;
     float4 *outp = a.out + ((long long)b * n * 2 + v) * npix + wp + lane;
     const long long ostep = 2 * npix;
-    const long long pbase = b * cv.s[0] + wp + lane;  // element offset of the thread's first pixel in a frame
+    const int ps = a.inter ? 3 : 1;  // pixel stride: channel-interleaved (HWC) or planar frames
+    const long long pbase = b * cv.s[0] + (wp + lane) * ps;  // element offset of the thread's first pixel in a frame
     auto load_raw = [&](int it, unsigned (&ra)[3], unsigned (&rb)[3]) {
         if (it >= NI) return;  // uniform
         const int t = a.f0 - (FL - 1) + it;
@@ -910,13 +916,13 @@ __global__ void __launch_bounds__(CVVDP_TSR_THREADS) k_temporal_sr(const __grid_
             const long long o = off + (a.cin == 3 ? ch : 0) * cv.s[1];
             if (USE_LUT || a.dtype == CVVDP_DTYPE_U8) {
                 ra[ch] = __ldg((const unsigned char *)cv.data + o);
-                rb[ch] = __ldg((const unsigned char *)cv.data + o + 32);
+                rb[ch] = __ldg((const unsigned char *)cv.data + o + 32 * ps);
             } else if (a.dtype == CVVDP_DTYPE_F32) {
                 ra[ch] = __ldg((const unsigned *)cv.data + o);
-                rb[ch] = __ldg((const unsigned *)cv.data + o + 32);
+                rb[ch] = __ldg((const unsigned *)cv.data + o + 32 * ps);
             } else {
                 ra[ch] = __ldg((const unsigned short *)cv.data + o);
-                rb[ch] = __ldg((const unsigned short *)cv.data + o + 32);
+                rb[ch] = __ldg((const unsigned short *)cv.data + o + 32 * ps);
             }
         }
     };

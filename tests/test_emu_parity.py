@@ -526,6 +526,23 @@ def test_long_filters_take_the_shared_ring_kernel(fps, dtype, display, padding, 
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
 
 
+@pytest.mark.parametrize("fps,dtype", [(30, "u8"), (60, "f32"), (24, "f16"), (120, "u8"), (90, "f32")])
+def test_channel_interleaved_frames_take_the_fast_temporal_kernels(fps, dtype, mock_device):
+    """FHWC clips (what decoded frames stacked in numpy look like): the two-stage and shared-ring kernels read the
+    interleaved pixels in place and give exactly the bits of the planar BCFHW layout; host and device residency."""
+    F, H, W = (11, 16, 64) if fps < 64 else (36, 16, 64)
+    tst, ref = synth.make_pair_u8(140 + fps, F, H, W)
+    if dtype != "u8":
+        tst, ref = (tst.astype(np.float32) / 255).astype(dtype.replace("f", "float")), (ref.astype(np.float32) / 255).astype(dtype.replace("f", "float"))
+    m = cv.cvvdp(display_name="standard_fhd")
+    _, planar = m.predict(tst, ref, frames_per_second=fps)
+    ti, ri = np.ascontiguousarray(tst[0].transpose(1, 2, 3, 0)), np.ascontiguousarray(ref[0].transpose(1, 2, 3, 0))  # [F,H,W,C]
+    _, host = m.predict(ti, ri, dim_order="FHWC", frames_per_second=fps)
+    assert np.array_equal(host["Q_per_ch"], planar["Q_per_ch"])
+    vs = cv.video_source_array(ti, ri, fps, dim_order='FHWC', display_photometry=m.display_photometry); Qd, _ = m.q_per_ch_from_tensors(vs.test_video, vs.reference_video, F, fps, _resident=True); dev_res = dict(Q_per_ch=Qd.numpy())
+    assert np.array_equal(dev_res["Q_per_ch"], planar["Q_per_ch"])
+
+
 def test_shared_ring_kernel_is_independent_of_the_frame_partition(mock_device):
     """The shared-ring kernel emits two frames per pass where it can; any split of the clip into frame ranges (odd and
     even lengths, single frames) must give the bits of the whole clip."""

@@ -372,6 +372,23 @@ def test_long_filters_take_the_shared_ring_kernel(fps, dtype, display, padding):
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
 
 
+@pytest.mark.parametrize("fps,dtype", [(30, "u8"), (60, "f32"), (24, "f16"), (120, "u8"), (90, "f32")])
+def test_channel_interleaved_frames_take_the_fast_temporal_kernels(fps, dtype):
+    """FHWC clips (what decoded frames stacked in numpy look like): the two-stage and shared-ring kernels read the
+    interleaved pixels in place and give exactly the bits of the planar BCFHW layout; host and device residency."""
+    F, H, W = (11, 16, 64) if fps < 64 else (36, 16, 64)
+    tst, ref = synth.make_pair_u8(140 + fps, F, H, W)
+    if dtype != "u8":
+        tst, ref = (tst.astype(np.float32) / 255).astype(dtype.replace("f", "float")), (ref.astype(np.float32) / 255).astype(dtype.replace("f", "float"))
+    m = cv.cvvdp(display_name="standard_fhd", device=DEV)
+    _, planar = m.predict(tst, ref, frames_per_second=fps)
+    ti, ri = np.ascontiguousarray(tst[0].transpose(1, 2, 3, 0)), np.ascontiguousarray(ref[0].transpose(1, 2, 3, 0))  # [F,H,W,C]
+    _, host = m.predict(ti, ri, dim_order="FHWC", frames_per_second=fps)
+    assert np.array_equal(host["Q_per_ch"], planar["Q_per_ch"])
+    _, dev_res = m.predict(_t(ti), _t(ri), dim_order='FHWC', frames_per_second=fps)
+    assert np.array_equal(dev_res["Q_per_ch"], planar["Q_per_ch"])
+
+
 @pytest.mark.parametrize("shape", [(6, 16, 64), (3, 20, 28)])  # two-stage temporal kernel / generic kernel
 @pytest.mark.parametrize("resident", ["device", "host"])
 def test_input_validation_on_the_fused_path(shape, resident, caplog):
