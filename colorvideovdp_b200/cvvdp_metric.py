@@ -213,6 +213,17 @@ class cvvdp(vq_metric):
                                      display_photometry=self.display_photometry)
         return self.predict_video_source(test_vs)
 
+    def loss(self, test_cont, reference_cont, dim_order="BCFHW", frames_per_second=0):
+        """10 - JOD (cvvdp_metric.py:294-298), as a value.  The reference differentiates through its torch ops; this
+        engine has forward kernels only, so content that requires a gradient is refused instead of silently returning a
+        constant."""
+        for c in (test_cont, reference_cont):
+            if isinstance(c, torch.Tensor) and c.requires_grad:
+                raise NotImplementedError("colorvideovdp_b200 has no backward kernels: loss() cannot be differentiated "
+                                          "(detach the tensors to get the value, or use the reference for optimisation)")
+        Q_jod, _ = self.predict(test_cont, reference_cont, dim_order=dim_order, frames_per_second=frames_per_second)
+        return 10.0 - Q_jod
+
     # ------------------------------------------------------------------------------------------
     def _plan(self, B, H, W, F, fps, cin, dtype_id, photo, yuv=None, features=False, prefiltered=False):
         """(Re)build the native plan when the job or the display changed.  photo=None: frames already

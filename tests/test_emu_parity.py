@@ -450,6 +450,17 @@ def test_yuv_files_are_read_through_descriptors(tmp_path, mock_device, monkeypat
         m.predict_video_source(vs)
 
 
+def test_loss_is_ten_minus_jod_and_refuses_gradients(mock_device):
+    """cvvdp.loss (cvvdp_metric.py:294-298): the value, and a clear refusal when a gradient is expected."""
+    tst, ref = synth.make_pair_u8(33, 1, 24, 40)
+    m = cv.cvvdp(display_name="standard_fhd")
+    t, r = torch.from_numpy(tst[0, :, 0]).float() / 255, torch.from_numpy(ref[0, :, 0]).float() / 255
+    jod, _ = m.predict(t, r, dim_order="CHW")
+    assert float(m.loss(t, r, dim_order="CHW")) == pytest.approx(10.0 - float(jod), abs=1e-6)
+    with pytest.raises(NotImplementedError, match="backward"):
+        m.loss(t.clone().requires_grad_(True), r, dim_order="CHW")
+
+
 def test_yuv_filename_metadata():
     p = cv.decode_video_props("/x/clip_1280x720_10b_444_2020_59.94fps.yuv")
     assert (p["width"], p["height"], p["bit_depth"], p["chroma_ss"], p["color_space"], p["fps"]) == (1280, 720, 10, "444", "2020", 59.94)
