@@ -593,7 +593,6 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     const bool inter = !YUV && a.inter != 0;
     const long long fstride = cv.s[2] * esz, cstride = inter ? row_bytes : cv.s[1] * esz;
     const unsigned char *wsrc = (const unsigned char *)cv.data + (b * cv.s[0] + (inter ? 3 * wp : wp)) * esz;
-    const int el_a = inter ? 3 * lane : lane, el_b = inter ? 3 * (lane + 32) : lane + 32, el_c = inter ? 1 : 64;  // stage elements
     const int n = a.f1 - a.f0;
     const int NI = (FL - 1) + n;  // iterations: FL-1 warm-up frames (temporal padding before frame 0), then the block
     // the thread's two pixels: lane and lane + 32 of the segment, or -- planar YUV -- the horizontal neighbours 2 lane and
@@ -672,17 +671,34 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
             const unsigned char *q = raw + g * frame_bytes;
             unsigned ba[3], bb[3];
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-                const int ec = ((DT >= 0 || a.cin == 3) ? ch : 0) * el_c;
-                if (eszv == 1) {
-                    ba[ch] = lds_u8(q + el_a + ec);
-                    bb[ch] = lds_u8(q + el_b + ec);
-                } else if (eszv == 2) {
-                    ba[ch] = ((const unsigned short *)q)[el_a + ec];
-                    bb[ch] = ((const unsigned short *)q)[el_b + ec];
-                } else {
-                    ba[ch] = ((const unsigned *)q)[el_a + ec];
-                    bb[ch] = ((const unsigned *)q)[el_b + ec];
+            if (!inter) {  // uniform; planar: the offsets of a frame's channels are immediates of the unrolled body
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const unsigned char *qc = q + ((DT >= 0 || a.cin == 3) ? ch : 0) * row_bytes;
+                    if (eszv == 1) {
+                        ba[ch] = lds_u8(qc + lane);
+                        bb[ch] = lds_u8(qc + lane + 32);
+                    } else if (eszv == 2) {
+                        ba[ch] = ((const unsigned short *)qc)[lane];
+                        bb[ch] = ((const unsigned short *)qc)[lane + 32];
+                    } else {
+                        ba[ch] = ((const unsigned *)qc)[lane];
+                        bb[ch] = ((const unsigned *)qc)[lane + 32];
+                    }
+                }
+            } else {  // channel-interleaved: elements 3 lane + ch and 3 (lane + 32) + ch of the frame's 192
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    if (eszv == 1) {
+                        ba[ch] = lds_u8(q + 3 * lane + ch);
+                        bb[ch] = lds_u8(q + 3 * lane + 96 + ch);
+                    } else if (eszv == 2) {
+                        ba[ch] = ((const unsigned short *)q)[3 * lane + ch];
+                        bb[ch] = ((const unsigned short *)q)[3 * lane + 96 + ch];
+                    } else {
+                        ba[ch] = ((const unsigned *)q)[3 * lane + ch];
+                        bb[ch] = ((const unsigned *)q)[3 * lane + 96 + ch];
+                    }
                 }
             }
             float2 d0, d1, d2;
