@@ -17,6 +17,8 @@
 
 #include "cvvdp_kernels.cuh"
 
+static const size_t kFlagsBytes = (4 + CVVDP_MEAN_SLOTS) * sizeof(int);  // validation counters + first-frame partial sums
+
 using namespace cvvdp;
 
 // Band kernel configuration (B2Geom / k_band2): 48-column strips, conflict-free phase A, phase C trailing by 16 rows.
@@ -91,7 +93,7 @@ struct cvvdp_b200_ctx {
     cudaEvent_t dev_done = nullptr;   // end of the last process_device / pool_device on the caller's stream
     bool dev_pending = false;
     cudaEvent_t hm_ready = nullptr, hm_copied = nullptr;
-    int *flags_dev = nullptr;     // [0..2] input validation counters, [3] clip frame 0 seen; then one float: DKL-A sum of test frame 0
+    int *flags_dev = nullptr;     // [0..2] input validation counters; then CVVDP_MEAN_SLOTS floats: partial DKL-A sums of test frame 0
     long long launches = 0;
     bool prof = false;
     struct ProfRec {
@@ -534,7 +536,8 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
             for (int k = 0; k < info.filter_len / 2; ++k)
                 if (ta.taps[c][k] != ta.taps[c][info.filter_len - 1 - k]) taps_symmetric = false;
         static const bool force_generic = getenv("CVVDP_B200_GENERIC_TEMPORAL") != nullptr;  // test hook: exercise the fallback
-        const bool two_stage = dense && info.filter_len >= 3 && info.filter_len <= 17 && taps_symmetric && !force_generic;
+        // (one tap = images: the same staged, table-driven front end, the FIR degenerates to the centre tap)
+        const bool two_stage = dense && info.filter_len >= 1 && info.filter_len <= 17 && taps_symmetric && !force_generic;
         dim3 grid_2s((unsigned)((npix / 64 + CVVDP_T2S_THREADS / 32 - 1) / (CVVDP_T2S_THREADS / 32)), (unsigned)(B * 2));
         bool launched = false;
 #define CVVDP_TEMPORAL_CASE(FLV)                                                                  \
@@ -564,6 +567,7 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
                 CVVDP_TEMPORAL_CASE(13)
                 CVVDP_TEMPORAL_CASE(15)
 #endif
+                CVVDP_TEMPORAL_CASE(1)
                 CVVDP_TEMPORAL_CASE(9)
                 CVVDP_TEMPORAL_CASE(17)
                 default: break;
@@ -936,7 +940,7 @@ int cvvdp_b200_create(const cvvdp_b200_params *params, const cvvdp_b200_csf_lut 
         delete ctx;
         return fail(nullptr, CVVDP_ERR_NOMEM, "cannot allocate the heat-map tone buffers");
     }
-    if (cudaMalloc(&ctx->flags_dev, 32) != cudaSuccess || cudaMemset(ctx->flags_dev, 0, 32) != cudaSuccess) {
+    if (cudaMalloc(&ctx->flags_dev, kFlagsBytes) != cudaSuccess || cudaMemset(ctx->flags_dev, 0, kFlagsBytes) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, CVVDP_ERR_NOMEM, "cannot allocate the validation flags");
     }
@@ -1747,15 +1751,19 @@ int cvvdp_b200_input_stats(cvvdp_b200_ctx *ctx, cvvdp_b200_input_report *out, in
     DeviceGuard dev_guard(ctx->device);
     CU_CHECK(ctx, dev_guard.err);
     CU_CHECK(ctx, cudaDeviceSynchronize());  // the temporal kernels of every stream of this context have finished
-    int h[8];
+    int h[4 + CVVDP_MEAN_SLOTS];
     CU_CHECK(ctx, cudaMemcpy(h, ctx->flags_dev, sizeof(h), cudaMemcpyDeviceToHost));
     out->out_of_range = h[0];
     out->nan = h[1];
     out->inf = h[2];
-    float sum;
-    memcpy(&sum, &h[4], sizeof(float));
-    out->first_frame_sum = (double)sum;
-    if (reset) CU_CHECK(ctx, cudaMemset(ctx->flags_dev, 0, 32));
+    double sum = 0.0;  // the kernels spread their partial sums over the slots (one address would serialise the atomics)
+    for (int i = 0; i < CVVDP_MEAN_SLOTS; ++i) {
+        float part;
+        memcpy(&part, &h[4 + i], sizeof(float));
+        sum += (double)part;
+    }
+    out->first_frame_sum = sum;
+    if (reset) CU_CHECK(ctx, cudaMemset(ctx->flags_dev, 0, kFlagsBytes));
     return CVVDP_OK;
 }
 

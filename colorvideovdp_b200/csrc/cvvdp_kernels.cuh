@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(256) k_resize(const ResizeArgs a) {
 // (round 1 carried three more generations -- one pixel per thread with direct loads, cp.async-staged, packed
 // but fully unrolled -- all superseded by the two-stage kernel and removed; measurements in DESIGN.md.)
 // =================================================================================================
+#define CVVDP_MEAN_SLOTS 64
 struct TemporalArgs {
     ClipView clip[2];
     DisplayDev dd;
@@ -348,7 +349,7 @@ struct TemporalArgs {
     float4 *out;  // level 0: [B][n][2][H*W]
     int *flags;   // [0..2]: warps that saw out-of-range / NaN / Inf input values (null: no validation)
     int inter;    // two-stage / shared-ring kernels: 1 = channel-interleaved pixels (HWC frames: pixel stride 3, channel stride 1)
-    float *mean0; // sum over the pixels of clip frame 0 of the TEST video of its achromatic DKL channel (video_source.py:64-71)
+    float *mean0; // [CVVDP_MEAN_SLOTS] partial sums (a CTA / warp adds to slot index & (SLOTS-1)) over the pixels of clip frame 0 of the TEST video of its achromatic DKL channel (video_source.py:64-71)
     float taps[4][CVVDP_MAX_FILTER_LEN];  // taps[c][k] multiplies frame f-(fl-1)+k (= F_c flipped, l.556)
 };
 
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(CVVDP_TEMPORAL_THREADS) k_temporal(const Tempo
             if (tid == 0) {
                 float tot = 0.f;
                 for (int w = 0; w < CVVDP_TEMPORAL_THREADS / 32; ++w) tot += s_part[w];
-                atomicAdd(a.mean0, tot);
+                atomicAdd(a.mean0 + (blockIdx.x & (CVVDP_MEAN_SLOTS - 1)), tot);
             }
         }
         ring[(slot * 3 + 0) * CVVDP_TEMPORAL_THREADS + tid] = d0;
@@ -670,7 +671,6 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
         for (int g = 0; g < G; ++g) {
             const unsigned char *q = raw + g * frame_bytes;
             unsigned ba[3], bb[3];
-#pragma unroll
             if (!inter) {  // uniform; planar: the offsets of a frame's channels are immediates of the unrolled body
 #pragma unroll
                 for (int ch = 0; ch < 3; ++ch) {
@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     if (it_zero >= 0 && it_zero < NI) {  // uniform per CTA
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
-        if (lane == 0) atomicAdd(a.mean0, msum);
+        if (lane == 0) atomicAdd(a.mean0 + ((blockIdx.x * 4 + warp) & (CVVDP_MEAN_SLOTS - 1)), msum);
     }
 }
 
@@ -1073,7 +1073,7 @@ __global__ void __launch_bounds__(CVVDP_TSR_THREADS) k_temporal_sr(const __grid_
     if (it_zero >= 0 && it_zero < NI) {  // uniform per CTA
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
-        if (lane == 0) atomicAdd(a.mean0, msum);
+        if (lane == 0) atomicAdd(a.mean0 + ((blockIdx.x * 4 + warp) & (CVVDP_MEAN_SLOTS - 1)), msum);
     }
 }
 

@@ -537,6 +537,26 @@ def test_long_filters_take_the_shared_ring_kernel(fps, dtype, display, padding, 
     assert abs(float(jod) - float(jod_o)) <= gu.JOD_TOL
 
 
+@pytest.mark.parametrize("dtype", ["u8", "f32"])
+def test_image_batches_take_the_one_tap_two_stage_kernel(dtype, mock_device):
+    """Images whose planes are whole 64-pixel segments (planar BCHW and interleaved BHWC batches) use the staged,
+    table-driven front end with a one-tap FIR; other sizes the generic kernel.  All against the oracle, and the two
+    layouts bit-identical."""
+    B, H, W = 3, 24, 64
+    tst = np.concatenate([synth.make_pair_u8(150 + b, 1, H, W)[0] for b in range(B)], 0)  # [B,3,1,H,W]
+    ref = np.concatenate([synth.make_pair_u8(150 + b, 1, H, W)[1] for b in range(B)], 0)
+    if dtype == "f32":
+        tst, ref = tst.astype(np.float32) / 255, ref.astype(np.float32) / 255
+    m = cv.cvvdp(display_name="standard_fhd")
+    jod, planar = m.predict(tst[:, :, 0], ref[:, :, 0], dim_order="BCHW")
+    jod_o, want = O.predict(tst, ref, "BCFHW", 0, "standard_fhd")
+    gu.assert_q_close(planar["Q_per_ch"], want["Q_per_ch"], "image batch")
+    assert np.max(np.abs(np.asarray(jod.cpu() if hasattr(jod, "cpu") else jod, dtype=np.float64) - np.asarray(jod_o))) <= gu.JOD_TOL
+    ti, ri = np.ascontiguousarray(tst[:, :, 0].transpose(0, 2, 3, 1)), np.ascontiguousarray(ref[:, :, 0].transpose(0, 2, 3, 1))
+    _, inter = m.predict(ti, ri, dim_order="BHWC")
+    assert np.array_equal(inter["Q_per_ch"], planar["Q_per_ch"])
+
+
 @pytest.mark.parametrize("fps,dtype", [(30, "u8"), (60, "f32"), (24, "f16"), (120, "u8"), (90, "f32")])
 def test_channel_interleaved_frames_take_the_fast_temporal_kernels(fps, dtype, mock_device):
     """FHWC clips (what decoded frames stacked in numpy look like): the two-stage and shared-ring kernels read the
