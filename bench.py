@@ -248,11 +248,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Start polling (nvidia-smi needs a few hundred ms before its first line: call this before the warm-up)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -260,14 +262,32 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def begin(self):
+        self.t_begin = time.monotonic()
+
+    def end(self):
+        self.t_end = time.monotonic()
+
+    def stop(self, load_fn=None):
+        """Samples taken between begin() and end().  A timed region shorter than the polling period can miss them all:
+        then `load_fn` (the same step, untimed) keeps the GPU under the same load until two samples have arrived."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        inside = lambda: [r for (t, r) in self.rows if self.t_begin is not None and self.t_begin <= t <= (self.t_end or t)]  # noqa: E731
+        note = "timed region"
+        if len(inside()) < 2 and load_fn is not None:
+            note = "timed region + untimed repeats of the same step"
+            t_stop = time.monotonic() + 4.0
+            self.t_end = None
+            while len(inside()) < 2 and time.monotonic() < t_stop:
+                load_fn()
+            self.t_end = time.monotonic()
+        rows = inside()
         self.proc.terminate()
         sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[7]))
             except Exception:
@@ -276,7 +296,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None, "sampled_during": note}
 
 
 def start_watchdog(seconds):
@@ -527,6 +547,8 @@ def main():
     pix_per_step = n * F * H * W
     clocks = ClockSampler(local)
     metric._ctx.profile_enable(False)
+    if rank == 0:
+        clocks.start()
     # ---- device-resident arm ----
     for _ in range(args.warmup):
         step_device()
@@ -534,13 +556,18 @@ def main():
     launches0 = metric._ctx.launch_count()
     metric._ctx.profile_enable(True)
     metric._ctx.profile_read()
-    if rank == 0:
-        clocks.start()
+    clocks.begin()
     ms_dev, jod = timed(step_device, args.steps, 0)
+    clocks.end()
     prof = metric._ctx.profile_read()
     metric._ctx.profile_enable(False)
-    clk = clocks.stop() if rank == 0 else None
     launches = metric._ctx.launch_count() - launches0
+
+    def load_again():  # rank 0 only, after the timed region: no collective inside step_device
+        step_device()
+        torch.cuda.synchronize(dev)
+
+    clk = clocks.stop(load_again if world == 1 else None) if rank == 0 else None
     value = pix_per_step / 1e6 / (ms_dev / 1e3)
 
     # ---- end-to-end arm: pinned host clips through the public API ----

@@ -543,6 +543,13 @@ __device__ __forceinline__ void bits_to_dkl2(const TemporalArgs &a, const float 
 }
 
 #define CVVDP_T2S_THREADS 128
+#ifndef CVVDP_T2S_UNROLL_LUT
+#define CVVDP_T2S_UNROLL_LUT 3   // frames of the stage-1 loop in flight: table variant
+#endif
+#ifndef CVVDP_T2S_UNROLL_SPEC
+#define CVVDP_T2S_UNROLL_SPEC 2  // ... compile-time (dtype, EOTF) bodies
+#endif
+constexpr int kT2sUnrollLut = CVVDP_T2S_UNROLL_LUT, kT2sUnrollSpec = CVVDP_T2S_UNROLL_SPEC;
 template <int FL>
 struct T2SGeom {
     static constexpr int RP = FL + 1;   // ring period (even)
@@ -667,7 +674,7 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
         const int eszv = ESZ > 0 ? ESZ : esz;
         // three frames in flight for the table variant (a dozen instructions per frame), two for a specialised body; the
         // generic per-pixel EOTF is long enough to hide its own latencies and must not be replicated
-#pragma unroll(USE_LUT ? 3 : (DT >= 0 ? 2 : 1))
+#pragma unroll(USE_LUT ? kT2sUnrollLut : (DT >= 0 ? kT2sUnrollSpec : 1))
         for (int g = 0; g < G; ++g) {
             const unsigned char *q = raw + g * frame_bytes;
             unsigned ba[3], bb[3];
@@ -878,7 +885,10 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
     if (it_zero >= 0 && it_zero < NI) {  // uniform per CTA
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
-        if (lane == 0) atomicAdd(a.mean0 + ((blockIdx.x * 4 + warp) & (CVVDP_MEAN_SLOTS - 1)), msum);
+        // (the slot comes from the block index alone: keeping `warp` alive to this point tipped the register allocator of
+        // the two-stage kernel into rematerialising thread and block indices inside the frame loop -- S2R / LEA / IMAD per
+        // frame, 8.3 -> 9.8 ms for the 8-bit and 14.5 -> 18.9 ms for the fp32 4K clip; profiles/r02_ab_temporal_remat.txt)
+        if (lane == 0) atomicAdd(a.mean0 + (blockIdx.x & (CVVDP_MEAN_SLOTS - 1)), msum);
     }
 }
 
@@ -1073,7 +1083,7 @@ __global__ void __launch_bounds__(CVVDP_TSR_THREADS) k_temporal_sr(const __grid_
     if (it_zero >= 0 && it_zero < NI) {  // uniform per CTA
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
-        if (lane == 0) atomicAdd(a.mean0 + ((blockIdx.x * 4 + warp) & (CVVDP_MEAN_SLOTS - 1)), msum);
+        if (lane == 0) atomicAdd(a.mean0 + (blockIdx.x & (CVVDP_MEAN_SLOTS - 1)), msum);
     }
 }
 

@@ -101,3 +101,23 @@ def test_info_string_format():
         assert m.quality_unit() == "JOD" and m.short_name() == "cvvdp"
     finally:
         cvvdp_metric._set_mock_library_for_tests(None)
+
+
+def test_two_stage_temporal_kernel_keeps_its_indices_in_registers():
+    """Guard against a code-generation cliff seen in round 2: one more live value at the end of k_temporal_2s made ptxas
+    rematerialise thread / block indices and addresses inside the frame loop (S2R, S2UR, LEA per frame) and cost 15-30 %
+    of the kernel.  The healthy 17-tap table variant has a handful of S2R and about 3000 instructions."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cuobjdump) or not os.path.isfile(N.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    out = subprocess.run([cuobjdump, "-sass", "-fun", "_ZN5cvvdp13k_temporal_2sILi17ELi1EEEvNS_12TemporalArgsE", N.LIB_PATH],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    ops = [ln.split()[1 if not ln.split()[1].startswith("@") else 2] for ln in out.splitlines()
+           if ln.strip().startswith("/*") and len(ln.split()) > 2 and ln.split()[0].endswith("*/")]
+    if not ops:
+        pytest.skip("kernel not found in the library (development build)")
+    s2r = sum(1 for o in ops if o.startswith("S2R") or o.startswith("S2UR"))
+    assert s2r <= 16, f"{s2r} S2R/S2UR in k_temporal_2s<17, LUT>: indices are being rematerialised in the frame loop"
+    assert len(ops) <= 3200, f"k_temporal_2s<17, LUT> grew to {len(ops)} instructions"

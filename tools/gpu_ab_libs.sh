@@ -1,7 +1,7 @@
 #!/bin/bash
 # Same-box A/B of library builds under build/ab/*.so: u8 and f32 headline shape, temporal kernel and step times.
 cp colorvideovdp_b200/libcvvdp_b200.so /tmp/lib_keep.so
-for rep in 1 2; do
+for rep in 1; do
 for lib in build/ab/*.so; do
   cp $lib colorvideovdp_b200/libcvvdp_b200.so
   for dt in u8 f32; do
