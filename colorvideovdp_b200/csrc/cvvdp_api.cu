@@ -557,7 +557,14 @@ int run_block(cvvdp_b200_ctx *ctx, const cvvdp_b200_clip *test, const cvvdp_b200
         }                                                                                         \
         launched = true;                                                                          \
     } break;
-        if (two_stage) {
+        // images of 8-bit planes: the table front end alone (one frame per item in the block)
+        if (two_stage && info.filter_len == 1 && use_lut && n == 1 && npix % 4 == 0) {
+            const unsigned gx = (unsigned)std::min<long long>((npix + 1023) / 1024, (long long)ctx->num_sms * 8);
+            auto kfn = k_image_lut;
+            CVVDP_LAUNCH(kfn, dim3(gx, (unsigned)(B * 2)), dim3(256), 0, st, ta);
+            launched = true;
+        }
+        if (two_stage && !launched) {
             switch (info.filter_len) {
 #ifndef CVVDP_DEV_FAST  // development builds keep only the 30 and 60 fps specialisations
                 CVVDP_TEMPORAL_CASE(3)

@@ -893,6 +893,83 @@ __global__ void __launch_bounds__(CVVDP_T2S_THREADS, 3) k_temporal_2s(const __gr
 }
 
 // =================================================================================================
+// Images of 8-bit planes (the reference's everyday case: predict(img_test, img_ref, 'HWC'), batches of them): no time
+// axis, so the whole temporal stage is unpack -> EOTF table -> DKL -> level 0.  A thread converts four consecutive
+// pixels per step (three 32-bit loads, twelve table look-ups, four 128-bit stores); CTAs stride over the plane so that
+// the 256-entry table is built once per CTA.  Planar and channel-interleaved frames; dense, 16-byte aligned planes of
+// whole 64-pixel segments (the host checks), everything else goes to k_temporal_2s<1> / k_temporal.
+// Per pixel the arithmetic of bits_to_dkl2 and of the one-tap FIR (tap x value), so the bits match those kernels.
+// =================================================================================================
+__global__ void __launch_bounds__(256) k_image_lut(const __grid_constant__ TemporalArgs a) {
+    __shared__ float s_lut[256];
+    __shared__ float s_part[8];
+    const int tid = threadIdx.x;
+    {
+        float v[3] = {(float)tid / 255.0f, 0.f, 0.f};
+        eotf_forward_n<1>(v, a.dd);
+        s_lut[tid] = v[0];
+    }
+    __syncthreads();
+    const long long npix = (long long)a.H * a.W;
+    const int b = blockIdx.y >> 1, v = blockIdx.y & 1;
+    const ClipView &cv = a.clip[v];
+    const bool inter = a.inter != 0;
+    const unsigned char *src = (const unsigned char *)cv.data + b * cv.s[0] + (long long)frame_slot(cv, a.f0) * cv.s[2];
+    float4 *out = a.out + ((long long)b * 2 + v) * npix;
+    const float t0 = a.taps[0][0], t1 = a.taps[1][0], t2 = a.taps[2][0], t3 = a.taps[3][0];
+    float msum = 0.f;
+    for (long long p = ((long long)blockIdx.x * 256 + tid) * 4; p < npix; p += (long long)gridDim.x * 1024) {
+        unsigned w0, w1, w2;  // planar: four pixels of each channel; interleaved: the twelve bytes of four pixels
+        if (inter) {
+            const unsigned *q = reinterpret_cast<const unsigned *>(src + 3 * p);
+            w0 = __ldg(q);
+            w1 = __ldg(q + 1);
+            w2 = __ldg(q + 2);
+        } else {
+            w0 = __ldg(reinterpret_cast<const unsigned *>(src + p));
+            w1 = a.cin == 3 ? __ldg(reinterpret_cast<const unsigned *>(src + cv.s[1] + p)) : w0;
+            w2 = a.cin == 3 ? __ldg(reinterpret_cast<const unsigned *>(src + 2 * cv.s[1] + p)) : w0;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned c0, c1, c2;
+            if (inter) {  // byte 3 i + ch of the twelve
+                const unsigned long long lo = ((unsigned long long)w1 << 32) | w0;
+                c0 = i < 3 ? (unsigned)(lo >> (24 * i)) & 0xffu : (w2 >> 8) & 0xffu;
+                c1 = i < 2 ? (unsigned)(lo >> (24 * i + 8)) & 0xffu : (i == 2 ? (w1 >> 24) & 0xffu : (w2 >> 16) & 0xffu);
+                c2 = i < 2 ? (unsigned)(lo >> (24 * i + 16)) & 0xffu : (i == 2 ? w2 & 0xffu : (w2 >> 24) & 0xffu);
+            } else {
+                c0 = (w0 >> (8 * i)) & 0xffu;
+                c1 = (w1 >> (8 * i)) & 0xffu;
+                c2 = (w2 >> (8 * i)) & 0xffu;
+            }
+            const float v0 = s_lut[c0], v1 = s_lut[c1], v2 = s_lut[c2];
+            float d0, d1, d2;
+            if (a.cin == 3) {  // the operation order of bits_to_dkl2
+                d0 = fmaf(v2, a.dd.M[2], fmaf(v0, a.dd.M[0], v1 * a.dd.M[1]));
+                d1 = fmaf(v2, a.dd.M[5], fmaf(v0, a.dd.M[3], v1 * a.dd.M[4]));
+                d2 = fmaf(v2, a.dd.M[8], fmaf(v0, a.dd.M[6], v1 * a.dd.M[7]));
+            } else {
+                d0 = d1 = d2 = v0;
+            }
+            msum += d0;
+            out[p + i] = make_float4(t0 * d0, t1 * d1, t2 * d2, t3 * d0);
+        }
+    }
+    if (v == 0 && a.mean0 != nullptr && a.f0 == 0) {  // uniform per CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, o);
+        if ((tid & 31) == 0) s_part[tid >> 5] = msum;
+        __syncthreads();
+        if (tid == 0) {
+            float tot = 0.f;
+            for (int w = 0; w < 8; ++w) tot += s_part[w];
+            atomicAdd(a.mean0 + (blockIdx.x & (CVVDP_MEAN_SLOTS - 1)), tot);
+        }
+    }
+}
+
+// =================================================================================================
 // Temporal stage for long filters (19 taps and more: frame rates above 64 fps; 120 fps = 31 taps).  The register ring
 // of k_temporal_2s does not fit, so the ring lives in shared memory: [FL][3][threads] fp32x2, one slab per thread
 // (nobody else reads it: no barriers).  Same pixel ownership (lane, lane + 32 of a 64-pixel segment) and the same

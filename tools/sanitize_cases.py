@@ -42,6 +42,12 @@ m = cv.cvvdp(display_name="standard_hdr_linear", device=dev)
 out.append(float(m.predict((t(tst).float() * 2).half(), (t(ref).float() * 2).half(), frames_per_second=30)[0]))
 m = cv.cvvdp(display_name="standard_hdr_pq", device=dev)
 out.append(float(m.predict((t(tst).to(torch.int32) * 200).to(torch.int16), (t(ref).to(torch.int32) * 200).to(torch.int16), frames_per_second=30)[0]))
+# 8-bit image batches: the table front-end kernel, planar and interleaved; a gray image
+tst, ref = synth.make_pair_u8(14, 1, 64, 128)
+m = cv.cvvdp(display_name="standard_fhd", device=dev)
+out.append(float(m.predict(t(tst)[:, :, 0], t(ref)[:, :, 0], dim_order="BCHW")[0]))
+out.append(float(m.predict(t(tst)[0, :, 0].permute(1, 2, 0).contiguous(), t(ref)[0, :, 0].permute(1, 2, 0).contiguous(), dim_order="HWC")[0]))
+out.append(float(m.predict(t(tst)[0, 0, 0], t(ref)[0, 0, 0], dim_order="HW")[0]))
 # long filters (120 and 90 fps: 31 and 25 taps): shared-memory-ring temporal kernel, table and float variants
 tst, ref = synth.make_pair_u8(13, 37, 32, 128)
 m = cv.cvvdp(display_name="standard_fhd", device=dev, temp_padding="symmetric")
