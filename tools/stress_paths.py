@@ -64,9 +64,9 @@ tp, rp = np.ascontiguousarray(t[0].transpose(1, 2, 3, 0)), np.ascontiguousarray(
 _, s = m.predict(tp, rp, dim_order="FHWC", frames_per_second=60)
 jod_p = s
 _, s2 = m.predict(torch.from_numpy(tp).to(dev), torch.from_numpy(rp).to(dev), dim_order="FHWC", frames_per_second=60)
-check("1080p x 400 @60: FHWC numpy vs FHWC device (generic temporal kernel)", s2, jod_p)
+check("1080p x 400 @60: FHWC numpy vs FHWC device", s2, jod_p)
 d = np.abs(s2["Q_per_ch"].astype(np.float64) - base["Q_per_ch"]) / (1e-3 * np.abs(base["Q_per_ch"]) + 1e-5)
-print(f"     FHWC (generic kernel) vs BCFHW (two-stage kernel): max err/gate {d.max():.4f}")
+print(f"     FHWC (interleaved stage) vs BCFHW (planar stage), both the two-stage kernel: max err/gate {d.max():.4f}")
 if d.max() > 1:
     bad.append(("FHWC vs BCFHW", float(d.max())))
 del t, r, tp, rp
