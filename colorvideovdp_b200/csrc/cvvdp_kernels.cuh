@@ -330,11 +330,14 @@ __global__ void __launch_bounds__(256) k_resize(const ResizeArgs a) {
 // =================================================================================================
 // Temporal stage: front end fused with the causal FIR  (cvvdp_metric.py:453-561)
 // Every input frame is read and EOTF-ed exactly once per block (+ fl-1 history frames at the start of
-// the block).  Two kernels; the host picks (cvvdp_api.cu, run_block):
-//   k_temporal_2s  two pixels per thread (fp32x2), rolled front end + unrolled symmetric FIR: dense,
-//                  16-byte aligned planes of whole 64-pixel segments, 3..17 symmetric taps (8..64 fps)  [default]
-//   k_temporal     generic shared-memory ring: any layout (strided / permuted views, planar YUV), any
-//                  filter length, images
+// the block).  Four kernels; the host picks (cvvdp_api.cu, run_block):
+//   k_temporal_2s  two pixels per thread (fp32x2), rolled front end + unrolled symmetric FIR with the ring in
+//                  registers: dense, 16-byte aligned planes of whole 64-pixel segments (planar, channel-interleaved
+//                  or planar YUV), 1..17 symmetric taps (images, 8..64 fps)                                   [default]
+//   k_temporal_sr  the same ownership with the ring in shared memory: 19..73 taps (frame rates above 64 fps)
+//   k_image_lut    images of 8-bit planes: the table front end alone
+//   k_temporal     generic shared-memory ring, one pixel per thread: any layout (strided / permuted views, planar YUV
+//                  of other widths), any filter
 // (round 1 carried three more generations -- one pixel per thread with direct loads, cp.async-staged, packed
 // but fully unrolled -- all superseded by the two-stage kernel and removed; measurements in DESIGN.md.)
 // =================================================================================================
